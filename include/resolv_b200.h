@@ -1,0 +1,203 @@
+/* resolv_b200.h — C ABI of libresolv_b200.so, the B200-native replacement for resolv's collision hot path.
+ *
+ * The reference (SolarLune/resolv v0.8.0, pure Go) has no FFI seam; the drop-in is a Go package with the same
+ * import path and exported API whose Space / ShapeBase methods call these entry points through cgo
+ * (INTEGRATION.md shows the binding). Each entry point cites the reference code it replaces (file:line relative
+ * to the reference tree).
+ *
+ * Conventions
+ *  - Every function returns int32_t: RSV_OK (0) or a negative RSV_ERR_* code. No exceptions, no abort, no
+ *    callbacks into the host language. rsv_last_error() returns a human-readable message for the last failure.
+ *  - All device memory and all pinned host staging / result buffers are owned by the library and freed by
+ *    rsv_destroy(). The library never retains a caller pointer after a call returns (cgo pointer rules).
+ *  - One CUDA stream per rsv_space. Calls on one space must be serialised by the caller; different spaces may
+ *    be driven from different threads. Every call selects the space's device itself.
+ *  - There is NO CPU fallback: rsv_create fails with RSV_ERR_NO_DEVICE when no CUDA device is usable.
+ *  - Shapes are addressed by slot index i in [0, n_shapes); the host layer maps resolv shape IDs to slots.
+ */
+#ifndef RESOLV_B200_H
+#define RESOLV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSV_ABI_VERSION 1
+
+#define RSV_OK 0
+#define RSV_ERR_BAD_ARG (-1)
+#define RSV_ERR_OOM (-2)
+#define RSV_ERR_CUDA (-3)
+#define RSV_ERR_CAPACITY (-4) /* an output buffer overflowed; counts hold the required sizes: rsv_reserve + retry */
+#define RSV_ERR_NO_DEVICE (-5)
+
+typedef struct rsv_space rsv_space;
+
+/* Replaces NewSpace(spaceWidth, spaceHeight, cellWidth, cellHeight) (space.go:16-30) and Space.Resize
+ * (space.go:113-131): grid = ceil(space_w/cell_w) x ceil(space_h/cell_h) cells. n_spaces > 1 creates a batch
+ * of independent, identically-sized Spaces in one device grid (RL-style env batches; shape i belongs to space
+ * space_idx[i]). row_lo/row_hi select the strip of cell rows [row_lo,row_hi) held by this device for
+ * multi-GPU strip partitioning (0,0 = the whole grid): cells outside the strip behave as if they held no
+ * shapes, exactly like out-of-grid cells (space.go:135-142). */
+typedef struct rsv_config {
+    int32_t space_w, space_h;
+    int32_t cell_w, cell_h;
+    uint32_t n_spaces;
+    uint32_t max_shapes;   /* capacity N (shape slots) */
+    uint32_t max_verts;    /* capacity of the shared polygon vertex pool (sum of vertex counts) */
+    uint32_t max_entries;  /* capacity R of (cell, shape) registrations; 0 = auto */
+    uint32_t max_pairs;    /* capacity of the AABB-gated pair / hit-header buffer; 0 = auto */
+    uint32_t max_contacts; /* capacity of the contact buffer; 0 = auto */
+    uint32_t max_rays;     /* capacity of one rsv_linetest batch; 0 = auto */
+    int32_t device;        /* CUDA device ordinal */
+    int32_t row_lo, row_hi;
+    uint32_t flags;        /* reserved, 0 */
+} rsv_config;
+
+/* Host-visible SoA staging buffers (library-owned pinned memory the host writes directly, then rsv_commit()s).
+ * This is the device-resident restatement of ShapeBase / Circle / ConvexPolygon state (shape.go:54-62,
+ * circle.go:4-7, convexPolygon.go:12-20). */
+enum {
+    RSV_BUF_POS = 0,        /* f64[2N]  ShapeBase.position */
+    RSV_BUF_LOCAL_AABB = 1, /* f64[4N]  polygon: ConvexPolygon.bounds as cached by updateBounds (convexPolygon.go:163-197,
+                                        minX,minY,maxX,maxY, position NOT applied); circle: (-r,-r,+r,+r) (circle.go:33-39) */
+    RSV_BUF_RADIUS = 2,     /* f64[N]   Circle.radius (0 for polygons) */
+    RSV_BUF_TAGS = 3,       /* u64[N]   *ShapeBase.tags (tags.go:8) */
+    RSV_BUF_META = 4,       /* u32[N]   RSV_META_* bits | vertex count << 8 */
+    RSV_BUF_VERT_OFF = 5,   /* u32[N]   first vertex of polygon i in RSV_BUF_VERTS */
+    RSV_BUF_VERTS = 6,      /* f64[2*max_verts] polygon points with scale and rotation applied and position NOT applied:
+                                        the value of p in ConvexPolygon.Transformed before "+ position" (convexPolygon.go:146-151) */
+    RSV_BUF_QMASK = 7,      /* u64[2N]  per tester: (ByTags mask, OR of NotByTags masks) (shapefilter.go:47-61) */
+    RSV_BUF_SPACE_IDX = 8,  /* u32[N]   which Space of the batch the shape was Add()ed to (0 when n_spaces == 1) */
+    RSV_BUF_COUNT = 9
+};
+
+#define RSV_META_POLYGON 0x1u  /* 0 = Circle, 1 = ConvexPolygon */
+#define RSV_META_CLOSED 0x2u   /* ConvexPolygon.Closed (convexPolygon.go:18) */
+#define RSV_META_TESTER 0x4u   /* this shape runs IntersectionTest in rsv_frame */
+#define RSV_META_USE_ANY 0x8u  /* tester's filter chain contains ByTags(qmask[2i]) */
+#define RSV_META_ABSENT 0x10u  /* slot is free / shape was Space.Remove()d (space.go:50-66): in no cell, never a tester */
+#define RSV_META_NV_SHIFT 8
+#define RSV_MAX_POLY_VERTS 255
+
+/* Per-frame counters (the SURVEY's N, R, P, H, K) and overflow information. */
+typedef struct rsv_counts {
+    uint64_t n_shapes;      /* N */
+    uint64_t n_testers;
+    uint64_t n_entries;     /* R: (cell, shape) registrations == sum of len(cell.Shapes) */
+    uint64_t n_candidates;  /* P: ordered (tester, other) pairs after dedupe + tag filters == pair tests */
+    uint64_t n_gated;       /* ordered pairs that pass the Bounds gate (utils.go:146-173) */
+    uint64_t n_hits;        /* H: ordered pairs with a non-empty IntersectionSet */
+    uint64_t n_contacts;    /* K */
+    uint32_t overflow;      /* RSV_OVF_* bits */
+    uint32_t reserved;
+} rsv_counts;
+
+#define RSV_OVF_ENTRIES 0x1u
+#define RSV_OVF_PAIRS 0x2u
+#define RSV_OVF_CONTACTS 0x4u
+
+/* One record per AABB-gated ordered pair, grouped by tester (all records of one tester are contiguous and in the
+ * reference's candidate generation order: row-major cell walk, in-cell order, first occurrence; cell.go:86-121).
+ * n_contacts == 0 means the IntersectionSet was empty (no callback). Replaces IntersectionSet (contactSet.go:15-20)
+ * for shape-shape tests (Center is zero there). */
+typedef struct rsv_hit {
+    uint32_t a;             /* tester slot */
+    uint32_t b;             /* IntersectionSet.OtherShape slot */
+    uint32_t first_contact; /* index into the contact buffer */
+    uint32_t count_rank;    /* n_contacts in bits 0..7, candidate generation rank in bits 8..31 (tie-break for the
+                               distance sort of shape.go:291-293) */
+    double mtv_x, mtv_y;    /* IntersectionSet.MTV */
+} rsv_hit;
+
+/* Replaces Intersection (contactSet.go:8-11). */
+typedef struct rsv_contact {
+    double px, py; /* Point */
+    double nx, ny; /* Normal */
+} rsv_contact;
+
+/* Borrowed views of the pinned result mirrors, valid until the next rsv_frame / rsv_linetest on the space. */
+typedef struct rsv_results {
+    const rsv_hit* hits;
+    uint64_t n_hit_records; /* == counts.n_gated (dense by gated pair; filter n_contacts > 0) */
+    const rsv_contact* contacts;
+    uint64_t n_contacts;
+} rsv_results;
+
+#define RSV_FRAME_DOWNLOAD 0x1u        /* copy hits + contacts to the pinned mirrors (rsv_results) */
+#define RSV_FRAME_ALL_CANDIDATES 0x2u  /* parity/debug: emit a record for EVERY candidate pair, not only gated ones;
+                                          records failing the Bounds gate carry RSV_HIT_NOT_GATED in count_rank bit 7 */
+#define RSV_FRAME_TIMING 0x4u          /* record per-kernel CUDA events; read with rsv_timing */
+#define RSV_HIT_NOT_GATED 0x80u
+
+/* Per-kernel device times of the last RSV_FRAME_TIMING frame, microseconds, CUDA events on the space's stream. */
+enum {
+    RSV_K_CLEAR = 0, RSV_K_BOUNDS = 1, RSV_K_SCAN = 2, RSV_K_SCATTER = 3, RSV_K_CELLSORT = 4,
+    RSV_K_PAIRS = 5, RSV_K_NARROW = 6, RSV_K_COUNT = 7
+};
+typedef struct rsv_timing_info {
+    float kernel_us[8];
+    float frame_us; /* first kernel start to last kernel end */
+} rsv_timing_info;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------- */
+int32_t rsv_abi_version(void);
+int32_t rsv_device_count(void);
+/* NewSpace (space.go:16-30). */
+int32_t rsv_create(const rsv_config* cfg, rsv_space** out);
+int32_t rsv_destroy(rsv_space* s);
+const char* rsv_last_error(const rsv_space* s); /* s may be NULL: error of the last failed rsv_create on this thread */
+/* Grid dimensions in cells: Space.WidthInCells / HeightInCells (space.go:160-171). */
+int32_t rsv_grid_dims(const rsv_space* s, int32_t* w_cells, int32_t* h_cells);
+/* Grow output capacities after RSV_ERR_CAPACITY (0 = keep). */
+int32_t rsv_reserve(rsv_space* s, uint32_t max_entries, uint32_t max_pairs, uint32_t max_contacts);
+
+/* ---- shape state ---------------------------------------------------------------------------------------- */
+/* Pinned staging buffer `which` (RSV_BUF_*); *bytes receives its size. */
+void* rsv_staging(rsv_space* s, int32_t which, size_t* bytes);
+/* Number of live slots / vertices (Space.Add / Remove bookkeeping, space.go:33-66, stays on the host). */
+int32_t rsv_set_counts(rsv_space* s, uint32_t n_shapes, uint32_t n_verts);
+/* Upload slots [lo,hi) of every buffer in `which_mask` (bit RSV_BUF_x); RSV_BUF_VERTS uploads the whole live
+ * vertex pool. Replaces the write side of ShapeBase.update (shape.go:239-242): the host only marks dirty ranges. */
+int32_t rsv_commit(rsv_space* s, uint32_t which_mask, uint32_t lo, uint32_t hi);
+/* Device address of buffer `which` (for device-side producers such as the multi-GPU halo unpack). */
+void* rsv_device_buffer(rsv_space* s, int32_t which);
+
+/* ---- the frame ------------------------------------------------------------------------------------------ */
+/* Bulk restatement of, for every tester A (RSV_META_TESTER):
+ *   A.IntersectionTest(IntersectionTestSettings{TestAgainst: A.SelectTouchingCells(margin).FilterShapes()
+ *       [.ByTags(any)][.NotByTags(none)], OnIntersect: <record>})                  (shape.go:220-237, 273-316)
+ * against the frozen world: grid rebuild (shape.go:183-214, cell.go:19-38) -> candidate pairs (cell.go:86-121,
+ * shapefilter.go:26-61) -> Bounds gate + SAT narrowphase (shape.go:318-479, convexPolygon.go:418-514,715-789).
+ * OnIntersect is replayed by the host from rsv_results. */
+int32_t rsv_frame(rsv_space* s, int32_t margin, uint32_t flags, rsv_counts* out);
+/* The same frame split in two so that a host can queue work without blocking: rsv_frame_launch enqueues every
+ * kernel on the space's stream and returns; rsv_frame_finish waits, fills the counters and (RSV_FRAME_DOWNLOAD)
+ * the result mirrors. rsv_frame == launch + finish. */
+int32_t rsv_frame_launch(rsv_space* s, int32_t margin, uint32_t flags);
+int32_t rsv_frame_finish(rsv_space* s, rsv_counts* out);
+int32_t rsv_results_view(rsv_space* s, rsv_results* out);
+int32_t rsv_timing(rsv_space* s, rsv_timing_info* out);
+/* Block until all work queued on the space's stream is done. */
+int32_t rsv_sync(rsv_space* s);
+/* CUDA-event stopwatch on the space's stream (the stream every kernel of this space is launched on):
+ * rsv_timer_start records an event; rsv_timer_stop records a second one, waits for it and returns the elapsed
+ * device time in milliseconds. */
+int32_t rsv_timer_start(rsv_space* s);
+int32_t rsv_timer_stop(rsv_space* s, float* ms);
+
+/* ---- parity / debug dumps --------------------------------------------------------------------------------- */
+/* Cell membership after the last frame: cell_end[c] (exclusive end offset of cell c in `entries`, cells row-major,
+ * spaces concatenated; start = cell_end[c-1] or 0) and the shape slots per cell in ascending slot order. Either
+ * pointer may be NULL. Mirrors Cell.Shapes (cell.go:4-7). */
+int32_t rsv_debug_cells(rsv_space* s, uint32_t* cell_end, uint64_t n_cells, uint32_t* entries, uint64_t cap_entries);
+/* Per-shape inclusive cell rect (cx,cy,ex,ey) = Bounds.toCellSpace (utils.go:90-98) after the last frame. */
+int32_t rsv_debug_cell_rects(rsv_space* s, int32_t* rects4, uint64_t n_shapes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RESOLV_B200_H */

@@ -59,6 +59,8 @@ def lib():
     L.orc_add_rectangle_top_left.argtypes = [vp, f64, f64, f64, f64, u64]
     L.orc_add_line.restype = i32
     L.orc_add_line.argtypes = [vp, f64, f64, f64, f64, u64]
+    L.orc_add_bulk.argtypes = [vp, i32, P(C.c_uint8), P(f64), P(f64), P(f64), P(C.c_uint32), P(C.c_uint32), P(f64),
+                               P(C.c_uint8), P(u64)]
     L.orc_set_position.argtypes = [vp, i32, f64, f64]
     L.orc_move.argtypes = [vp, i32, f64, f64]
     L.orc_set_tags.argtypes = [vp, i32, u64]
@@ -144,6 +146,18 @@ class OracleSpace:
 
     def add_line(self, x1, y1, x2, y2, tags=0):
         return self.L.orc_add_line(self.h, x1, y1, x2, y2, tags)
+
+    def add_bulk(self, kind, pos0, pos, radius, vert_off, nv, verts, closed, tags):
+        """Adds len(kind) shapes in index order (see orc_add_bulk)."""
+        c = np.ascontiguousarray
+        kind, closed = c(kind, dtype=np.uint8), c(closed, dtype=np.uint8)
+        pos0, pos, radius, verts = (c(a, dtype=np.float64) for a in (pos0, pos, radius, verts))
+        vert_off, nv, tags = c(vert_off, dtype=np.uint32), c(nv, dtype=np.uint32), c(tags, dtype=np.uint64)
+        if verts.size == 0:
+            verts = np.zeros(2)
+        self.L.orc_add_bulk(self.h, len(kind), _ptr(kind, C.c_uint8), _ptr(pos0, C.c_double), _ptr(pos, C.c_double),
+                            _ptr(radius, C.c_double), _ptr(vert_off, C.c_uint32), _ptr(nv, C.c_uint32),
+                            _ptr(verts, C.c_double), _ptr(closed, C.c_uint8), _ptr(tags, C.c_uint64))
 
     def set_position(self, i, x, y):
         self.L.orc_set_position(self.h, i, x, y)

@@ -880,6 +880,28 @@ int orc_add_line(void* p, double x1, double y1, double x2, double y2, uint64_t t
     return orc_add_polygon(p, cx, cy, pts, 2, 1, tags);
 }
 
+// Bulk construction for generated worlds. Polygon i is built at pos0 (NewConvexPolygon -> AddPoints ->
+// updateBounds, convexPolygon.go:28-46,92-107), moved to pos while still outside any Space (like
+// NewRectangleFromTopLeft's Move, convexPolygon.go:638-643), then Space.Add()ed (space.go:33-46).
+void orc_add_bulk(void* p, int n, const uint8_t* kind, const double* pos0, const double* pos, const double* radius,
+                  const uint32_t* vert_off, const uint32_t* nv, const double* verts, const uint8_t* closed,
+                  const uint64_t* tags) {
+    OrcWorld* w = (OrcWorld*)p;
+    for (int i = 0; i < n; i++) {
+        Shape* s = new Shape;
+        s->tags = tags ? tags[i] : 0;
+        if (kind[i] == 0) {
+            s->kind = kCircle; s->pos = Vec{pos[2 * i], pos[2 * i + 1]}; s->radius = radius[i];
+        } else {
+            s->kind = kPolygon; s->pos = Vec{pos0[2 * i], pos0[2 * i + 1]}; s->closed = closed[i] != 0;
+            for (uint32_t k = 0; k < nv[i]; k++) s->points.push_back(Vec{verts[2 * (vert_off[i] + k)], verts[2 * (vert_off[i] + k) + 1]});
+            s->update_bounds();
+            s->pos = Vec{pos[2 * i], pos[2 * i + 1]};
+        }
+        add_shape(w, s);
+    }
+}
+
 void orc_set_position(void* p, int i, double x, double y) { ((OrcWorld*)p)->all[i]->set_position(x, y); }
 void orc_move(void* p, int i, double dx, double dy) { ((OrcWorld*)p)->all[i]->move(dx, dy); }
 void orc_set_tags(void* p, int i, uint64_t t) { ((OrcWorld*)p)->all[i]->tags = t; }

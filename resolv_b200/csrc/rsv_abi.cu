@@ -1,0 +1,489 @@
+// rsv_abi.cu — the C ABI of libresolv_b200.so (include/resolv_b200.h): memory ownership, staging, frame
+// orchestration on one CUDA stream per space, result mirrors, timing and parity dumps.
+//
+// Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false
+//             -Xcompiler -fPIC -shared rsv_abi.cu -o libresolv_b200.so
+// -fmad=false is part of the numerical contract (Go/amd64 does not fuse multiply-add), see rsv_math.cuh.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/resolv_b200.h"
+#include "rsv_device.cuh"
+#include "rsv_grid.cuh"
+#include "rsv_lines.cuh"
+#include "rsv_narrow.cuh"
+#include "rsv_pairs.cuh"
+
+using namespace rsv;
+
+static thread_local std::string g_create_error;
+
+struct rsv_space {
+    rsv_config cfg{};
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    DevView d{};
+    // device allocations behind the const views
+    void* dev_buf[RSV_BUF_COUNT] = {};
+    void* host_buf[RSV_BUF_COUNT] = {};
+    size_t buf_bytes[RSV_BUF_COUNT] = {};
+    size_t elem_bytes[RSV_BUF_COUNT] = {};
+    uint32_t n_shapes = 0, n_verts = 0;
+    uint32_t n_tiles = 0;
+    // pinned mirrors
+    Counters* h_ctr = nullptr;
+    rsv_hit* h_hits = nullptr;
+    rsv_contact* h_contacts = nullptr;
+    uint32_t h_cap_pairs = 0, h_cap_contacts = 0;
+    // frame state
+    uint32_t launched_flags = 0;
+    bool frame_pending = false;
+    rsv_counts last_counts{};
+    uint64_t last_records = 0, last_contacts = 0;
+    cudaEvent_t ev[RSV_K_COUNT + 1] = {};
+    cudaEvent_t ev_timer[2] = {};
+    rsv_timing_info timing{};
+    int narrow_blocks = 148 * 4;
+    // line tests
+    LineState lines{};
+    std::string error;
+};
+
+static int32_t fail(rsv_space* s, int32_t code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (s) s->error = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define CU(s, call)                                                                                   \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess)                                                                       \
+            return fail((s), e__ == cudaErrorMemoryAllocation ? RSV_ERR_OOM : RSV_ERR_CUDA, "%s: %s", #call, \
+                        cudaGetErrorString(e__));                                                     \
+    } while (0)
+
+static size_t buf_elem_bytes(int which) {
+    switch (which) {
+        case RSV_BUF_POS: return 16;
+        case RSV_BUF_LOCAL_AABB: return 32;
+        case RSV_BUF_RADIUS: return 8;
+        case RSV_BUF_TAGS: return 8;
+        case RSV_BUF_META: return 4;
+        case RSV_BUF_VERT_OFF: return 4;
+        case RSV_BUF_VERTS: return 16;
+        case RSV_BUF_QMASK: return 16;
+        case RSV_BUF_SPACE_IDX: return 4;
+    }
+    return 0;
+}
+
+static void bind_views(rsv_space* s) {
+    DevView& d = s->d;
+    d.pos = (const double2*)s->dev_buf[RSV_BUF_POS];
+    d.laabb = (const Box*)s->dev_buf[RSV_BUF_LOCAL_AABB];
+    d.radius = (const double*)s->dev_buf[RSV_BUF_RADIUS];
+    d.tags = (const unsigned long long*)s->dev_buf[RSV_BUF_TAGS];
+    d.meta = (const uint32_t*)s->dev_buf[RSV_BUF_META];
+    d.vert_off = (const uint32_t*)s->dev_buf[RSV_BUF_VERT_OFF];
+    d.verts = (const double2*)s->dev_buf[RSV_BUF_VERTS];
+    d.qmask = (const ulonglong2*)s->dev_buf[RSV_BUF_QMASK];
+    d.space_idx = (const uint32_t*)s->dev_buf[RSV_BUF_SPACE_IDX];
+}
+
+extern "C" {
+
+int32_t rsv_abi_version(void) { return RSV_ABI_VERSION; }
+
+int32_t rsv_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* rsv_last_error(const rsv_space* s) { return s ? s->error.c_str() : g_create_error.c_str(); }
+
+static int32_t alloc_outputs(rsv_space* s, uint32_t cap_entries, uint32_t cap_pairs, uint32_t cap_contacts) {
+    DevView& d = s->d;
+    if (cap_entries > d.cap_entries) {
+        if (d.entries) cudaFree(d.entries);
+        d.entries = nullptr; d.cap_entries = 0;
+        CU(s, cudaMalloc(&d.entries, (size_t)cap_entries * 4));
+        d.cap_entries = cap_entries;
+    }
+    if (cap_pairs > d.cap_pairs) {
+        if (d.hits) cudaFree(d.hits);
+        d.hits = nullptr; d.cap_pairs = 0;
+        CU(s, cudaMalloc(&d.hits, (size_t)cap_pairs * sizeof(rsv_hit)));
+        d.cap_pairs = cap_pairs;
+    }
+    if (cap_contacts > d.cap_contacts) {
+        if (d.contacts) cudaFree(d.contacts);
+        d.contacts = nullptr; d.cap_contacts = 0;
+        CU(s, cudaMalloc(&d.contacts, (size_t)cap_contacts * sizeof(rsv_contact)));
+        d.cap_contacts = cap_contacts;
+    }
+    return RSV_OK;
+}
+
+int32_t rsv_create(const rsv_config* cfg, rsv_space** out) {
+    if (!cfg || !out) return fail(nullptr, RSV_ERR_BAD_ARG, "rsv_create: null argument");
+    *out = nullptr;
+    if (cfg->space_w <= 0 || cfg->space_h <= 0 || cfg->cell_w <= 0 || cfg->cell_h <= 0)
+        return fail(nullptr, RSV_ERR_BAD_ARG, "rsv_create: space and cell sizes must be positive");
+    if (cfg->max_shapes == 0 || cfg->max_shapes >= (1u << 29))
+        return fail(nullptr, RSV_ERR_BAD_ARG, "rsv_create: max_shapes must be in [1, 2^29)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, RSV_ERR_NO_DEVICE, "rsv_create: no CUDA device (there is no CPU fallback)");
+    }
+    if (cfg->device < 0 || cfg->device >= ndev)
+        return fail(nullptr, RSV_ERR_BAD_ARG, "rsv_create: device %d out of range (have %d)", cfg->device, ndev);
+    rsv_space* s = new (std::nothrow) rsv_space;
+    if (!s) return fail(nullptr, RSV_ERR_OOM, "rsv_create: out of host memory");
+    s->cfg = *cfg;
+    s->device = cfg->device;
+    // Grid dimensions: NewSpace -> Resize(ceil(w/cw), ceil(h/ch)) (space.go:23)
+    int W = (int)std::ceil((double)cfg->space_w / (double)cfg->cell_w);
+    int H = (int)std::ceil((double)cfg->space_h / (double)cfg->cell_h);
+    int row_lo = 0, row_hi = H;
+    if (!(cfg->row_lo == 0 && cfg->row_hi == 0)) {
+        row_lo = cfg->row_lo; row_hi = cfg->row_hi;
+        if (row_lo < 0 || row_hi > H || row_lo >= row_hi) {
+            delete s;
+            return fail(nullptr, RSV_ERR_BAD_ARG, "rsv_create: strip [%d,%d) not inside [0,%d)", row_lo, row_hi, H);
+        }
+    }
+    uint32_t n_spaces = cfg->n_spaces ? cfg->n_spaces : 1;
+    unsigned long long cps = (unsigned long long)W * (unsigned long long)(row_hi - row_lo);
+    unsigned long long n_cells = cps * n_spaces;
+    if (n_cells + 1 >= (1ull << 32)) {
+        delete s;
+        return fail(nullptr, RSV_ERR_BAD_ARG, "rsv_create: %llu cells exceed the 32-bit cell index", n_cells);
+    }
+    DevView& d = s->d;
+    d.W = W; d.H = H; d.row_lo = row_lo; d.row_hi = row_hi;
+    d.cell_w = (double)cfg->cell_w; d.cell_h = (double)cfg->cell_h;
+    d.cells_per_space = (uint32_t)cps; d.n_cells = (uint32_t)n_cells; d.n_spaces = n_spaces;
+    d.n_shapes = 0;
+
+    auto bail = [&](int32_t code) {
+        std::string msg = s->error;
+        rsv_destroy(s);
+        g_create_error = msg;
+        return code;
+    };
+#define CUC(call)                                                                                                  \
+    do {                                                                                                           \
+        cudaError_t e__ = (call);                                                                                  \
+        if (e__ != cudaSuccess) {                                                                                  \
+            fail(s, e__ == cudaErrorMemoryAllocation ? RSV_ERR_OOM : RSV_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+            return bail(e__ == cudaErrorMemoryAllocation ? RSV_ERR_OOM : RSV_ERR_CUDA);                            \
+        }                                                                                                          \
+    } while (0)
+
+    CUC(cudaSetDevice(s->device));
+    cudaDeviceProp prop;
+    CUC(cudaGetDeviceProperties(&prop, s->device));
+    s->sm_count = prop.multiProcessorCount;
+    CUC(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    const uint32_t N = cfg->max_shapes;
+    const uint32_t NV = cfg->max_verts ? cfg->max_verts : 1;
+    for (int b = 0; b < RSV_BUF_COUNT; b++) {
+        s->elem_bytes[b] = buf_elem_bytes(b);
+        size_t n = (b == RSV_BUF_VERTS) ? NV : N;
+        s->buf_bytes[b] = n * s->elem_bytes[b];
+        CUC(cudaMalloc(&s->dev_buf[b], s->buf_bytes[b]));
+        CUC(cudaMemsetAsync(s->dev_buf[b], 0, s->buf_bytes[b], s->stream));
+        CUC(cudaHostAlloc(&s->host_buf[b], s->buf_bytes[b], cudaHostAllocDefault));
+        memset(s->host_buf[b], 0, s->buf_bytes[b]);
+    }
+    bind_views(s);
+    CUC(cudaMalloc(&d.aabb, (size_t)N * sizeof(Box)));
+    CUC(cudaMalloc(&d.crect, (size_t)N * sizeof(int4)));
+    s->n_tiles = (uint32_t)((n_cells + 1 + kScanTile - 1) / kScanTile);
+    CUC(cudaMalloc(&d.cell, ((size_t)s->n_tiles * kScanTile) * 4));
+    CUC(cudaMemsetAsync(d.cell, 0, ((size_t)s->n_tiles * kScanTile) * 4, s->stream));
+    CUC(cudaMalloc(&d.tile_state, (size_t)s->n_tiles * 8));
+    CUC(cudaMalloc(&d.tester_start, (size_t)N * 4));
+    CUC(cudaMalloc(&d.tester_count, (size_t)N * 4));
+    CUC(cudaMalloc(&d.ctr, sizeof(Counters)));
+    CUC(cudaHostAlloc(&s->h_ctr, sizeof(Counters), cudaHostAllocDefault));
+    uint32_t ce = cfg->max_entries ? cfg->max_entries : (uint32_t)std::min<unsigned long long>(4ull * N + 4096, 0xfffffff0ull);
+    uint32_t cp = cfg->max_pairs ? cfg->max_pairs : (uint32_t)std::min<unsigned long long>(2ull * N + 4096, 0xfffffff0ull);
+    uint32_t cc = cfg->max_contacts ? cfg->max_contacts : (uint32_t)std::min<unsigned long long>(2ull * N + 4096, 0xfffffff0ull);
+    if (alloc_outputs(s, ce, cp, cc) != RSV_OK) return bail(RSV_ERR_OOM);
+    for (auto& e : s->ev) CUC(cudaEventCreate(&e));
+    for (auto& e : s->ev_timer) CUC(cudaEventCreate(&e));
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_narrow, kNarrowBlock, 0) == cudaSuccess && occ > 0)
+        s->narrow_blocks = s->sm_count * occ;
+    CUC(cudaStreamSynchronize(s->stream));
+#undef CUC
+    *out = s;
+    return RSV_OK;
+}
+
+int32_t rsv_destroy(rsv_space* s) {
+    if (!s) return RSV_OK;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    for (int b = 0; b < RSV_BUF_COUNT; b++) {
+        if (s->dev_buf[b]) cudaFree(s->dev_buf[b]);
+        if (s->host_buf[b]) cudaFreeHost(s->host_buf[b]);
+    }
+    DevView& d = s->d;
+    void* dev[] = {d.aabb, d.crect, d.cell, d.entries, d.tile_state, d.tester_start, d.tester_count, d.hits, d.contacts, d.ctr};
+    for (void* p : dev) if (p) cudaFree(p);
+    if (s->h_ctr) cudaFreeHost(s->h_ctr);
+    if (s->h_hits) cudaFreeHost(s->h_hits);
+    if (s->h_contacts) cudaFreeHost(s->h_contacts);
+    lines_free(s->lines);
+    for (auto& e : s->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : s->ev_timer) if (e) cudaEventDestroy(e);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    cudaGetLastError();
+    delete s;
+    return RSV_OK;
+}
+
+int32_t rsv_grid_dims(const rsv_space* s, int32_t* w, int32_t* h) {
+    if (!s) return RSV_ERR_BAD_ARG;
+    if (w) *w = s->d.W;
+    if (h) *h = s->d.H;
+    return RSV_OK;
+}
+
+int32_t rsv_reserve(rsv_space* s, uint32_t max_entries, uint32_t max_pairs, uint32_t max_contacts) {
+    if (!s) return RSV_ERR_BAD_ARG;
+    CU(s, cudaSetDevice(s->device));
+    CU(s, cudaStreamSynchronize(s->stream));
+    return alloc_outputs(s, max_entries, max_pairs, max_contacts);
+}
+
+void* rsv_staging(rsv_space* s, int32_t which, size_t* bytes) {
+    if (!s || which < 0 || which >= RSV_BUF_COUNT) return nullptr;
+    if (bytes) *bytes = s->buf_bytes[which];
+    return s->host_buf[which];
+}
+
+void* rsv_device_buffer(rsv_space* s, int32_t which) {
+    if (!s || which < 0 || which >= RSV_BUF_COUNT) return nullptr;
+    return s->dev_buf[which];
+}
+
+int32_t rsv_set_counts(rsv_space* s, uint32_t n_shapes, uint32_t n_verts) {
+    if (!s) return RSV_ERR_BAD_ARG;
+    if (n_shapes > s->cfg.max_shapes) return fail(s, RSV_ERR_BAD_ARG, "rsv_set_counts: %u shapes > capacity %u", n_shapes, s->cfg.max_shapes);
+    if (n_verts > (s->cfg.max_verts ? s->cfg.max_verts : 1)) return fail(s, RSV_ERR_BAD_ARG, "rsv_set_counts: %u vertices > capacity %u", n_verts, s->cfg.max_verts);
+    s->n_shapes = n_shapes;
+    s->n_verts = n_verts;
+    s->d.n_shapes = n_shapes;
+    return RSV_OK;
+}
+
+int32_t rsv_commit(rsv_space* s, uint32_t which_mask, uint32_t lo, uint32_t hi) {
+    if (!s) return RSV_ERR_BAD_ARG;
+    if (hi > s->n_shapes) hi = s->n_shapes;
+    CU(s, cudaSetDevice(s->device));
+    for (int b = 0; b < RSV_BUF_COUNT; b++) {
+        if (!(which_mask & (1u << b))) continue;
+        size_t off, len;
+        if (b == RSV_BUF_VERTS) { off = 0; len = (size_t)s->n_verts * s->elem_bytes[b]; }
+        else {
+            if (lo >= hi) continue;
+            off = (size_t)lo * s->elem_bytes[b]; len = (size_t)(hi - lo) * s->elem_bytes[b];
+        }
+        if (len == 0) continue;
+        CU(s, cudaMemcpyAsync((char*)s->dev_buf[b] + off, (char*)s->host_buf[b] + off, len, cudaMemcpyHostToDevice, s->stream));
+    }
+    return RSV_OK;
+}
+
+int32_t rsv_sync(rsv_space* s) {
+    if (!s) return RSV_ERR_BAD_ARG;
+    CU(s, cudaSetDevice(s->device));
+    CU(s, cudaStreamSynchronize(s->stream));
+    return RSV_OK;
+}
+
+static inline int blocks_for(uint32_t n, int block, int cap) {
+    long long b = ((long long)n + block - 1) / block;
+    if (b < 1) b = 1;
+    if (b > cap) b = cap;
+    return (int)b;
+}
+
+int32_t rsv_frame_launch(rsv_space* s, int32_t margin, uint32_t flags) {
+    if (!s) return RSV_ERR_BAD_ARG;
+    if (margin < 0 || margin > (1 << 20)) return fail(s, RSV_ERR_BAD_ARG, "rsv_frame: margin %d out of range", margin);
+    CU(s, cudaSetDevice(s->device));
+    DevView& d = s->d;
+    cudaStream_t st = s->stream;
+    const bool timing = (flags & RSV_FRAME_TIMING) != 0;
+    auto mark = [&](int k) { if (timing) cudaEventRecord(s->ev[k], st); };
+    mark(RSV_K_CLEAR);
+    CU(s, cudaMemsetAsync(d.cell, 0, ((size_t)d.n_cells + 1) * 4, st));
+    CU(s, cudaMemsetAsync(d.tile_state, 0, (size_t)s->n_tiles * 8, st));
+    CU(s, cudaMemsetAsync(d.ctr, 0, offsetof(Counters, ray_hit_cursor), st));
+    mark(RSV_K_BOUNDS);
+    const int gcap = s->sm_count * 8;
+    if (d.n_shapes) k_bounds<<<blocks_for(d.n_shapes, kGridBlock, gcap), kGridBlock, 0, st>>>(d);
+    mark(RSV_K_SCAN);
+    k_scan<<<(d.n_cells + 1 + kScanTile - 1) / kScanTile, kScanBlock, 0, st>>>(d.cell, d.n_cells + 1, d.tile_state, &d.ctr->scan_ticket);
+    mark(RSV_K_SCATTER);
+    if (d.n_shapes) k_scatter<<<blocks_for(d.n_shapes, kGridBlock, gcap), kGridBlock, 0, st>>>(d);
+    mark(RSV_K_CELLSORT);
+    k_cellsort<<<blocks_for(d.n_cells, kGridBlock, gcap), kGridBlock, 0, st>>>(d);
+    mark(RSV_K_PAIRS);
+    if (d.n_shapes) k_pairs<<<blocks_for(d.n_shapes, kPairsBlock, s->sm_count * 16), kPairsBlock, 0, st>>>(d, margin, flags);
+    mark(RSV_K_NARROW);
+    k_narrow<<<s->narrow_blocks, kNarrowBlock, 0, st>>>(d);
+    mark(RSV_K_COUNT);
+    CU(s, cudaGetLastError());
+    CU(s, cudaMemcpyAsync(s->h_ctr, d.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    s->launched_flags = flags;
+    s->frame_pending = true;
+    return RSV_OK;
+}
+
+static int32_t ensure_mirrors(rsv_space* s) {
+    if (s->h_cap_pairs < s->d.cap_pairs) {
+        if (s->h_hits) cudaFreeHost(s->h_hits);
+        s->h_hits = nullptr; s->h_cap_pairs = 0;
+        CU(s, cudaHostAlloc(&s->h_hits, (size_t)s->d.cap_pairs * sizeof(rsv_hit), cudaHostAllocDefault));
+        s->h_cap_pairs = s->d.cap_pairs;
+    }
+    if (s->h_cap_contacts < s->d.cap_contacts) {
+        if (s->h_contacts) cudaFreeHost(s->h_contacts);
+        s->h_contacts = nullptr; s->h_cap_contacts = 0;
+        CU(s, cudaHostAlloc(&s->h_contacts, (size_t)s->d.cap_contacts * sizeof(rsv_contact), cudaHostAllocDefault));
+        s->h_cap_contacts = s->d.cap_contacts;
+    }
+    return RSV_OK;
+}
+
+int32_t rsv_frame_finish(rsv_space* s, rsv_counts* out) {
+    if (!s) return RSV_ERR_BAD_ARG;
+    if (!s->frame_pending) return fail(s, RSV_ERR_BAD_ARG, "rsv_frame_finish: no frame launched");
+    CU(s, cudaSetDevice(s->device));
+    CU(s, cudaStreamSynchronize(s->stream));
+    s->frame_pending = false;
+    const Counters& c = *s->h_ctr;
+    rsv_counts rc{};
+    rc.n_shapes = s->d.n_shapes;
+    rc.n_testers = c.n_testers;
+    rc.n_entries = c.n_entries;
+    rc.n_candidates = c.n_candidates;
+    rc.n_gated = c.n_pairs_needed;
+    rc.n_hits = c.n_hits;
+    rc.n_contacts = c.n_contacts_needed;
+    rc.overflow = c.overflow;
+    if (c.n_entries > s->d.cap_entries) rc.overflow |= RSV_OVF_ENTRIES;
+    if (c.n_pairs_needed > s->d.cap_pairs) rc.overflow |= RSV_OVF_PAIRS;
+    if (c.n_contacts_needed > s->d.cap_contacts) rc.overflow |= RSV_OVF_CONTACTS;
+    s->last_counts = rc;
+    if (out) *out = rc;
+    if (s->launched_flags & RSV_FRAME_TIMING) {
+        for (int k = 0; k < RSV_K_COUNT; k++) cudaEventElapsedTime(&s->timing.kernel_us[k], s->ev[k], s->ev[k + 1]);
+        for (int k = 0; k < RSV_K_COUNT; k++) s->timing.kernel_us[k] *= 1000.f;
+        cudaEventElapsedTime(&s->timing.frame_us, s->ev[0], s->ev[RSV_K_COUNT]);
+        s->timing.frame_us *= 1000.f;
+    }
+    s->last_records = 0; s->last_contacts = 0;
+    if (rc.overflow)
+        return fail(s, RSV_ERR_CAPACITY, "rsv_frame: capacity exceeded (need entries=%llu pairs=%llu contacts=%llu; have %u/%u/%u)",
+                    (unsigned long long)rc.n_entries, (unsigned long long)rc.n_gated, (unsigned long long)rc.n_contacts,
+                    s->d.cap_entries, s->d.cap_pairs, s->d.cap_contacts);
+    if (s->launched_flags & RSV_FRAME_DOWNLOAD) {
+        int32_t rcode = ensure_mirrors(s);
+        if (rcode != RSV_OK) return rcode;
+        if (rc.n_gated) CU(s, cudaMemcpyAsync(s->h_hits, s->d.hits, (size_t)rc.n_gated * sizeof(rsv_hit), cudaMemcpyDeviceToHost, s->stream));
+        if (rc.n_contacts) CU(s, cudaMemcpyAsync(s->h_contacts, s->d.contacts, (size_t)rc.n_contacts * sizeof(rsv_contact), cudaMemcpyDeviceToHost, s->stream));
+        CU(s, cudaStreamSynchronize(s->stream));
+        s->last_records = rc.n_gated;
+        s->last_contacts = rc.n_contacts;
+    }
+    return RSV_OK;
+}
+
+int32_t rsv_frame(rsv_space* s, int32_t margin, uint32_t flags, rsv_counts* out) {
+    int32_t rc = rsv_frame_launch(s, margin, flags);
+    if (rc != RSV_OK) return rc;
+    return rsv_frame_finish(s, out);
+}
+
+int32_t rsv_results_view(rsv_space* s, rsv_results* out) {
+    if (!s || !out) return RSV_ERR_BAD_ARG;
+    out->hits = s->h_hits;
+    out->n_hit_records = s->last_records;
+    out->contacts = s->h_contacts;
+    out->n_contacts = s->last_contacts;
+    return RSV_OK;
+}
+
+int32_t rsv_timing(rsv_space* s, rsv_timing_info* out) {
+    if (!s || !out) return RSV_ERR_BAD_ARG;
+    *out = s->timing;
+    return RSV_OK;
+}
+
+int32_t rsv_timer_start(rsv_space* s) {
+    if (!s) return RSV_ERR_BAD_ARG;
+    CU(s, cudaSetDevice(s->device));
+    CU(s, cudaEventRecord(s->ev_timer[0], s->stream));
+    return RSV_OK;
+}
+
+int32_t rsv_timer_stop(rsv_space* s, float* ms) {
+    if (!s || !ms) return RSV_ERR_BAD_ARG;
+    CU(s, cudaSetDevice(s->device));
+    CU(s, cudaEventRecord(s->ev_timer[1], s->stream));
+    CU(s, cudaEventSynchronize(s->ev_timer[1]));
+    CU(s, cudaEventElapsedTime(ms, s->ev_timer[0], s->ev_timer[1]));
+    return RSV_OK;
+}
+
+int32_t rsv_debug_cells(rsv_space* s, uint32_t* cell_end, uint64_t n_cells, uint32_t* entries, uint64_t cap_entries) {
+    if (!s) return RSV_ERR_BAD_ARG;
+    CU(s, cudaSetDevice(s->device));
+    CU(s, cudaStreamSynchronize(s->stream));
+    if (cell_end) {
+        if (n_cells != s->d.n_cells) return fail(s, RSV_ERR_BAD_ARG, "rsv_debug_cells: expected %u cells", s->d.n_cells);
+        CU(s, cudaMemcpy(cell_end, s->d.cell + 1, (size_t)n_cells * 4, cudaMemcpyDeviceToHost));
+    }
+    if (entries) {
+        uint64_t R = s->last_counts.n_entries;
+        if (cap_entries < R) return fail(s, RSV_ERR_BAD_ARG, "rsv_debug_cells: need room for %llu entries", (unsigned long long)R);
+        if (R > s->d.cap_entries) return fail(s, RSV_ERR_CAPACITY, "rsv_debug_cells: last frame overflowed the entry buffer");
+        std::vector<uint32_t> tmp(R);
+        if (R) CU(s, cudaMemcpy(tmp.data(), s->d.entries, (size_t)R * 4, cudaMemcpyDeviceToHost));
+        for (uint64_t k = 0; k < R; k++) entries[k] = tmp[k] >> 3;
+    }
+    return RSV_OK;
+}
+
+int32_t rsv_debug_cell_rects(rsv_space* s, int32_t* rects4, uint64_t n_shapes) {
+    if (!s || !rects4) return RSV_ERR_BAD_ARG;
+    if (n_shapes != s->d.n_shapes) return fail(s, RSV_ERR_BAD_ARG, "rsv_debug_cell_rects: expected %u shapes", s->d.n_shapes);
+    CU(s, cudaSetDevice(s->device));
+    CU(s, cudaStreamSynchronize(s->stream));
+    if (n_shapes) CU(s, cudaMemcpy(rects4, s->d.crect, (size_t)n_shapes * 16, cudaMemcpyDeviceToHost));
+    return RSV_OK;
+}
+
+}  // extern "C"
+
+#include "rsv_lines_abi.inl"

@@ -1,0 +1,97 @@
+// rsv_device.cuh — device-side view of one rsv_space (SoA buffers resident in HBM) shared by all kernels.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/resolv_b200.h"
+#include "rsv_math.cuh"
+
+namespace rsv {
+
+struct alignas(16) Box {  // (minx, miny, maxx, maxy); loaded as two 128-bit halves
+    double minx, miny, maxx, maxy;
+};
+
+// Device counters of one frame. Cursors are 32-bit (capacities are < 2^32); statistics are 64-bit.
+struct Counters {
+    unsigned long long n_testers;
+    unsigned long long n_entries;
+    unsigned long long n_candidates;
+    unsigned long long n_hits;
+    unsigned long long n_contacts_needed;  // total contacts produced, even past capacity
+    unsigned long long n_pairs_needed;     // total pair records produced, even past capacity
+    unsigned int pair_cursor;              // allocation cursor of the pair/hit record buffer
+    unsigned int contact_cursor;           // allocation cursor of the contact buffer
+    unsigned int overflow;                 // RSV_OVF_*
+    unsigned int scan_ticket;              // dynamic tile ids of the chained scan
+    // line tests
+    unsigned int ray_hit_cursor;
+    unsigned int ray_contact_cursor;
+    unsigned long long n_ray_candidates;
+    unsigned long long n_ray_hits;
+    unsigned long long n_ray_hits_needed;
+    unsigned long long n_ray_contacts_needed;
+};
+
+struct DevView {
+    // ---- host-committed shape state (RSV_BUF_*)
+    const double2* pos;
+    const Box* laabb;
+    const double* radius;
+    const unsigned long long* tags;
+    const uint32_t* meta;
+    const uint32_t* vert_off;
+    const double2* verts;
+    const ulonglong2* qmask;
+    const uint32_t* space_idx;
+    // ---- rebuilt every frame
+    Box* aabb;            // world Bounds() per shape (circle.go:33-39, convexPolygon.go:158-161)
+    int4* crect;          // Bounds.toCellSpace() per shape (utils.go:90-98), clamped to +-2^30
+    uint32_t* cell;       // [n_cells+1]: after the frame, cell c holds entries[cell[c] .. cell[c+1])
+    uint32_t* entries;    // shape slot << 3 | tester << 2 | firstCol << 1 | firstRow, ascending per cell
+    unsigned long long* tile_state;  // chained-scan tile descriptors
+    uint32_t* tester_start;          // first pair record of tester i
+    uint32_t* tester_count;          // number of pair records of tester i
+    // ---- results
+    rsv_hit* hits;
+    rsv_contact* contacts;
+    Counters* ctr;
+    // ---- geometry of the grid
+    uint32_t n_shapes;
+    int32_t W, H;            // grid size in cells (space.go:23)
+    int32_t row_lo, row_hi;  // stored strip of rows, [row_lo,row_hi) within [0,H)
+    double cell_w, cell_h;   // float64(cellWidth), float64(cellHeight)
+    uint32_t cells_per_space;  // W * (row_hi-row_lo)
+    uint32_t n_cells;          // cells_per_space * n_spaces
+    uint32_t n_spaces;
+    uint32_t cap_entries, cap_pairs, cap_contacts;
+};
+
+__device__ __forceinline__ Box load_box(const Box* p) {
+    const double2* q = reinterpret_cast<const double2*>(p);
+    double2 lo = __ldg(q), hi = __ldg(q + 1);
+    return Box{lo.x, lo.y, hi.x, hi.y};
+}
+__device__ __forceinline__ Box load_box_nc(const Box* p) {  // written earlier in the same frame: plain loads
+    const double2* q = reinterpret_cast<const double2*>(p);
+    double2 lo = q[0], hi = q[1];
+    return Box{lo.x, lo.y, hi.x, hi.y};
+}
+__device__ __forceinline__ void store_box(Box* p, Box b) {
+    double2* q = reinterpret_cast<double2*>(p);
+    q[0] = make_double2(b.minx, b.miny);
+    q[1] = make_double2(b.maxx, b.maxy);
+}
+
+constexpr int kClampCell = 1 << 30;
+
+// int(math.Floor(v / cell)) (utils.go:92-95), saturated to +-2^30 so that "+- margin" cannot overflow int32.
+// Saturation never changes which in-grid cells a rect covers because grids are < 2^30 cells wide.
+__device__ __forceinline__ int cell_of(double v, double cell) {
+    double f = floor(v / cell);
+    if (!(f > -(double)kClampCell)) return -kClampCell;  // also catches NaN
+    if (f > (double)kClampCell) return kClampCell;
+    return (int)f;
+}
+
+}  // namespace rsv

@@ -1,0 +1,211 @@
+// rsv_grid.cuh — per-frame bulk rebuild of the cell grid.
+//
+// Replaces the reference's incremental, pointer-chasing maintenance
+//   ShapeBase.update -> removeFromTouchingCells / addToTouchingCells   (shape.go:183-214,239-242)
+//   Cell.register / unregister / Contains                              (cell.go:19-48)
+//   Space.Cell (nil outside the grid)                                  (space.go:135-142)
+// with a counting sort of (cell, shape) registrations: k_bounds counts per cell (RED atomics), k_scan turns
+// counts into offsets (single-pass chained scan), k_scatter places shape slots, k_cellsort orders each cell by
+// slot so that the in-cell order equals the reference's for a freshly built Space (append order, cell.go:21).
+// The resulting membership relation "shape in cell(x,y)" is the reference's, bit for bit.
+#pragma once
+#include "rsv_device.cuh"
+
+namespace rsv {
+
+constexpr int kGridBlock = 256;
+
+// In-grid part of a shape's inclusive cell rect; false if the shape touches no stored cell.
+__device__ __forceinline__ bool clamp_rect(const DevView& d, int4 r, int& x0, int& y0, int& x1, int& y1) {
+    x0 = max(r.x, 0);
+    y0 = max(r.y, d.row_lo);
+    x1 = min(r.z, d.W - 1);
+    y1 = min(r.w, d.row_hi - 1);
+    return x0 <= x1 && y0 <= y1;
+}
+
+__device__ __forceinline__ uint32_t cell_base(const DevView& d, uint32_t i) {
+    return d.n_spaces > 1 ? __ldg(d.space_idx + i) * d.cells_per_space : 0u;
+}
+
+// Bounds() -> toCellSpace() per shape, and the per-cell registration counts.
+//   Circle.Bounds                circle.go:33-39      (pos +- r  ==  pos + (-r, +r), exact in IEEE)
+//   ConvexPolygon.Bounds         convexPolygon.go:158-161 (cached local bounds + position)
+//   Bounds.toCellSpace           utils.go:90-98
+//   addToTouchingCells           shape.go:191-214     (cells outside the grid are skipped)
+__global__ void __launch_bounds__(kGridBlock) k_bounds(DevView d) {
+    unsigned long long my_entries = 0, my_testers = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < d.n_shapes; i += gridDim.x * blockDim.x) {
+        uint32_t meta = __ldg(d.meta + i);
+        double2 p = __ldg(d.pos + i);
+        Box lb = load_box(d.laabb + i);
+        Box b{dadd(lb.minx, p.x), dadd(lb.miny, p.y), dadd(lb.maxx, p.x), dadd(lb.maxy, p.y)};
+        int4 r;
+        r.x = cell_of(b.minx, d.cell_w);
+        r.y = cell_of(b.miny, d.cell_h);
+        r.z = cell_of(b.maxx, d.cell_w);
+        r.w = cell_of(b.maxy, d.cell_h);
+        if (meta & RSV_META_ABSENT) r = make_int4(kClampCell, kClampCell, -kClampCell, -kClampCell);
+        store_box(d.aabb + i, b);
+        d.crect[i] = r;
+        if ((meta & RSV_META_TESTER) && !(meta & RSV_META_ABSENT)) my_testers++;
+        int x0, y0, x1, y1;
+        if (clamp_rect(d, r, x0, y0, x1, y1)) {
+            uint32_t base = cell_base(d, i);
+            for (int y = y0; y <= y1; y++) {
+                uint32_t row = base + (uint32_t)(y - d.row_lo) * (uint32_t)d.W;
+                for (int x = x0; x <= x1; x++) atomicAdd(d.cell + row + x + 1, 1u);
+            }
+            my_entries += (unsigned long long)(x1 - x0 + 1) * (unsigned long long)(y1 - y0 + 1);
+        }
+    }
+    // block reduction of the two statistics -> one atomic each per block
+    for (int o = 16; o > 0; o >>= 1) {
+        my_entries += __shfl_down_sync(0xffffffffu, my_entries, o);
+        my_testers += __shfl_down_sync(0xffffffffu, my_testers, o);
+    }
+    __shared__ unsigned long long s_e[kGridBlock / 32], s_t[kGridBlock / 32];
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s_e[warp] = my_entries; s_t[warp] = my_testers; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long e = 0, t = 0;
+        for (int w = 0; w < kGridBlock / 32; w++) { e += s_e[w]; t += s_t[w]; }
+        if (e) atomicAdd(&d.ctr->n_entries, e);
+        if (t) atomicAdd(&d.ctr->n_testers, t);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Single-pass chained ("decoupled look-back") exclusive scan of uint32, in place: one read and one write of the
+// array. Tiles take their id from an atomic ticket so a tile only ever waits on tiles that already started.
+constexpr int kScanBlock = 256;
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kScanBlock * kScanItems;
+
+__device__ __forceinline__ unsigned long long ld_state(const unsigned long long* p) {
+    return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+__device__ __forceinline__ void st_state(unsigned long long* p, unsigned long long v) {
+    *reinterpret_cast<volatile unsigned long long*>(p) = v;
+}
+
+__global__ void __launch_bounds__(kScanBlock) k_scan(uint32_t* __restrict__ data, uint32_t n,
+                                                     unsigned long long* __restrict__ state, unsigned int* ticket) {
+    __shared__ uint32_t s_tile, s_prefix, s_warp[kScanBlock / 32];
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t base = tile * kScanTile + threadIdx.x * kScanItems;
+    uint32_t v[kScanItems];
+    if (base + kScanItems <= n) {
+        const uint4* p = reinterpret_cast<const uint4*>(data + base);
+#pragma unroll
+        for (int k = 0; k < kScanItems / 4; k++) {
+            uint4 q = p[k];
+            v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanItems; k++) v[k] = (base + k < n) ? data[base + k] : 0u;
+    }
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) sum += v[k];
+    // inclusive warp scan of the per-thread sums
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t warp_excl = 0, block_sum = 0;
+#pragma unroll
+    for (int w = 0; w < kScanBlock / 32; w++) {
+        uint32_t t = s_warp[w];
+        if (w < warp) warp_excl += t;
+        block_sum += t;
+    }
+    if (threadIdx.x == 0) {
+        uint32_t excl = 0;
+        if (tile == 0) {
+            st_state(state, (2ull << 32) | block_sum);
+        } else {
+            st_state(state + tile, (1ull << 32) | block_sum);
+            int t = (int)tile - 1;
+            for (;;) {
+                unsigned long long s;
+                do { s = ld_state(state + t); } while ((s >> 32) == 0);
+                excl += (uint32_t)s;
+                if ((s >> 32) == 2) break;
+                t--;
+            }
+            st_state(state + tile, (2ull << 32) | (unsigned long long)(excl + block_sum));
+        }
+        s_prefix = excl;
+    }
+    __syncthreads();
+    uint32_t run = s_prefix + warp_excl + (inc - sum);
+    if (base + kScanItems <= n) {
+        uint4* p = reinterpret_cast<uint4*>(data + base);
+#pragma unroll
+        for (int k = 0; k < kScanItems / 4; k++) {
+            uint4 q;
+            q.x = run; run += v[4 * k];
+            q.y = run; run += v[4 * k + 1];
+            q.z = run; run += v[4 * k + 2];
+            q.w = run; run += v[4 * k + 3];
+            p[k] = q;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanItems; k++)
+            if (base + k < n) { data[base + k] = run; run += v[k]; }
+    }
+}
+
+// Entry encoding: slot << 3 | tester << 2 | firstCol << 1 | firstRow. firstCol / firstRow say that this cell is
+// the first in-grid column / row of the shape's own cell rect; with them the candidate walk can apply the
+// owner-cell rule (emit a shape only from the first cell it shares with the query rect, i.e. the first
+// occurrence in the reference's row-major walk, cell.go:86-121) without loading the other shape's rect.
+constexpr uint32_t kEntFirstRow = 1u, kEntFirstCol = 2u, kEntTester = 4u;
+
+__global__ void __launch_bounds__(kGridBlock) k_scatter(DevView d) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < d.n_shapes; i += gridDim.x * blockDim.x) {
+        int4 r = d.crect[i];
+        int x0, y0, x1, y1;
+        if (!clamp_rect(d, r, x0, y0, x1, y1)) continue;
+        uint32_t meta = __ldg(d.meta + i);
+        uint32_t base = cell_base(d, i);
+        uint32_t tag = (i << 3) | ((meta & RSV_META_TESTER) ? kEntTester : 0u);
+        for (int y = y0; y <= y1; y++) {
+            uint32_t row = base + (uint32_t)(y - d.row_lo) * (uint32_t)d.W;
+            for (int x = x0; x <= x1; x++) {
+                uint32_t slot = atomicAdd(d.cell + row + x + 1, 1u);
+                if (slot < d.cap_entries)
+                    d.entries[slot] = tag | (x == x0 ? kEntFirstCol : 0u) | (y == y0 ? kEntFirstRow : 0u);
+            }
+        }
+    }
+}
+
+// Orders every cell's entries by shape slot (the atomics above place them in arrival order).
+__global__ void __launch_bounds__(kGridBlock) k_cellsort(DevView d) {
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < d.n_cells; c += gridDim.x * blockDim.x) {
+        uint32_t s = d.cell[c], e = d.cell[c + 1];
+        if (e - s < 2 || e > d.cap_entries) continue;
+        uint32_t* a = d.entries + s;
+        uint32_t n = e - s;
+        for (uint32_t i = 1; i < n; i++) {
+            uint32_t key = a[i];
+            uint32_t j = i;
+            while (j > 0 && a[j - 1] > key) { a[j] = a[j - 1]; j--; }
+            a[j] = key;
+        }
+    }
+}
+
+}  // namespace rsv

@@ -1,0 +1,358 @@
+// rsv_narrow.cuh — SAT / analytic narrowphase over the gated pair records.
+//
+// Replaces Shape.Intersection(other) and everything below it:
+//   Circle.Intersection / ConvexPolygon.Intersection   circle.go:69-82, convexPolygon.go:288-300
+//   convexConvexTest / convexCircleTest / circleConvexTest / circleCircleTest   shape.go:318-479
+//   ConvexPolygon.Transformed / Lines / Project / SATAxes / Center / calculateMTV
+//                                                       convexPolygon.go:117-154,200-243,418-514
+//   Circle.Project                                      circle.go:41-54
+//   collidingLine.Normal / IntersectionPointsLine / IntersectionPointsCircle   convexPolygon.go:705-789
+//
+// Every float64 operation is performed in the reference's order with IEEE rounding and no FMA, so results are
+// bit-identical to the Go code on amd64 (where the reference re-derives Transformed() / Unit() several times it
+// gets the same bits each time, so deriving them once per pair is exact). One thread owns one ordered pair;
+// the transformed vertices of both polygons are staged once in shared memory ([vertex][thread] layout, conflict
+// free 128-bit accesses). Contacts are produced in two passes (count, then write) around one warp-aggregated
+// allocation in the contact buffer.
+#pragma once
+#include <cfloat>
+
+#include "rsv_device.cuh"
+
+namespace rsv {
+
+constexpr int kNarrowBlock = 128;
+constexpr int kStageVerts = 8;  // polygons with more vertices are read through L1 instead of shared memory
+
+struct Poly {
+    const double2* sm;  // staged transformed vertices of this thread (stride kNarrowBlock) or nullptr
+    const double2* gl;  // local vertices in global memory
+    V2 pos;
+    int n;   // vertices
+    int nl;  // lines: n if Closed and n > 2, else n-1 (convexPolygon.go:117-141)
+    __device__ __forceinline__ V2 get(int i) const {
+        if (sm) {
+            double2 v = sm[i * kNarrowBlock];
+            return V2{v.x, v.y};
+        }
+        double2 v = __ldg(gl + i);
+        return V2{dadd(v.x, pos.x), dadd(v.y, pos.y)};  // Transformed(): p + position (convexPolygon.go:151)
+    }
+    __device__ __forceinline__ V2 line_end(int i) const { return get(i + 1 == n ? 0 : i + 1); }
+};
+
+struct Proj {
+    double mn, mx;
+};
+
+// ConvexPolygon.Project after axis.Unit() (convexPolygon.go:218-232); u is already normalised.
+__device__ __forceinline__ Proj project_poly(const Poly& p, V2 u) {
+    double mn = vdot(u, p.get(0)), mx = mn;
+    for (int i = 1; i < p.n; i++) {
+        double q = vdot(u, p.get(i));
+        if (q < mn) mn = q;
+        else if (q > mx) mx = q;
+    }
+    return Proj{mn, mx};
+}
+
+// Circle.Project after axis.Unit() (circle.go:41-54).
+__device__ __forceinline__ Proj project_circle(V2 pos, double radius, V2 u) {
+    double pc = vdot(u, pos);
+    double pr = dmul(vmag(u), radius);
+    double mn = dsub(pc, pr), mx = dadd(pc, pr);
+    if (mn > mx) { double t = mn; mn = mx; mx = t; }
+    return Proj{mn, mx};
+}
+
+// Projection.Overlap (utils.go:75-77).
+__device__ __forceinline__ double overlap(Proj a, Proj b) { return go_min(dsub(a.mx, b.mn), dsub(b.mx, a.mn)); }
+
+// Necessary condition for 0 < fl(num/det) < 1: same sign, both non-zero, |num| < |det|. Lets almost every edge
+// pair skip the two IEEE divisions; pairs that pass still take the exact reference test below.
+__device__ __forceinline__ bool may_be_inside(double num, double det) {
+    return (num > 0 && det > 0 && num < det) || (num < 0 && det < 0 && num > det);
+}
+
+// collidingLine.IntersectionPointsLine (convexPolygon.go:715-744), including the "+ 1" fudge.
+__device__ __forceinline__ bool line_x_line(V2 ls, V2 le, V2 os, V2 oe, V2& out) {
+    double ldx = dsub(le.x, ls.x), ldy = dsub(le.y, ls.y);
+    double odx = dsub(oe.x, os.x), ody = dsub(oe.y, os.y);
+    double det = dsub(dmul(ldx, ody), dmul(odx, ldy));
+    if (!(det != 0)) return false;
+    double sy = dsub(ls.y, os.y), sx = dsub(ls.x, os.x);
+    double numL = dadd(dsub(dmul(sy, odx), dmul(sx, ody)), 1.0);
+    if (!may_be_inside(numL, det)) return false;
+    double numG = dadd(dsub(dmul(sy, ldx), dmul(sx, ldy)), 1.0);
+    if (!may_be_inside(numG, det)) return false;
+    double lambda = numL / det, gamma = numG / det;
+    if ((0 < lambda && lambda < 1) && (0 < gamma && gamma < 1)) {
+        out = V2{dadd(ls.x, dmul(lambda, ldx)), dadd(ls.y, dmul(lambda, ldy))};
+        return true;
+    }
+    return false;
+}
+
+// collidingLine.IntersectionPointsCircle (convexPolygon.go:747-789). Returns 0..2 points in the reference's order.
+__device__ __forceinline__ int line_x_circle(V2 s, V2 e, V2 c, double radius, V2 out[2]) {
+    V2 ls = vsub(s, c), le = vsub(e, c), diff = vsub(le, ls);
+    double a = dadd(dmul(diff.x, diff.x), dmul(diff.y, diff.y));
+    double b = dmul(2.0, dadd(dmul(diff.x, ls.x), dmul(diff.y, ls.y)));
+    double cc = dsub(dadd(dmul(ls.x, ls.x), dmul(ls.y, ls.y)), dmul(radius, radius));
+    double det = dsub(dmul(b, b), dmul(dmul(4.0, a), cc));
+    int n = 0;
+    if (det < 0) {
+    } else if (det == 0) {
+        double t = -b / dmul(2.0, a);
+        if (t >= 0 && t <= 1) out[n++] = V2{dadd(s.x, dmul(t, diff.x)), dadd(s.y, dmul(t, diff.y))};
+    } else {
+        // NaN det falls here too, like the reference's else branch; the comparisons below then fail.
+        double sq = sqrt(det), a2 = dmul(2.0, a);
+        double t = dadd(-b, sq) / a2;
+        if (t >= 0 && t <= 1) out[n++] = V2{dadd(s.x, dmul(t, diff.x)), dadd(s.y, dmul(t, diff.y))};
+        t = dsub(-b, sq) / a2;
+        if (t >= 0 && t <= 1) out[n++] = V2{dadd(s.x, dmul(t, diff.x)), dadd(s.y, dmul(t, diff.y))};
+    }
+    return n;
+}
+
+// Bounds.Center of the world AABB (utils.go:101-103) == ConvexPolygon.Center (convexPolygon.go:200-215).
+__device__ __forceinline__ V2 box_center(const Box& b) {
+    return V2{dadd(b.minx, dmul(dsub(b.maxx, b.minx), 0.5)), dadd(b.miny, dmul(dsub(b.maxy, b.miny), 0.5))};
+}
+
+// One SAT axis step of calculateMTV (convexPolygon.go:430-441 and twins). axis is a line normal.
+template <class ProjOther>
+__device__ __forceinline__ bool sat_axis(const Poly& cp, V2 axis, ProjOther projOther, V2& smallest) {
+    V2 u = vunit(axis);  // Project() re-normalises its argument
+    double ov = overlap(project_poly(cp, u), projOther(u));
+    if (ov <= 0) return false;
+    if (vmag(smallest) > ov) smallest = vscale(axis, ov);
+    return true;
+}
+
+// ConvexPolygon.calculateMTV, *ConvexPolygon case (convexPolygon.go:426-465, 503-513).
+__device__ __forceinline__ bool mtv_poly_poly(const Poly& cp, const Poly& other, V2 centerCp, V2 centerOther, V2& out) {
+    V2 smallest{DBL_MAX, 0.0};
+    auto projOther = [&](V2 u) { return project_poly(other, u); };
+    for (int i = 0; i < cp.nl; i++)
+        if (!sat_axis(cp, edge_normal(cp.get(i), cp.line_end(i)), projOther, smallest)) return false;
+    for (int i = 0; i < other.nl; i++)
+        if (!sat_axis(cp, edge_normal(other.get(i), other.line_end(i)), projOther, smallest)) return false;
+    if (vdot(vsub(centerCp, centerOther), smallest) < 0) smallest = vinv(smallest);
+    V2 delta = smallest;
+    if (vdot(vsub(other.pos, cp.pos), delta) > 0) delta = vinv(delta);
+    out = delta;
+    return true;
+}
+
+// ConvexPolygon.calculateMTV, *Circle case (convexPolygon.go:467-513). The reference sorts a copy of the
+// vertices by distance to the circle centre only to take element 0; under its (stable, n <= 12) insertion sort
+// that is the first vertex attaining the strict minimum.
+__device__ __forceinline__ bool mtv_poly_circle(const Poly& cp, V2 centerCp, V2 cpos, double radius, V2& out) {
+    V2 closest = cp.get(0);
+    double best = vmag(vsub(closest, cpos));
+    for (int i = 1; i < cp.n; i++) {
+        V2 v = cp.get(i);
+        double m = vmag(vsub(v, cpos));
+        if (m < best) { best = m; closest = v; }
+    }
+    auto projOther = [&](V2 u) { return project_circle(cpos, radius, u); };
+    V2 axis{dsub(cpos.x, closest.x), dsub(cpos.y, closest.y)};
+    V2 u = vunit(axis);
+    double ov = overlap(project_poly(cp, u), projOther(u));
+    if (ov <= 0) return false;
+    V2 smallest = vscale(u, ov);  // axis.Unit().Scale(overlap)
+    for (int i = 0; i < cp.nl; i++)
+        if (!sat_axis(cp, edge_normal(cp.get(i), cp.line_end(i)), projOther, smallest)) return false;
+    if (vdot(vsub(centerCp, cpos), smallest) < 0) smallest = vinv(smallest);
+    V2 delta = smallest;
+    if (vdot(vsub(cpos, cp.pos), delta) > 0) delta = vinv(delta);
+    out = delta;
+    return true;
+}
+
+// Stable insertion sort of contacts by squared distance to `c` (sort.Slice with n <= 12 is an insertion sort;
+// shape.go:385-387, 467-469).
+__device__ __forceinline__ void sort_contacts(rsv_contact* a, int n, V2 c) {
+    for (int i = 1; i < n; i++) {
+        rsv_contact key = a[i];
+        double kd = vdist2(V2{key.px, key.py}, c);
+        int j = i;
+        while (j > 0 && kd < vdist2(V2{a[j - 1].px, a[j - 1].py}, c)) { a[j] = a[j - 1]; j--; }
+        a[j] = key;
+    }
+}
+
+__device__ __forceinline__ void store_contact(rsv_contact* p, V2 pt, V2 nrm) {
+    double2* q = reinterpret_cast<double2*>(p);
+    q[0] = make_double2(pt.x, pt.y);
+    q[1] = make_double2(nrm.x, nrm.y);
+}
+
+// Visits the contacts of convexConvexTest in generation order: for otherLine in B.Lines(): for line in A.Lines()
+// (shape.go:446-461). f(point, j) with j the index of B's line.
+template <class F>
+__device__ __forceinline__ void visit_poly_poly(const Poly& A, const Poly& B, F f) {
+    for (int j = 0; j < B.nl; j++) {
+        V2 os = B.get(j), oe = B.line_end(j);
+        for (int i = 0; i < A.nl; i++) {
+            V2 pt;
+            if (line_x_line(A.get(i), A.line_end(i), os, oe, pt)) f(pt, j);
+        }
+    }
+}
+
+// Visits line/circle contacts for each line of the polygon (shape.go:328-341, 366-383). f(point, lineIndex).
+template <class F>
+__device__ __forceinline__ void visit_poly_circle(const Poly& P, V2 cpos, double radius, F f) {
+    for (int i = 0; i < P.nl; i++) {
+        V2 pts[2];
+        V2 s = P.get(i), e = P.line_end(i);
+        int n = line_x_circle(s, e, cpos, radius, pts);
+        for (int k = 0; k < n; k++) f(pts[k], i);
+    }
+}
+
+__device__ __forceinline__ Poly make_poly(const DevView& d, uint32_t slot, uint32_t meta, V2 pos, double2* stage) {
+    Poly p;
+    p.n = (int)(meta >> RSV_META_NV_SHIFT);
+    p.nl = ((meta & RSV_META_CLOSED) && p.n > 2) ? p.n : max(p.n - 1, 0);
+    p.pos = pos;
+    p.gl = d.verts + __ldg(d.vert_off + slot);
+    p.sm = nullptr;
+    if (p.n <= kStageVerts) {
+        for (int i = 0; i < p.n; i++) {
+            double2 v = __ldg(p.gl + i);
+            stage[i * kNarrowBlock] = make_double2(dadd(v.x, pos.x), dadd(v.y, pos.y));
+        }
+        p.sm = stage;
+    }
+    return p;
+}
+
+__global__ void __launch_bounds__(kNarrowBlock) k_narrow(DevView d) {
+    __shared__ double2 s_va[kStageVerts][kNarrowBlock];
+    __shared__ double2 s_vb[kStageVerts][kNarrowBlock];
+    const int lane = threadIdx.x & 31;
+    const uint32_t n_rec = min(d.ctr->pair_cursor, d.cap_pairs);
+    const uint32_t stride = gridDim.x * kNarrowBlock;
+    for (uint32_t base = blockIdx.x * kNarrowBlock; base < n_rec; base += stride) {
+        const uint32_t p = base + threadIdx.x;
+        const bool live = p < n_rec;
+        uint32_t A = 0, B = 0, cr = 0;
+        if (live) {
+            uint4 rec = *reinterpret_cast<const uint4*>(d.hits + p);
+            A = rec.x; B = rec.y; cr = rec.w;
+        }
+        const bool run = live && !(cr & RSV_HIT_NOT_GATED);
+        uint32_t metaA = 0, metaB = 0;
+        V2 pa{0, 0}, pb{0, 0};
+        double ra = 0, rb = 0;
+        Poly PA, PB;
+        PA.n = PB.n = 0;
+        int kind = -1;  // 0 circle-circle, 1 circle-convex, 2 convex-circle, 3 convex-convex
+        uint32_t n = 0;
+        if (run) {
+            metaA = __ldg(d.meta + A); metaB = __ldg(d.meta + B);
+            double2 t = __ldg(d.pos + A); pa = V2{t.x, t.y};
+            t = __ldg(d.pos + B); pb = V2{t.x, t.y};
+            const bool polyA = metaA & RSV_META_POLYGON, polyB = metaB & RSV_META_POLYGON;
+            kind = (polyA ? 2 : 0) | (polyB ? 1 : 0);
+            if (polyA) PA = make_poly(d, A, metaA, pa, &s_va[0][threadIdx.x]); else ra = __ldg(d.radius + A);
+            if (polyB) PB = make_poly(d, B, metaB, pb, &s_vb[0][threadIdx.x]); else rb = __ldg(d.radius + B);
+            // ---- pass 1: count contacts
+            if (kind == 3) {
+                visit_poly_poly(PA, PB, [&](V2, int) { n++; });
+            } else if (kind == 2) {
+                visit_poly_circle(PA, pb, rb, [&](V2, int) { n++; });
+            } else if (kind == 1) {
+                visit_poly_circle(PB, pa, ra, [&](V2, int) { n++; });
+            } else {
+                // circleCircleTest (shape.go:407-411)
+                double dx = dsub(pb.x, pa.x), dy = dsub(pb.y, pa.y);
+                double dist = sqrt(dadd(dmul(dx, dx), dmul(dy, dy)));
+                if (!(dist > dadd(ra, rb) || dist < fabs(dsub(ra, rb)) || dist == 0)) n = 2;
+            }
+        }
+        // ---- warp-aggregated allocation in the contact buffer
+        uint32_t inc = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+        uint32_t nhits = __popc(__ballot_sync(0xffffffffu, n > 0));
+        uint32_t first = 0;
+        if (lane == 0 && total) {
+            first = atomicAdd(&d.ctr->contact_cursor, total);
+            atomicAdd(&d.ctr->n_contacts_needed, (unsigned long long)total);
+            atomicAdd(&d.ctr->n_hits, (unsigned long long)nhits);
+            if (first + total > d.cap_contacts || first + total < first) atomicOr(&d.ctr->overflow, RSV_OVF_CONTACTS);
+        }
+        first = __shfl_sync(0xffffffffu, first, 0) + (inc - n);
+        if (!live) continue;
+        V2 mtv{0, 0};
+        if (n > 127) { atomicOr(&d.ctr->overflow, RSV_OVF_CONTACTS); n = 127; }
+        if (n && (unsigned long long)first + n <= d.cap_contacts) {
+            rsv_contact* out = d.contacts + first;
+            uint32_t w = 0;
+            if (kind == 3) {
+                // convexConvexTest (shape.go:438-479)
+                visit_poly_poly(PA, PB, [&](V2 pt, int j) {
+                    if (w < n) store_contact(out + w, pt, edge_normal(PB.get(j), PB.line_end(j)));
+                    w++;
+                });
+                Box ba = load_box_nc(d.aabb + A), bb = load_box_nc(d.aabb + B);
+                V2 ca = box_center(ba);
+                sort_contacts(out, (int)n, ca);
+                V2 m;
+                if (mtv_poly_poly(PA, PB, ca, box_center(bb), m)) mtv = m;
+            } else if (kind == 2) {
+                // convexCircleTest (shape.go:356-397)
+                visit_poly_circle(PA, pb, rb, [&](V2 pt, int) {
+                    if (w < n) store_contact(out + w, pt, vunit(vsub(pt, pb)));
+                    w++;
+                });
+                sort_contacts(out, (int)n, pb);
+                V2 m;
+                if (mtv_poly_circle(PA, box_center(load_box_nc(d.aabb + A)), pb, rb, m)) mtv = m;
+            } else if (kind == 1) {
+                // circleConvexTest (shape.go:318-354): edge normals, unsorted, inverted MTV
+                visit_poly_circle(PB, pa, ra, [&](V2 pt, int i) {
+                    if (w < n) store_contact(out + w, pt, edge_normal(PB.get(i), PB.line_end(i)));
+                    w++;
+                });
+                V2 m;
+                if (mtv_poly_circle(PB, box_center(load_box_nc(d.aabb + B)), pa, ra, m)) mtv = vinv(m);
+            } else {
+                // circleCircleTest (shape.go:413-433)
+                double dx = dsub(pb.x, pa.x), dy = dsub(pb.y, pa.y);
+                double dist = sqrt(dadd(dmul(dx, dx), dmul(dy, dy)));
+                double a = dadd(dsub(dmul(ra, ra), dmul(rb, rb)), dmul(dist, dist)) / dmul(2.0, dist);
+                double h = sqrt(dsub(dmul(ra, ra), dmul(a, a)));
+                double x2 = dadd(pa.x, dmul(a, dx) / dist);
+                double y2 = dadd(pa.y, dmul(a, dy) / dist);
+                double hx = dmul(h, dy) / dist, hy = dmul(h, dx) / dist;
+                V2 p0{dadd(x2, hx), dsub(y2, hy)}, p1{dsub(x2, hx), dadd(y2, hy)};
+                store_contact(out, p0, vunit(vsub(p0, pa)));
+                store_contact(out + 1, p1, vunit(vsub(p1, pa)));
+                V2 m{dsub(pa.x, pb.x), dsub(pa.y, pb.y)};
+                double md = vmag(m);
+                mtv = vscale(vunit(m), dsub(dadd(ra, rb), md));
+            }
+        } else if (n) {
+            n = 0;  // contact buffer overflow: report as capacity error, never write out of bounds
+        }
+        rsv_hit hrec;
+        hrec.a = A; hrec.b = B; hrec.first_contact = first;
+        hrec.count_rank = (cr & ~0x7fu) | n;
+        hrec.mtv_x = mtv.x; hrec.mtv_y = mtv.y;
+        uint4* hp = reinterpret_cast<uint4*>(d.hits + p);
+        hp[0] = make_uint4(hrec.a, hrec.b, hrec.first_contact, hrec.count_rank);
+        reinterpret_cast<double2*>(hp)[1] = make_double2(hrec.mtv_x, hrec.mtv_y);
+    }
+}
+
+}  // namespace rsv

@@ -1,0 +1,112 @@
+"""Shared helpers for the parity tests: build oracle Spaces from a worlds.World and canonicalise both sides."""
+import numpy as np
+
+from oracle.oracle import OracleSpace
+
+
+class OracleBatch:
+    """One OracleSpace per Space of a (possibly batched) World, with global<->local index maps."""
+
+    def __init__(self, w):
+        self.w = w
+        self.spaces, self.glob, self.loc = [], [], np.zeros(w.n, dtype=np.int64)
+        for s in range(w.n_spaces):
+            idx = np.nonzero(w.space_idx == s)[0]
+            sp = OracleSpace(w.space_w, w.space_h, w.cell_w, w.cell_h)
+            # vertex pool must be re-based per space
+            nv = w.nv[idx]
+            voff = (np.cumsum(nv) - nv).astype(np.uint32)
+            verts = np.concatenate([w.verts[o:o + n] for o, n in zip(w.vert_off[idx], nv)]) if nv.sum() else np.zeros((0, 2))
+            sp.add_bulk(w.kind[idx], w.pos0[idx], w.pos[idx], w.radius[idx], voff, nv, verts, w.closed[idx], w.tags[idx])
+            self.spaces.append(sp)
+            self.glob.append(idx)
+            self.loc[idx] = np.arange(len(idx))
+
+    def set_positions(self, pos):
+        for sp, idx in zip(self.spaces, self.glob):
+            sp.set_positions(pos[idx])
+
+    def frame(self, margin):
+        """Returns (counts dict, candidate array (a,b,rank), hits dict) in global indices."""
+        w = self.w
+        tot = dict(testers=0, candidates=0, hits=0, contacts=0)
+        ca, cb, cr, cd = [], [], [], []
+        ha, hb, ho, hc, hm, hd, con = [], [], [], [], [], [], []
+        for sp, idx in zip(self.spaces, self.glob):
+            fc, cand, hits = sp.frame(margin, tester=w.tester[idx], use_any=w.use_any[idx], any_mask=w.any_mask[idx],
+                                      none_mask=w.none_mask[idx])
+            for k in tot:
+                tot[k] += getattr(fc, k)
+            ca.append(idx[cand["a"]]); cb.append(idx[cand["b"]]); cr.append(cand["rank"]); cd.append(cand["dist"])
+            ha.append(idx[hits.a]); hb.append(idx[hits.b]); ho.append(hits.order); hc.append(hits.count)
+            hm.append(hits.mtv); hd.append(hits.dist); con.append(hits.contacts)
+        cat = np.concatenate
+        cands = dict(a=cat(ca), b=cat(cb), rank=cat(cr), dist=cat(cd))
+        hits = dict(a=cat(ha), b=cat(hb), order=cat(ho), count=cat(hc), mtv=cat(hm), dist=cat(hd), contacts=cat(con))
+        hits["first"] = np.cumsum(hits["count"]) - hits["count"]
+        return tot, cands, hits
+
+    def cells(self):
+        """Per global cell (spaces concatenated, row-major): sorted tuple of global shape indices."""
+        out = []
+        for sp, idx in zip(self.spaces, self.glob):
+            counts, entries = sp.cells()
+            ends = np.cumsum(counts)
+            starts = ends - counts
+            for s, e in zip(starts, ends):
+                out.append(tuple(sorted(idx[entries[s:e]].tolist())))
+        return out
+
+
+def device_cells(ds, n_entries):
+    end, ent = ds.debug_cells(n_entries)
+    start = np.concatenate([[0], end[:-1]])
+    return [tuple(ent[s:e].tolist()) for s, e in zip(start, end)]
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+def compare_frame(ds, ob, margin, check_candidates=True, check_rank=True):
+    """Runs one frame on both sides and asserts: candidate set (with generation rank) bit-exact, hit set bit-exact,
+    contacts/MTV within 1e-9 absolute (the north-star tolerance) — and reports whether they are bit-identical."""
+    from resolv_b200 import _abi
+    flags = _abi.FRAME_DOWNLOAD | (_abi.FRAME_ALL_CANDIDATES if check_candidates else 0)
+    c = ds.frame(margin, flags, grow=True)
+    tot, cands, oh = ob.frame(margin)
+    hits, con = ds.results()
+    assert c.n_testers == tot["testers"]
+    assert c.n_candidates == tot["candidates"], (c.n_candidates, tot["candidates"])
+    if check_candidates:
+        # The generation rank is defined for a Space whose cells are in append order (freshly built). After moves
+        # the reference's in-cell order depends on its swap-remove history (cell.go:26-38), so against a moved
+        # oracle only the candidate SET is compared (check_rank=False).
+        rank = hits["count_rank"] >> 8
+        dev = np.stack([hits["a"], hits["b"], rank if check_rank else 0 * rank], -1).astype(np.int64)
+        ora = np.stack([cands["a"], cands["b"], cands["rank"] if check_rank else 0 * cands["rank"]], -1).astype(np.int64)
+        dev = dev[np.lexsort((dev[:, 1], dev[:, 0]))]
+        ora = ora[np.lexsort((ora[:, 1], ora[:, 0]))]
+        assert dev.shape == ora.shape and np.array_equal(dev, ora), "candidate set / generation rank mismatch"
+    n = hits["count_rank"] & 0x7f
+    live = n > 0
+    assert c.n_hits == tot["hits"] == int(live.sum()), (c.n_hits, tot["hits"], int(live.sum()))
+    assert c.n_contacts == tot["contacts"]
+    dh = hits[live]
+    dn = n[live]
+    # canonical order: by (a, b)
+    do = np.lexsort((dh["b"], dh["a"]))
+    oo = np.lexsort((oh["b"], oh["a"]))
+    assert np.array_equal(dh["a"][do], oh["a"][oo]) and np.array_equal(dh["b"][do], oh["b"][oo]), "hit set mismatch"
+    assert np.array_equal(dn[do], oh["count"][oo]), "contact counts mismatch"
+    dm = dh["mtv"][do]
+    om = oh["mtv"][oo]
+    assert np.all(np.abs(dm - om) <= 1e-9), "MTV beyond 1e-9"
+    dcon = np.concatenate([np.concatenate([con["p"][f:f + k], con["n"][f:f + k]], -1)
+                           for f, k in zip(dh["first_contact"][do], dn[do])]) if len(do) else np.zeros((0, 4))
+    ocon = np.concatenate([oh["contacts"][f:f + k] for f, k in zip(oh["first"][oo], oh["count"][oo])]) if len(oo) else np.zeros((0, 4))
+    same_nan = np.isnan(dcon) == np.isnan(ocon)
+    assert same_nan.all()
+    assert np.all((np.abs(dcon - ocon) <= 1e-9) | np.isnan(ocon)), "contacts beyond 1e-9"
+    exact = bool(np.array_equal(bits(dm), bits(om)) and np.array_equal(bits(dcon), bits(ocon)))
+    return c, exact
