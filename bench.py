@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the resolv collision hot path (grid broadphase + SAT narrowphase) on B200.
+
+A "step" is one full frame over the workload: (positions resident in HBM) grid rebuild -> candidate pairs ->
+Bounds gate + SAT narrowphase -> compacted IntersectionSet buffer. `value` times K back-to-back frames with CUDA
+events on the library's stream (inputs resident); `e2e` times the same frame through the C ABI with HOST buffers:
+H2D of that step's positions from pinned staging + the frame + D2H of the compacted hits/contacts.
+
+N = 1 workload: BASELINE.json configs[1] — 1M axis-aligned 8-32 px rectangles in a 65536x65536 Space with 32x32
+cells. N > 1 (torchrun, one rank per GPU): the world grows with N (N x 1M shapes in a 65536 x N*65536 Space,
+same density), strip-partitioned by cell rows with a per-frame halo exchange (weak scaling).
+
+--impl reference times the reference's own CPU algorithm (the oracle port: no Go toolchain exists in this image,
+so the real reference cannot run) on the box's host cores over the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "shapes_per_sec_full_frame"
+UNIT = "shapes/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"])
+    ap.add_argument("--shapes", type=int, default=1_000_000, help="shapes per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-threads", type=int, default=0)
+    return ap.parse_args()
+
+
+def make_world(args, n_gpus=1):
+    from resolv_b200 import worlds
+    n = args.shapes * n_gpus
+    if n_gpus > 1:
+        raise NotImplementedError
+    if args.workload == "cfg2":
+        return worlds.make_rects(n)
+    return worlds.make_mixed(n)
+
+
+def workload_name(args, n_gpus):
+    base = {"cfg2": "configs[1]: axis-aligned 8-32 px rectangles, 65536x65536 Space, 32x32 cells, margin 1, no filter",
+            "cfg3": "configs[2]: mixed circles + convex 3-8-gons, tag-filtered, 65536x65536 Space, 32x32 cells, margin 1"}[args.workload]
+    return f"{args.shapes * n_gpus} shapes, {base}"
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def kernel_algorithmic_bytes(c, w, n_cells):
+    """Algorithmic bytes each kernel must move per launch: every datum counted once per
+    producer/consumer hand-off, caches assumed perfect within a kernel."""
+    N, R, P, G, K = c.n_shapes, c.n_entries, c.n_candidates, c.n_gated, c.n_contacts
+    poly = int((w.kind == 1).sum())
+    nv_touch = 16 * float(w.nv.sum()) / max(N, 1)  # average vertex bytes per shape
+    return {
+        "clear": 4 * (n_cells + 1),
+        "bounds": N * (16 + 32 + 4) + N * (32 + 16) + 4 * R,            # pos+laabb+meta in, aabb+crect out, one RED per entry
+        "scan": 8 * (n_cells + 1),                                       # read + write cell offsets
+        "scatter": N * (16 + 4) + 8 * R,                                 # crect+meta in, cursor RMW + entry out
+        "cellsort": 4 * (n_cells + 1) + 8 * R,                           # offsets in, entries in/out
+        "pairs": N * (4 + 16 + 32 + 16) + 4 * (n_cells + 1) + 4 * R + 32 * N + 16 * G + 8 * N,
+        # meta+crect+aabb+qmask per tester, every cell offset and entry once, every shape's aabb once as a candidate,
+        # pair record out, tester table out
+        "narrow": G * (16 + 2 * (16 + 4 + 4)) + G * 2 * nv_touch + 32 * G + 32 * K,
+        # record in, pos/meta/vert_off of both, vertices of both, hit header out, contacts out
+    }
+
+
+def run_b200(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    if world_size > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        from resolv_b200 import strips
+        return strips.run_bench(args, rank, world_size, local_rank)
+
+    from resolv_b200 import _abi, space_for_world, worlds
+    K, W = args.steps, max(args.warmup, 3)
+    w = make_world(args)
+    N = w.n
+    ds = space_for_world(w, device=local_rank)
+    margin = w.margin
+    base_flags = 0 if (w.use_any.any() or w.none_mask.any()) else _abi.FRAME_NO_TAG_FILTERS
+    # positions for every step (per-frame motion), precomputed outside the timed regions
+    frames = []
+    for f in range(min(K + W, 8)):
+        worlds.advance(w, f + 1)
+        frames.append(w.pos.copy())
+    # ---- warm-up (also sizes the output buffers)
+    c = ds.frame(margin, _abi.FRAME_DOWNLOAD | base_flags, grow=True)
+    for i in range(W):
+        ds.set_positions(frames[i % len(frames)])
+        c = ds.frame(margin, _abi.FRAME_DOWNLOAD | base_flags, grow=True)
+    n_cells = ds.grid_w * ds.rows * ds.n_spaces
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    # ---- value: K frames back to back, inputs resident in HBM, CUDA events on the library's stream
+    ds.sync()
+    torch.cuda.synchronize()
+    ds.timer_start()
+    for i in range(K):
+        ds.frame_launch(margin, base_flags)
+    ms = ds.timer_stop()
+    c = ds.frame_finish()
+    torch.cuda.synchronize()
+    ms_per_step = ms / K
+    # ---- per-kernel durations over another K frames (events between kernels)
+    acc = {k: 0.0 for k in _abi.KERNEL_NAMES}
+    for i in range(K):
+        ds.frame(margin, _abi.FRAME_TIMING | base_flags)
+        t = ds.timing()
+        for k in acc:
+            acc[k] += t[k] / K
+    # ---- e2e: host buffers, H2D of the step's positions + frame + D2H of hits/contacts, every step
+    e2e_t = 0.0
+    h2d = d2h = 0
+    for i in range(K):
+        ds.buf[_abi.BUF_POS][:2 * N] = frames[i % len(frames)].reshape(-1)   # the game moving its shapes (untimed)
+        t0 = time.perf_counter()
+        ds.commit(1 << _abi.BUF_POS)
+        ce = ds.frame(margin, _abi.FRAME_DOWNLOAD | base_flags)
+        e2e_t += time.perf_counter() - t0
+        h2d += 16 * N
+        d2h += 32 * int(ce.n_gated) + 32 * int(ce.n_contacts) + 128
+    clocks = sampler.stop()
+
+    peak, peak_src = measured_peaks()
+    algo = kernel_algorithmic_bytes(c, w, n_cells)
+    dom = max(acc, key=lambda k: acc[k])
+    achieved = algo[dom] / (acc[dom] * 1e-6) / 1e9 if acc[dom] > 0 else 0.0
+    frame_bytes = sum(algo.values())
+    out = {
+        "metric": METRIC, "value": N / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args, 1), "l2": "inputs + per-frame intermediates (~0.3 GB) exceed the 126 MB L2",
+                   "margin": margin},
+        "pair_tests_per_sec": int(c.n_candidates) / (ms_per_step * 1e-3),
+        "counts": c.as_dict(),
+        "clocks": clocks,
+        "e2e": {"value": N * K / e2e_t, "unit": UNIT, "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K,
+                "ms_per_step": 1e3 * e2e_t / K},
+        "gpu_launches": K * 6,
+        "kernels_us": {k: round(v, 2) for k, v in acc.items()},
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frame_algorithmic_bytes": int(frame_bytes),
+                     "frame_frac": frame_bytes / (ms_per_step * 1e-3) / 1e9 / peak},
+    }
+    if not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args, budget_s=20.0)
+    ds.close()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_baseline(args, budget_s=20.0, steps=None, warmup=1):
+    """The reference's algorithm (oracle port) on the host cores: a step = SetPosition on every shape (grid
+    maintenance, shape.go:239-242) single-threaded as in the reference + every tester's IntersectionTest on
+    `threads` threads with thread-local scratch."""
+    from oracle import oracle as orc
+    from resolv_b200 import worlds
+    threads = args.cpu_threads or orc.hardware_threads() or 1
+    # bounded sample: the same world generator at a shape count whose frame takes ~1 s on one core
+    n = min(args.shapes, 250_000 if steps is None else args.shapes)
+    a2 = argparse.Namespace(**vars(args))
+    a2.shapes = n
+    w = make_world(a2)
+    if n != args.shapes:   # keep the density of the full workload: shrink the Space with sqrt(n / N)
+        side = int(round(65536 * (n / args.shapes) ** 0.5 / 32)) * 32
+        w = (worlds.make_rects(n, space=side) if args.workload == "cfg2" else worlds.make_mixed(n, space=side))
+    sp = orc.OracleSpace(w.space_w, w.space_h, w.cell_w, w.cell_h)
+    sp.add_bulk(w.kind, w.pos0, w.pos, w.radius, w.vert_off, w.nv, w.verts, w.closed, w.tags)
+    kw = dict(tester=w.tester, use_any=w.use_any, any_mask=w.any_mask, none_mask=w.none_mask, record=False, threads=threads)
+    t_total, done, cands = 0.0, 0, 0
+    t_begin = time.perf_counter()
+    f = 0
+    while True:
+        worlds.advance(w, f + 1)
+        t0 = time.perf_counter()
+        sp.set_positions(w.pos)
+        fc, _, _ = sp.frame(w.margin, **kw)
+        dt = time.perf_counter() - t0
+        f += 1
+        if f > warmup:
+            t_total += dt
+            done += 1
+            cands += fc.candidates
+        if steps is not None and done >= steps:
+            break
+        if steps is None and (time.perf_counter() - t_begin > budget_s or done >= 10):
+            break
+    return {"value": n * done / t_total, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{done} full frames (SetPosition on every shape, 1 thread, + all IntersectionTests, {threads} threads) "
+                      f"of the same generator at {n} shapes and the workload's density; oracle port of the Go reference "
+                      f"(no Go toolchain in this image)",
+            "pair_tests_per_sec": cands / t_total, "ms_per_step": 1e3 * t_total / done}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    K, W = args.steps, args.warmup
+    # bounded: at most ~250k shapes per step so that K+W steps end within a few minutes on any host
+    cb = cpu_baseline(args, steps=K, warmup=W)
+    n_gpus = args.gpus
+    return {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
+            "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": workload_name(args, 1), "margin": 1},
+            "pair_tests_per_sec": cb["pair_tests_per_sec"], "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    args = parse()
+    out = run_reference(args) if args.impl == "reference" else run_b200(args)
+    if out is not None and int(os.environ.get("RANK", "0")) == 0:
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

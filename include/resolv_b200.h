@@ -131,6 +131,9 @@ typedef struct rsv_results {
 #define RSV_FRAME_ALL_CANDIDATES 0x2u  /* parity/debug: emit a record for EVERY candidate pair, not only gated ones;
                                           records failing the Bounds gate carry RSV_HIT_NOT_GATED in count_rank bit 7 */
 #define RSV_FRAME_TIMING 0x4u          /* record per-kernel CUDA events; read with rsv_timing */
+#define RSV_FRAME_NO_TAG_FILTERS 0x8u  /* the host asserts that no tester's TestAgainst chain contains ByTags / NotByTags
+                                          this frame: RSV_BUF_QMASK / RSV_BUF_TAGS are not read (META_USE_ANY ignored) */
+#define RSV_FRAME_TESTER_TABLE 0x10u   /* also fill the per-tester (first record, record count) table for random access */
 #define RSV_HIT_NOT_GATED 0x80u
 
 /* Per-kernel device times of the last RSV_FRAME_TIMING frame, microseconds, CUDA events on the space's stream. */

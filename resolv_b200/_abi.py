@@ -19,7 +19,7 @@ BUF_DTYPES = {BUF_POS: np.float64, BUF_LOCAL_AABB: np.float64, BUF_RADIUS: np.fl
               BUF_META: np.uint32, BUF_VERT_OFF: np.uint32, BUF_VERTS: np.float64, BUF_QMASK: np.uint64,
               BUF_SPACE_IDX: np.uint32}
 META_POLYGON, META_CLOSED, META_TESTER, META_USE_ANY, META_ABSENT, META_NV_SHIFT = 1, 2, 4, 8, 16, 8
-FRAME_DOWNLOAD, FRAME_ALL_CANDIDATES, FRAME_TIMING = 1, 2, 4
+FRAME_DOWNLOAD, FRAME_ALL_CANDIDATES, FRAME_TIMING, FRAME_NO_TAG_FILTERS, FRAME_TESTER_TABLE = 1, 2, 4, 8, 16
 HIT_NOT_GATED = 0x80
 KERNEL_NAMES = ["clear", "bounds", "scan", "scatter", "cellsort", "pairs", "narrow"]
 

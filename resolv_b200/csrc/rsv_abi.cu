@@ -50,6 +50,7 @@ struct rsv_space {
     cudaEvent_t ev_timer[2] = {};
     rsv_timing_info timing{};
     int narrow_blocks = 148 * 4;
+    int pairs_blocks = 148 * 8;
     // line tests
     LineState lines{};
     std::string error;
@@ -118,8 +119,10 @@ static int32_t alloc_outputs(rsv_space* s, uint32_t cap_entries, uint32_t cap_pa
     DevView& d = s->d;
     if (cap_entries > d.cap_entries) {
         if (d.entries) cudaFree(d.entries);
-        d.entries = nullptr; d.cap_entries = 0;
+        if (d.ent_box) cudaFree(d.ent_box);
+        d.entries = nullptr; d.ent_box = nullptr; d.cap_entries = 0;
         CU(s, cudaMalloc(&d.entries, (size_t)cap_entries * 4));
+        CU(s, cudaMalloc(&d.ent_box, (size_t)cap_entries * sizeof(float4)));
         d.cap_entries = cap_entries;
     }
     if (cap_pairs > d.cap_pairs) {
@@ -219,6 +222,7 @@ int32_t rsv_create(const rsv_config* cfg, rsv_space** out) {
     CUC(cudaMalloc(&d.tile_state, (size_t)s->n_tiles * 8));
     CUC(cudaMalloc(&d.tester_start, (size_t)N * 4));
     CUC(cudaMalloc(&d.tester_count, (size_t)N * 4));
+    CUC(cudaMalloc(&d.orphans, (size_t)N * 4));
     CUC(cudaMalloc(&d.ctr, sizeof(Counters)));
     CUC(cudaHostAlloc(&s->h_ctr, sizeof(Counters), cudaHostAllocDefault));
     uint32_t ce = cfg->max_entries ? cfg->max_entries : (uint32_t)std::min<unsigned long long>(4ull * N + 4096, 0xfffffff0ull);
@@ -230,6 +234,8 @@ int32_t rsv_create(const rsv_config* cfg, rsv_space** out) {
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_narrow, kNarrowBlock, 0) == cudaSuccess && occ > 0)
         s->narrow_blocks = s->sm_count * occ;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pairs, kPairsBlock, 0) == cudaSuccess && occ > 0)
+        s->pairs_blocks = s->sm_count * occ;
     CUC(cudaStreamSynchronize(s->stream));
 #undef CUC
     *out = s;
@@ -245,7 +251,7 @@ int32_t rsv_destroy(rsv_space* s) {
         if (s->host_buf[b]) cudaFreeHost(s->host_buf[b]);
     }
     DevView& d = s->d;
-    void* dev[] = {d.aabb, d.crect, d.cell, d.entries, d.tile_state, d.tester_start, d.tester_count, d.hits, d.contacts, d.ctr};
+    void* dev[] = {d.aabb, d.crect, d.cell, d.entries, d.ent_box, d.tile_state, d.tester_start, d.tester_count, d.orphans, d.hits, d.contacts, d.ctr};
     for (void* p : dev) if (p) cudaFree(p);
     if (s->h_ctr) cudaFreeHost(s->h_ctr);
     if (s->h_hits) cudaFreeHost(s->h_hits);
@@ -340,7 +346,7 @@ int32_t rsv_frame_launch(rsv_space* s, int32_t margin, uint32_t flags) {
     CU(s, cudaMemsetAsync(d.ctr, 0, offsetof(Counters, ray_hit_cursor), st));
     mark(RSV_K_BOUNDS);
     const int gcap = s->sm_count * 8;
-    if (d.n_shapes) k_bounds<<<blocks_for(d.n_shapes, kGridBlock, gcap), kGridBlock, 0, st>>>(d);
+    if (d.n_shapes) k_bounds<<<blocks_for(d.n_shapes, kGridBlock, gcap), kGridBlock, 0, st>>>(d, margin);
     mark(RSV_K_SCAN);
     k_scan<<<(d.n_cells + 1 + kScanTile - 1) / kScanTile, kScanBlock, 0, st>>>(d.cell, d.n_cells + 1, d.tile_state, &d.ctr->scan_ticket);
     mark(RSV_K_SCATTER);
@@ -348,7 +354,7 @@ int32_t rsv_frame_launch(rsv_space* s, int32_t margin, uint32_t flags) {
     mark(RSV_K_CELLSORT);
     k_cellsort<<<blocks_for(d.n_cells, kGridBlock, gcap), kGridBlock, 0, st>>>(d);
     mark(RSV_K_PAIRS);
-    if (d.n_shapes) k_pairs<<<blocks_for(d.n_shapes, kPairsBlock, s->sm_count * 16), kPairsBlock, 0, st>>>(d, margin, flags);
+    if (d.n_shapes) k_pairs<<<s->pairs_blocks, kPairsBlock, 0, st>>>(d, margin, flags);
     mark(RSV_K_NARROW);
     k_narrow<<<s->narrow_blocks, kNarrowBlock, 0, st>>>(d);
     mark(RSV_K_COUNT);
@@ -387,12 +393,12 @@ int32_t rsv_frame_finish(rsv_space* s, rsv_counts* out) {
     rc.n_testers = c.n_testers;
     rc.n_entries = c.n_entries;
     rc.n_candidates = c.n_candidates;
-    rc.n_gated = c.n_pairs_needed;
+    rc.n_gated = c.pair_cursor;
     rc.n_hits = c.n_hits;
     rc.n_contacts = c.n_contacts_needed;
     rc.overflow = c.overflow;
     if (c.n_entries > s->d.cap_entries) rc.overflow |= RSV_OVF_ENTRIES;
-    if (c.n_pairs_needed > s->d.cap_pairs) rc.overflow |= RSV_OVF_PAIRS;
+    if (c.pair_cursor > s->d.cap_pairs) rc.overflow |= RSV_OVF_PAIRS;
     if (c.n_contacts_needed > s->d.cap_contacts) rc.overflow |= RSV_OVF_CONTACTS;
     s->last_counts = rc;
     if (out) *out = rc;

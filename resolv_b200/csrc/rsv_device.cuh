@@ -19,8 +19,10 @@ struct Counters {
     unsigned long long n_candidates;
     unsigned long long n_hits;
     unsigned long long n_contacts_needed;  // total contacts produced, even past capacity
-    unsigned long long n_pairs_needed;     // total pair records produced, even past capacity
-    unsigned int pair_cursor;              // allocation cursor of the pair/hit record buffer
+    unsigned int pair_cursor;              // allocation cursor of the pair/hit record buffer (== records needed)
+    unsigned int chunk_cursor;             // next chunk of the entry array for k_pairs
+    unsigned int orphan_cursor;            // next batch of the orphan tester list for k_pairs
+    unsigned int n_orphans;                // testers that touch no stored cell but whose margin reaches the grid
     unsigned int contact_cursor;           // allocation cursor of the contact buffer
     unsigned int overflow;                 // RSV_OVF_*
     unsigned int scan_ticket;              // dynamic tile ids of the chained scan
@@ -49,9 +51,11 @@ struct DevView {
     int4* crect;          // Bounds.toCellSpace() per shape (utils.go:90-98), clamped to +-2^30
     uint32_t* cell;       // [n_cells+1]: after the frame, cell c holds entries[cell[c] .. cell[c+1])
     uint32_t* entries;    // shape slot << 3 | tester << 2 | firstCol << 1 | firstRow, ascending per cell
+    float4* ent_box;      // per entry: outward-rounded float32 copy of the shape's world AABB (minx,miny,maxx,maxy)
     unsigned long long* tile_state;  // chained-scan tile descriptors
     uint32_t* tester_start;          // first pair record of tester i
     uint32_t* tester_count;          // number of pair records of tester i
+    uint32_t* orphans;               // see Counters::n_orphans
     // ---- results
     rsv_hit* hits;
     rsv_contact* contacts;
@@ -81,6 +85,13 @@ __device__ __forceinline__ void store_box(Box* p, Box b) {
     double2* q = reinterpret_cast<double2*>(p);
     q[0] = make_double2(b.minx, b.miny);
     q[1] = make_double2(b.maxx, b.maxy);
+}
+
+// Outward-rounded float32 copy of a float64 box: contains the exact box, so "disjoint in float" implies
+// "disjoint in float64" and can be used as a cheap pre-reject in front of the exact Bounds gate.
+__device__ __forceinline__ float4 float_box(const Box& b) {
+    return make_float4(__double2float_rd(b.minx), __double2float_rd(b.miny), __double2float_ru(b.maxx),
+                       __double2float_ru(b.maxy));
 }
 
 constexpr int kClampCell = 1 << 30;

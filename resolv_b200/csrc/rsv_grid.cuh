@@ -33,7 +33,7 @@ __device__ __forceinline__ uint32_t cell_base(const DevView& d, uint32_t i) {
 //   ConvexPolygon.Bounds         convexPolygon.go:158-161 (cached local bounds + position)
 //   Bounds.toCellSpace           utils.go:90-98
 //   addToTouchingCells           shape.go:191-214     (cells outside the grid are skipped)
-__global__ void __launch_bounds__(kGridBlock) k_bounds(DevView d) {
+__global__ void __launch_bounds__(kGridBlock) k_bounds(DevView d, int margin) {
     unsigned long long my_entries = 0, my_testers = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < d.n_shapes; i += gridDim.x * blockDim.x) {
         uint32_t meta = __ldg(d.meta + i);
@@ -48,9 +48,19 @@ __global__ void __launch_bounds__(kGridBlock) k_bounds(DevView d) {
         if (meta & RSV_META_ABSENT) r = make_int4(kClampCell, kClampCell, -kClampCell, -kClampCell);
         store_box(d.aabb + i, b);
         d.crect[i] = r;
-        if ((meta & RSV_META_TESTER) && !(meta & RSV_META_ABSENT)) my_testers++;
+        d.tester_count[i] = 0;
+        const bool tester = (meta & RSV_META_TESTER) && !(meta & RSV_META_ABSENT);
+        if (tester) my_testers++;
         int x0, y0, x1, y1;
-        if (clamp_rect(d, r, x0, y0, x1, y1)) {
+        const bool in_grid = clamp_rect(d, r, x0, y0, x1, y1);
+        if (tester && !in_grid) {
+            // SelectTouchingCells(margin) can still reach stored cells (shape.go:220-237): k_pairs finds testers
+            // through their home registration, so these go to a side list.
+            int qx0 = max(r.x - margin, 0), qx1 = min(r.z + margin, d.W - 1);
+            int qy0 = max(r.y - margin, d.row_lo), qy1 = min(r.w + margin, d.row_hi - 1);
+            if (qx0 <= qx1 && qy0 <= qy1) d.orphans[atomicAdd(&d.ctr->n_orphans, 1u)] = i;
+        }
+        if (in_grid) {
             uint32_t base = cell_base(d, i);
             for (int y = y0; y <= y1; y++) {
                 uint32_t row = base + (uint32_t)(y - d.row_lo) * (uint32_t)d.W;
@@ -181,12 +191,15 @@ __global__ void __launch_bounds__(kGridBlock) k_scatter(DevView d) {
         uint32_t meta = __ldg(d.meta + i);
         uint32_t base = cell_base(d, i);
         uint32_t tag = (i << 3) | ((meta & RSV_META_TESTER) ? kEntTester : 0u);
+        const float4 fb = float_box(load_box_nc(d.aabb + i));
         for (int y = y0; y <= y1; y++) {
             uint32_t row = base + (uint32_t)(y - d.row_lo) * (uint32_t)d.W;
             for (int x = x0; x <= x1; x++) {
                 uint32_t slot = atomicAdd(d.cell + row + x + 1, 1u);
-                if (slot < d.cap_entries)
+                if (slot < d.cap_entries) {
                     d.entries[slot] = tag | (x == x0 ? kEntFirstCol : 0u) | (y == y0 ? kEntFirstRow : 0u);
+                    d.ent_box[slot] = fb;
+                }
             }
         }
     }
@@ -198,12 +211,16 @@ __global__ void __launch_bounds__(kGridBlock) k_cellsort(DevView d) {
         uint32_t s = d.cell[c], e = d.cell[c + 1];
         if (e - s < 2 || e > d.cap_entries) continue;
         uint32_t* a = d.entries + s;
+        float4* b = d.ent_box + s;
         uint32_t n = e - s;
         for (uint32_t i = 1; i < n; i++) {
             uint32_t key = a[i];
+            if (a[i - 1] <= key) continue;
+            float4 kb = b[i];
             uint32_t j = i;
-            while (j > 0 && a[j - 1] > key) { a[j] = a[j - 1]; j--; }
+            while (j > 0 && a[j - 1] > key) { a[j] = a[j - 1]; b[j] = b[j - 1]; j--; }
             a[j] = key;
+            b[j] = kb;
         }
     }
 }

@@ -42,11 +42,26 @@ __device__ __forceinline__ V2 vinv(V2 a) { return V2{-a.x, -a.y}; }             
 __device__ __forceinline__ V2 vscale(V2 a, double s) { return V2{dmul(a.x, s), dmul(a.y, s)}; }     // vector.go:273-277
 __device__ __forceinline__ double vdot(V2 a, V2 b) { return dadd(dmul(a.x, b.x), dmul(a.y, b.y)); } // vector.go:287-289
 __device__ __forceinline__ double vmag2(V2 a) { return dadd(dmul(a.x, a.x), dmul(a.y, a.y)); }      // vector.go:117-119
-__device__ __forceinline__ double vmag(V2 a) { return sqrt(vmag2(a)); }                             // vector.go:112-114
+// Exact shortcut for axis-aligned vectors (rectangles, tiles, walls — most of a 2D game): when one component is
+// +-0, x*x + 0 rounds to fl(x*x) and sqrt(fl(x*x)) == |x| exactly for every double whose square neither
+// overflows nor falls into the subnormal range, so the IEEE sqrt (a ~20-instruction sequence on the fp64 pipe)
+// can be skipped with bit-identical results. The range test keeps the generic path for everything else.
+__device__ __forceinline__ bool axis_safe(double m) { return m == 0.0 || (m > 1e-150 && m < 1e150); }
+
+__device__ __forceinline__ double vmag(V2 a) {                                                      // vector.go:112-114
+    if (a.y == 0.0) { double m = fabs(a.x); if (axis_safe(m)) return m; }
+    else if (a.x == 0.0) { double m = fabs(a.y); if (axis_safe(m)) return m; }
+    return sqrt(vmag2(a));
+}
 __device__ __forceinline__ double vdist2(V2 a, V2 b) { return vmag2(vsub(a, b)); }                  // vector.go:152-156
 __device__ __forceinline__ V2 vunit(V2 a) {                                                         // vector.go:167-175
     double l = vmag(a);
     if (l < 1e-8 || l == 1.0) return a;
+    // x / |x| == +-1 and +-0 / l == +-0 exactly: skip the two IEEE divisions for axis-aligned vectors
+    if (l < 1e150) {  // (finite: inf / inf must stay NaN)
+        if (a.y == 0.0 && l == fabs(a.x)) return V2{copysign(1.0, a.x), a.y};
+        if (a.x == 0.0 && l == fabs(a.y)) return V2{a.x, copysign(1.0, a.y)};
+    }
     return V2{a.x / l, a.y / l};
 }
 

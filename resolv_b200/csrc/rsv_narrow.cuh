@@ -191,14 +191,14 @@ __device__ __forceinline__ void store_contact(rsv_contact* p, V2 pt, V2 nrm) {
 }
 
 // Visits the contacts of convexConvexTest in generation order: for otherLine in B.Lines(): for line in A.Lines()
-// (shape.go:446-461). f(point, j) with j the index of B's line.
+// (shape.go:446-461). f(point, j, i) with j the index of B's line and i of A's.
 template <class F>
 __device__ __forceinline__ void visit_poly_poly(const Poly& A, const Poly& B, F f) {
     for (int j = 0; j < B.nl; j++) {
         V2 os = B.get(j), oe = B.line_end(j);
         for (int i = 0; i < A.nl; i++) {
             V2 pt;
-            if (line_x_line(A.get(i), A.line_end(i), os, oe, pt)) f(pt, j);
+            if (line_x_line(A.get(i), A.line_end(i), os, oe, pt)) f(pt, j, i);
         }
     }
 }
@@ -235,6 +235,7 @@ __global__ void __launch_bounds__(kNarrowBlock) k_narrow(DevView d) {
     __shared__ double2 s_va[kStageVerts][kNarrowBlock];
     __shared__ double2 s_vb[kStageVerts][kNarrowBlock];
     const int lane = threadIdx.x & 31;
+    if (d.ctr->overflow & RSV_OVF_PAIRS) return;  // records past the capacity were never written: frame is retried
     const uint32_t n_rec = min(d.ctr->pair_cursor, d.cap_pairs);
     const uint32_t stride = gridDim.x * kNarrowBlock;
     for (uint32_t base = blockIdx.x * kNarrowBlock; base < n_rec; base += stride) {
@@ -253,6 +254,8 @@ __global__ void __launch_bounds__(kNarrowBlock) k_narrow(DevView d) {
         PA.n = PB.n = 0;
         int kind = -1;  // 0 circle-circle, 1 circle-convex, 2 convex-circle, 3 convex-convex
         uint32_t n = 0;
+        unsigned long long xmask = 0;  // crossing edge pairs (bit j*nlA + i) when nlA*nlB <= 64
+        bool use_mask = false;
         if (run) {
             metaA = __ldg(d.meta + A); metaB = __ldg(d.meta + B);
             double2 t = __ldg(d.pos + A); pa = V2{t.x, t.y};
@@ -263,7 +266,11 @@ __global__ void __launch_bounds__(kNarrowBlock) k_narrow(DevView d) {
             if (polyB) PB = make_poly(d, B, metaB, pb, &s_vb[0][threadIdx.x]); else rb = __ldg(d.radius + B);
             // ---- pass 1: count contacts
             if (kind == 3) {
-                visit_poly_poly(PA, PB, [&](V2, int) { n++; });
+                use_mask = PA.nl * PB.nl <= 64;
+                visit_poly_poly(PA, PB, [&](V2, int j, int i) {
+                    n++;
+                    if (use_mask) xmask |= 1ull << (j * PA.nl + i);
+                });
             } else if (kind == 2) {
                 visit_poly_circle(PA, pb, rb, [&](V2, int) { n++; });
             } else if (kind == 1) {
@@ -300,10 +307,22 @@ __global__ void __launch_bounds__(kNarrowBlock) k_narrow(DevView d) {
             uint32_t w = 0;
             if (kind == 3) {
                 // convexConvexTest (shape.go:438-479)
-                visit_poly_poly(PA, PB, [&](V2 pt, int j) {
-                    if (w < n) store_contact(out + w, pt, edge_normal(PB.get(j), PB.line_end(j)));
-                    w++;
-                });
+                if (use_mask) {
+                    // second pass only over the edge pairs that crossed in the first
+                    for (unsigned long long m = xmask; m && w < n; m &= m - 1) {
+                        int idx = __ffsll((long long)m) - 1;
+                        int j = idx / PA.nl, i = idx - j * PA.nl;
+                        V2 pt;
+                        line_x_line(PA.get(i), PA.line_end(i), PB.get(j), PB.line_end(j), pt);
+                        store_contact(out + w, pt, edge_normal(PB.get(j), PB.line_end(j)));
+                        w++;
+                    }
+                } else {
+                    visit_poly_poly(PA, PB, [&](V2 pt, int j, int) {
+                        if (w < n) store_contact(out + w, pt, edge_normal(PB.get(j), PB.line_end(j)));
+                        w++;
+                    });
+                }
                 Box ba = load_box_nc(d.aabb + A), bb = load_box_nc(d.aabb + B);
                 V2 ca = box_center(ba);
                 sort_contacts(out, (int)n, ca);

@@ -1,4 +1,4 @@
-// rsv_pairs.cuh — candidate-pair emitter.
+// rsv_pairs.cuh — warp-cooperative candidate-pair emitter.
 //
 // Replaces, for every tester A at once,
 //   A.SelectTouchingCells(margin)            shape.go:220-237   (cell rect grown by margin, not clamped)
@@ -14,137 +14,358 @@
 // and (y is B's first row or y is the walk's first row) — two flag bits stored in the entry, no gather of B's rect.
 // Emission order per tester therefore equals the reference's candidate generation order (for a Space whose
 // cells are in append order), and `rank` is the candidate's index in possibleIntersections before the sort.
+//
+// Work distribution
+//  * Testers are taken in CELL ORDER straight from the sorted entry array: the entry carrying both first-row and
+//    first-column flags is the shape's "home" registration, so ballot-compacting those entries yields testers
+//    sorted by home cell for free; a warp's 32 testers walk overlapping cell rows. Warps grab chunks of the entry
+//    array from an atomic cursor. Testers that touch no stored cell but whose margin reaches the grid come from a
+//    small orphan list built by k_bounds.
+//  * A cell row of a query rect is ONE contiguous run of the entry array (cells are consecutive in a row), so a
+//    tester's walk is rows x (3 offsets + a run). Rows are taken four at a time: the warp prefix-sums the run
+//    lengths, flattens the (tester, entry) items and moves them 32 per step with cp.async into shared memory — all
+//    loads of a round are in flight together (the kernel is latency-bound otherwise) — then tests them from shared
+//    memory, every lane one item per step no matter how entries are distributed over testers.
+//  * Each entry carries an outward-rounded float32 copy of its shape's AABB. Disjoint float boxes imply disjoint
+//    float64 boxes, so ~90 % of candidates are rejected without touching the other shape's data; survivors are
+//    staged and take the exact float64 Bounds gate (utils.go:146-173) densely, one record per lane.
+//  * Records are written with one allocation per batch, 16 B per lane, grouped by tester in generation order. A
+//    batch that overflows the stage falls back to an inline count pass + direct-write pass.
 #pragma once
+#include <cuda_pipeline.h>
+
 #include "rsv_device.cuh"
 #include "rsv_grid.cuh"
 
 namespace rsv {
 
 constexpr int kPairsBlock = 128;
-constexpr int kStash = 8;  // pair records a thread can hold in shared memory before it needs a second walk
+constexpr int kPairsWarps = kPairsBlock / 32;
+constexpr int kPairsChunk = 256;  // entries per grabbed chunk
+constexpr int kPairStage = 128;   // staged records per warp batch
+constexpr int kRowGroup = 4;      // query-rect rows flattened together
+constexpr int kItemRound = 160;   // items staged through shared memory per round
+constexpr uint32_t kNoEntry = 0xffffffffu;
 
-// Walks tester A's query rect and calls emit(b, rank, gated) for every candidate in generation order.
-// Returns the number of candidates (P_A).
-template <class Emit>
-__device__ __forceinline__ uint32_t walk_candidates(const DevView& d, uint32_t A, uint32_t metaA, int margin,
-                                                    Emit emit) {
-    int4 r = d.crect[A];
-    int qx0 = max(r.x - margin, 0), qx1 = min(r.z + margin, d.W - 1);
-    int qy0 = max(r.y - margin, d.row_lo), qy1 = min(r.w + margin, d.row_hi - 1);
-    if (qx0 > qx1 || qy0 > qy1) return 0;
-    const Box a = load_box_nc(d.aabb + A);
-    const bool useAny = (metaA & RSV_META_USE_ANY) != 0;
-    ulonglong2 qm = __ldg(d.qmask + A);
-    const bool filtered = useAny || qm.y != 0;
-    const uint32_t base = cell_base(d, A);
-    uint32_t rank = 0;
-    for (int y = qy0; y <= qy1; y++) {
-        const uint32_t* row = d.cell + base + (uint32_t)(y - d.row_lo) * (uint32_t)d.W;
-        uint32_t e = row[qx0];
-        for (int x = qx0; x <= qx1; x++) {
-            uint32_t s = e;
-            e = row[x + 1];
-            uint32_t lim = min(e, d.cap_entries);
-            for (uint32_t k = s; k < lim; k++) {
-                uint32_t ent = d.entries[k];
-                uint32_t B = ent >> 3;
-                if (B == A) continue;                                         // cell.go:101, shape.go:279
-                if (!((ent & kEntFirstCol) || x == qx0)) continue;            // owner-cell rule == cell.go:105
-                if (!((ent & kEntFirstRow) || y == qy0)) continue;
-                if (filtered) {
-                    unsigned long long t = __ldg(d.tags + B);
-                    if (useAny && (t & qm.x) == 0) continue;                  // ByTags: Has == any bit, tags.go:29-31
-                    if ((t & qm.y) != 0) continue;                            // NotByTags
+struct PairsWarpSmem {
+    float4 itBox[kItemRound];   // cp.async landing zone: entry float boxes
+    float4 fbox[32];            // outward-rounded float AABB of each tester of the batch
+    uint4 cum[32];              // per tester: cumulative run lengths of the current row group
+    uint2 run[kRowGroup][32];   // per (row, tester): (start of run, end of the run's first cell)
+    unsigned long long any[32], none[32];
+    uint32_t itEnt[kItemRound]; // cp.async landing zone: entry words
+    uint16_t itMeta[kItemRound];  // tester lane | first-column-cell << 5 | first-row << 6
+    uint32_t queue[64];         // home entries waiting for a full batch
+    uint32_t A[32];             // tester slot
+    uint32_t flags[32];         // bit0 useAny, bit1 filtered
+    uint32_t cand[32];          // candidates so far (== next rank)
+    uint32_t gated[32];         // records so far
+    uint32_t excl[32];          // exclusive prefix of gated over the batch
+    uint32_t stB[kPairStage];   // staged records: other slot
+    uint32_t stR[kPairStage];   // rank << 8 | flags
+    uint32_t stT[kPairStage];   // tester lane << 24 | index within the tester's records
+};
+
+enum PairsMode { kStage = 0, kCount = 1, kWrite = 2 };
+
+__device__ __forceinline__ bool exact_gate(const DevView& d, uint32_t A, uint32_t B) {
+    const Box a = load_box_nc(d.aabb + A), o = load_box_nc(d.aabb + B);
+    return bounds_gate(a.minx, a.miny, a.maxx, a.maxy, o.minx, o.miny, o.maxx, o.maxy);
+}
+
+// One pass over all (tester, entry) items of the batch.
+//  kStage: count candidates; stage every candidate that survives the float gate (or every candidate in `all` mode).
+//  kCount: count candidates and records with the exact gate inline.   kWrite: same walk, records written in place.
+// Returns the number of staged (kStage) or produced (kCount/kWrite) records; uniform across the warp.
+template <int MODE>
+__device__ __forceinline__ uint32_t pairs_pass(const DevView& d, bool all, PairsWarpSmem& sm, bool have, int rows,
+                                               const uint32_t* row0, int ncols, uint32_t chunk) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t produced = 0;
+    for (int g = 0; __any_sync(0xffffffffu, have && g < rows); g += kRowGroup) {
+        uint32_t s0[kRowGroup], s1[kRowGroup], e[kRowGroup];
+#pragma unroll
+        for (int r = 0; r < kRowGroup; r++) {
+            s0[r] = s1[r] = e[r] = 0;
+            if (have && g + r < rows) {
+                const uint32_t* row = row0 + (size_t)(g + r) * (size_t)d.W;
+                s0[r] = row[0];
+                s1[r] = row[1];
+                e[r] = ncols > 1 ? row[ncols] : s1[r];
+            }
+        }
+        uint32_t c = 0;
+        uint32_t cum[kRowGroup];
+#pragma unroll
+        for (int r = 0; r < kRowGroup; r++) {
+            s0[r] = min(s0[r], d.cap_entries); s1[r] = min(s1[r], d.cap_entries); e[r] = min(e[r], d.cap_entries);
+            c += e[r] - s0[r];
+            cum[r] = c;
+            sm.run[r][lane] = make_uint2(s0[r], s1[r]);
+        }
+        sm.cum[lane] = make_uint4(cum[0], cum[1], cum[2], cum[3]);
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        __syncwarp();
+        for (uint32_t rbeg = 0; rbeg < total; rbeg += kItemRound) {
+            const uint32_t rend = min(rbeg + (uint32_t)kItemRound, total);
+            // ---- issue: locate every item of the round and start its copy into shared memory
+            for (uint32_t it = rbeg; it < rend; it += 32) {
+                const uint32_t i = min(it + lane, total - 1);  // (clamped lanes search too: shuffles need the full warp)
+                // owner tester t: smallest lane with incl[t] > i (5-step search over the warp's prefix sums)
+                int t = 0;
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    uint32_t v = __shfl_sync(0xffffffffu, incl, t + step - 1);
+                    if (v <= i) t += step;
                 }
-                Box o = load_box_nc(d.aabb + B);
-                bool gated = bounds_gate(a.minx, a.miny, a.maxx, a.maxy, o.minx, o.miny, o.maxx, o.maxy);
-                emit(B, rank, gated);
-                rank++;
+                t &= 31;
+                const uint32_t t_incl = __shfl_sync(0xffffffffu, incl, t);
+                if (it + lane < rend) {
+                    const uint4 tc = sm.cum[t];
+                    const uint32_t off = i - (t_incl - tc.w);
+                    const int r = (off >= tc.x) + (off >= tc.y) + (off >= tc.z);
+                    const uint32_t rb = r == 0 ? 0u : (r == 1 ? tc.x : (r == 2 ? tc.y : tc.z));
+                    const uint2 rn = sm.run[r][t];
+                    const uint32_t k = rn.x + (off - rb);
+                    const uint32_t slot = i - rbeg;
+                    __pipeline_memcpy_async(&sm.itEnt[slot], d.entries + k, 4);
+                    __pipeline_memcpy_async(&sm.itBox[slot], d.ent_box + k, 16);
+                    sm.itMeta[slot] = (uint16_t)(t | (k < rn.y ? 32 : 0) | ((g + r) == 0 ? 64 : 0));
+                }
+            }
+            __pipeline_commit();
+            __pipeline_wait_prior(0);
+            __syncwarp();
+            // ---- test: one item per lane per step, from shared memory
+            for (uint32_t it = rbeg; it < rend; it += 32) {
+                const uint32_t i = it + lane;
+                const bool valid = i < rend;
+                bool cand = false, maybe = false, gate = false;
+                uint32_t B = 0, t = 0;
+                if (valid) {
+                    const uint32_t slot = i - rbeg;
+                    const uint32_t ent = sm.itEnt[slot];
+                    const uint32_t m = sm.itMeta[slot];
+                    t = m & 31u;
+                    B = ent >> 3;
+                    cand = B != sm.A[t]                                     // cell.go:101, shape.go:279
+                           && ((ent & kEntFirstCol) || (m & 32u))           // owner-cell rule == cell.go:105
+                           && ((ent & kEntFirstRow) || (m & 64u));
+                    const uint32_t fl = sm.flags[t];
+                    if (cand && (fl & 2u)) {
+                        const unsigned long long tg = __ldg(d.tags + B);
+                        if ((fl & 1u) && (tg & sm.any[t]) == 0) cand = false;   // ByTags: Has == any bit, tags.go:29-31
+                        if ((tg & sm.none[t]) != 0) cand = false;              // NotByTags
+                    }
+                    const float4 fb = sm.itBox[slot], fa = sm.fbox[t];
+                    // float boxes are rounded outward, so "disjoint in float" implies the exact reject of utils.go:156
+                    maybe = cand && !(fb.z < fa.x || fb.x > fa.z || fb.w < fa.y || fb.y > fa.w);
+                    if (MODE != kStage && maybe) gate = exact_gate(d, sm.A[t], B);
+                }
+                const uint32_t peers = __match_any_sync(0xffffffffu, valid ? t : 32 + lane);
+                const uint32_t cmask = __ballot_sync(0xffffffffu, cand);
+                const uint32_t rank = sm.cand[t] + __popc(cmask & peers & lt);
+                const bool rec = MODE == kStage ? (maybe || (all && cand)) : (gate || (all && cand));
+                const uint32_t rmask = __ballot_sync(0xffffffffu, rec);
+                uint32_t gidx = 0;
+                if (MODE != kStage) gidx = sm.gated[t] + __popc(rmask & peers & lt);
+                __syncwarp();
+                if (valid && (peers & lt) == 0) {  // first lane of each tester's run updates its counters
+                    sm.cand[t] += __popc(cmask & peers);
+                    if (MODE != kStage) sm.gated[t] += __popc(rmask & peers);
+                }
+                if (rec) {
+                    if (MODE == kStage) {
+                        const uint32_t slot = produced + __popc(rmask & lt);
+                        if (slot < kPairStage) {
+                            sm.stB[slot] = B;
+                            sm.stR[slot] = (rank << 8) | (maybe ? 0u : RSV_HIT_NOT_GATED);
+                            sm.stT[slot] = t << 24;
+                        }
+                    } else if (MODE == kWrite) {
+                        const unsigned long long pos = (unsigned long long)chunk + sm.excl[t] + gidx;
+                        if (pos < d.cap_pairs)
+                            *reinterpret_cast<uint4*>(d.hits + pos) =
+                                make_uint4(sm.A[t], B, 0u, (rank << 8) | (gate ? 0u : RSV_HIT_NOT_GATED));
+                    }
+                }
+                produced += __popc(rmask);
+                __syncwarp();
             }
         }
     }
-    return rank;
+    return produced;
 }
 
-// One thread per tester. Each thread keeps its first kStash records in shared memory, the block allocates one
-// contiguous chunk of the record buffer (one atomic per block) and writes it tester by tester, so all records of
-// a tester are contiguous and in generation order. Threads with more than kStash records walk a second time.
-__global__ void __launch_bounds__(kPairsBlock) k_pairs(DevView d, int margin, uint32_t flags) {
-    __shared__ uint2 s_stash[kStash][kPairsBlock];
-    __shared__ uint32_t s_warp[kPairsBlock / 32];
-    __shared__ uint32_t s_chunk;
+// Exact float64 Bounds gate over the staged records, one record per lane, in stage order (which is rank order
+// within every tester). Assigns each surviving record its index within its tester.
+__device__ __forceinline__ uint32_t pairs_exact_gate(const DevView& d, bool all, PairsWarpSmem& sm, uint32_t staged) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t produced = 0;
+    for (uint32_t base = 0; base < staged; base += 32) {
+        const uint32_t r = base + lane;
+        const bool valid = r < staged;
+        uint32_t t = 0, word = 0;
+        bool gate = false;
+        if (valid) {
+            t = sm.stT[r] >> 24;
+            word = sm.stR[r];
+            if (!(word & RSV_HIT_NOT_GATED)) gate = exact_gate(d, sm.A[t], sm.stB[r]);
+        }
+        const bool rec = valid && (gate || all);
+        const uint32_t peers = __match_any_sync(0xffffffffu, valid ? t : 32 + lane);
+        const uint32_t rmask = __ballot_sync(0xffffffffu, rec);
+        const uint32_t gidx = sm.gated[t] + __popc(rmask & peers & lt);
+        __syncwarp();
+        if (valid) {
+            if ((peers & lt) == 0) sm.gated[t] += __popc(rmask & peers);
+            sm.stR[r] = (word & ~(uint32_t)RSV_HIT_NOT_GATED) | (gate ? 0u : RSV_HIT_NOT_GATED);
+            sm.stT[r] = rec ? ((t << 24) | (gidx & 0xffffffu)) : 0xffffffffu;
+        }
+        produced += __popc(rmask);
+        __syncwarp();
+    }
+    return produced;
+}
+
+// One batch: lane `lane` owns a tester, given by its home entry index `hk` (or, for orphans, directly by slot A).
+__device__ __forceinline__ void pairs_batch(const DevView& d, int margin, uint32_t flags, bool have, uint32_t hk,
+                                            uint32_t A, PairsWarpSmem& sm, unsigned long long& my_cands) {
+    const int lane = threadIdx.x & 31;
     const bool all = (flags & RSV_FRAME_ALL_CANDIDATES) != 0;
+    int rows = 0, ncols = 0;
+    const uint32_t* row0 = d.cell;
+    if (have) {
+        if (hk != kNoEntry) {
+            A = d.entries[hk] >> 3;
+            sm.fbox[lane] = d.ent_box[hk];
+        } else {
+            sm.fbox[lane] = float_box(load_box_nc(d.aabb + A));
+        }
+        const uint32_t metaA = __ldg(d.meta + A);
+        const int4 r = d.crect[A];
+        const int qx0 = max(r.x - margin, 0), qx1 = min(r.z + margin, d.W - 1);
+        const int qy0 = max(r.y - margin, d.row_lo), qy1 = min(r.w + margin, d.row_hi - 1);
+        if (qx0 <= qx1 && qy0 <= qy1) {
+            rows = qy1 - qy0 + 1;
+            ncols = qx1 - qx0 + 1;
+            row0 = d.cell + cell_base(d, A) + (size_t)(qy0 - d.row_lo) * (size_t)d.W + qx0;
+        }
+        const bool filters = !(flags & RSV_FRAME_NO_TAG_FILTERS);
+        const bool useAny = filters && (metaA & RSV_META_USE_ANY) != 0;
+        ulonglong2 qm = make_ulonglong2(0ull, 0ull);
+        if (filters) qm = __ldg(d.qmask + A);
+        sm.any[lane] = qm.x; sm.none[lane] = qm.y;
+        sm.flags[lane] = (useAny ? 1u : 0u) | ((useAny || qm.y != 0) ? 2u : 0u);
+    }
+    sm.A[lane] = A;
+    sm.cand[lane] = 0;
+    sm.gated[lane] = 0;
+    __syncwarp();
+    const uint32_t staged = pairs_pass<kStage>(d, all, sm, have, rows, row0, ncols, 0u);
+    const bool fits = staged <= kPairStage;
+    uint32_t total;
+    if (fits) {
+        total = pairs_exact_gate(d, all, sm, staged);
+    } else {
+        sm.cand[lane] = 0;
+        __syncwarp();
+        total = pairs_pass<kCount>(d, all, sm, have, rows, row0, ncols, 0u);
+    }
+    const uint32_t cnt = sm.gated[lane];
+    my_cands += sm.cand[lane];
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    uint32_t chunk = 0;
+    if (lane == 0 && total) {
+        chunk = atomicAdd(&d.ctr->pair_cursor, total);
+        if (chunk + total > d.cap_pairs || chunk + total < chunk) atomicOr(&d.ctr->overflow, RSV_OVF_PAIRS);
+    }
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    sm.excl[lane] = inc - cnt;
+    if (have && (flags & RSV_FRAME_TESTER_TABLE)) {
+        d.tester_start[A] = chunk + (inc - cnt);
+        d.tester_count[A] = cnt;
+    }
+    __syncwarp();
+    if (total == 0) return;
+    if (fits) {
+        for (uint32_t r = lane; r < staged; r += 32) {
+            const uint32_t tt = sm.stT[r];
+            if (tt == 0xffffffffu) continue;
+            const uint32_t t = tt >> 24;
+            const unsigned long long pos = (unsigned long long)chunk + sm.excl[t] + (tt & 0xffffffu);
+            if (pos < d.cap_pairs) *reinterpret_cast<uint4*>(d.hits + pos) = make_uint4(sm.A[t], sm.stB[r], 0u, sm.stR[r]);
+        }
+    } else {
+        sm.cand[lane] = 0;
+        sm.gated[lane] = 0;
+        __syncwarp();
+        pairs_pass<kWrite>(d, all, sm, have, rows, row0, ncols, chunk);
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(kPairsBlock) k_pairs(DevView d, int margin, uint32_t flags) {
+    __shared__ PairsWarpSmem s_warp[kPairsWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    PairsWarpSmem& sm = s_warp[warp];
+    uint32_t* q = sm.queue;
     unsigned long long my_cands = 0;
-    const uint32_t rounds = (d.n_shapes + gridDim.x * kPairsBlock - 1) / (gridDim.x * kPairsBlock);
-    for (uint32_t it = 0; it < rounds; it++) {
-        const uint32_t A = (it * gridDim.x + blockIdx.x) * kPairsBlock + threadIdx.x;
-        uint32_t metaA = 0;
-        bool active = false;
-        if (A < d.n_shapes) {
-            metaA = __ldg(d.meta + A);
-            active = (metaA & RSV_META_TESTER) && !(metaA & RSV_META_ABSENT);
-        }
-        uint32_t cnt = 0;
-        if (active) {
-            uint32_t P = walk_candidates(d, A, metaA, margin, [&](uint32_t B, uint32_t rank, bool gated) {
-                if (gated || all) {
-                    if (cnt < kStash) s_stash[cnt][threadIdx.x] = make_uint2(B, (rank << 8) | (gated ? 0u : RSV_HIT_NOT_GATED));
-                    cnt++;
-                }
-            });
-            my_cands += P;
-        }
-        // block-wide exclusive scan of cnt
-        uint32_t inc = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
-        }
-        if (lane == 31) s_warp[warp] = inc;
-        __syncthreads();
-        uint32_t off = inc - cnt, total = 0;
-#pragma unroll
-        for (int w = 0; w < kPairsBlock / 32; w++) {
-            uint32_t t = s_warp[w];
-            if (w < warp) off += t;
-            total += t;
-        }
-        if (threadIdx.x == 0) {
-            uint32_t chunk = 0;
-            if (total) {
-                chunk = atomicAdd(&d.ctr->pair_cursor, total);
-                atomicAdd(&d.ctr->n_pairs_needed, (unsigned long long)total);
-                if (chunk + total > d.cap_pairs || chunk + total < chunk) atomicOr(&d.ctr->overflow, RSV_OVF_PAIRS);
-            }
-            s_chunk = chunk;
-        }
-        __syncthreads();
-        const uint32_t start = s_chunk + off;
-        if (A < d.n_shapes) {
-            d.tester_start[A] = start;
-            d.tester_count[A] = cnt;
-        }
-        if (cnt && (unsigned long long)start + cnt <= d.cap_pairs) {
-            uint32_t n0 = min(cnt, (uint32_t)kStash);
-            for (uint32_t k = 0; k < n0; k++) {
-                uint2 sb = s_stash[k][threadIdx.x];
-                *reinterpret_cast<uint4*>(d.hits + start + k) = make_uint4(A, sb.x, 0u, sb.y);
-            }
-            if (cnt > kStash) {
-                uint32_t k = 0;
-                walk_candidates(d, A, metaA, margin, [&](uint32_t B, uint32_t rank, bool gated) {
-                    if (gated || all) {
-                        if (k >= kStash)
-                            *reinterpret_cast<uint4*>(d.hits + start + k) =
-                                make_uint4(A, B, 0u, (rank << 8) | (gated ? 0u : RSV_HIT_NOT_GATED));
-                        k++;
-                    }
-                });
+    const uint32_t R = (uint32_t)min((unsigned long long)d.cap_entries, d.ctr->n_entries);
+    const uint32_t n_chunks = (R + kPairsChunk - 1) / kPairsChunk;
+    uint32_t qn = 0;
+    for (;;) {
+        uint32_t c = 0;
+        if (lane == 0) c = atomicAdd(&d.ctr->chunk_cursor, 1u);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        if (c >= n_chunks) break;
+        const uint32_t lo = c * kPairsChunk, hi = min(lo + kPairsChunk, R);
+        for (uint32_t base = lo; base < hi; base += 32) {
+            uint32_t k = base + lane;
+            uint32_t ent = k < hi ? d.entries[k] : 0u;
+            const uint32_t want = kEntTester | kEntFirstCol | kEntFirstRow;   // the tester's home registration
+            bool home = (ent & want) == want;
+            uint32_t m = __ballot_sync(0xffffffffu, home);
+            if (home) q[qn + __popc(m & ((1u << lane) - 1u))] = k;
+            qn += __popc(m);
+            __syncwarp();
+            if (qn >= 32) {
+                uint32_t hk = q[lane];
+                __syncwarp();
+                pairs_batch(d, margin, flags, true, hk, 0u, sm, my_cands);
+                if (lane + 32 < qn) { uint32_t t = q[lane + 32]; q[lane] = t; }
+                qn -= 32;
+                __syncwarp();
             }
         }
-        __syncthreads();  // s_stash / s_warp are reused by the next round
+    }
+    if (qn) {
+        uint32_t hk = lane < qn ? q[lane] : kNoEntry;
+        pairs_batch(d, margin, flags, lane < qn, hk, 0u, sm, my_cands);
+    }
+    // testers with no stored cell whose margin still reaches the grid
+    const uint32_t n_orph = min(d.ctr->n_orphans, d.n_shapes);
+    for (;;) {
+        uint32_t o = 0;
+        if (lane == 0) o = atomicAdd(&d.ctr->orphan_cursor, 32u);
+        o = __shfl_sync(0xffffffffu, o, 0);
+        if (o >= n_orph) break;
+        bool have = o + lane < n_orph;
+        uint32_t A = have ? d.orphans[o + lane] : 0u;
+        pairs_batch(d, margin, flags, have, kNoEntry, A, sm, my_cands);
     }
     for (int o = 16; o > 0; o >>= 1) my_cands += __shfl_down_sync(0xffffffffu, my_cands, o);
     if (lane == 0 && my_cands) atomicAdd(&d.ctr->n_candidates, my_cands);
