@@ -353,6 +353,7 @@ int32_t rsv_frame_launch(rsv_space* s, int32_t margin, uint32_t flags) {
     if (d.n_shapes) k_scatter<<<blocks_for(d.n_shapes, kGridBlock, gcap), kGridBlock, 0, st>>>(d);
     mark(RSV_K_CELLSORT);
     k_cellsort<<<blocks_for(d.n_cells, kGridBlock, gcap), kGridBlock, 0, st>>>(d);
+    k_entboxes<<<gcap, kGridBlock, 0, st>>>(d);
     mark(RSV_K_PAIRS);
     if (d.n_shapes) k_pairs<<<s->pairs_blocks, kPairsBlock, 0, st>>>(d, margin, flags);
     mark(RSV_K_NARROW);

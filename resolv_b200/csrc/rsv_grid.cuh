@@ -191,15 +191,12 @@ __global__ void __launch_bounds__(kGridBlock) k_scatter(DevView d) {
         uint32_t meta = __ldg(d.meta + i);
         uint32_t base = cell_base(d, i);
         uint32_t tag = (i << 3) | ((meta & RSV_META_TESTER) ? kEntTester : 0u);
-        const float4 fb = float_box(load_box_nc(d.aabb + i));
         for (int y = y0; y <= y1; y++) {
             uint32_t row = base + (uint32_t)(y - d.row_lo) * (uint32_t)d.W;
             for (int x = x0; x <= x1; x++) {
                 uint32_t slot = atomicAdd(d.cell + row + x + 1, 1u);
-                if (slot < d.cap_entries) {
+                if (slot < d.cap_entries)
                     d.entries[slot] = tag | (x == x0 ? kEntFirstCol : 0u) | (y == y0 ? kEntFirstRow : 0u);
-                    d.ent_box[slot] = fb;
-                }
             }
         }
     }
@@ -211,18 +208,22 @@ __global__ void __launch_bounds__(kGridBlock) k_cellsort(DevView d) {
         uint32_t s = d.cell[c], e = d.cell[c + 1];
         if (e - s < 2 || e > d.cap_entries) continue;
         uint32_t* a = d.entries + s;
-        float4* b = d.ent_box + s;
         uint32_t n = e - s;
         for (uint32_t i = 1; i < n; i++) {
             uint32_t key = a[i];
-            if (a[i - 1] <= key) continue;
-            float4 kb = b[i];
             uint32_t j = i;
-            while (j > 0 && a[j - 1] > key) { a[j] = a[j - 1]; b[j] = b[j - 1]; j--; }
+            while (j > 0 && a[j - 1] > key) { a[j] = a[j - 1]; j--; }
             a[j] = key;
-            b[j] = kb;
         }
     }
+}
+
+// Fills the per-entry float32 boxes in final (sorted) entry order: one gather of the shape's AABB per entry,
+// coalesced 16 B stores. (Writing them from k_scatter instead would be 16 B stores to random slots.)
+__global__ void __launch_bounds__(kGridBlock) k_entboxes(DevView d) {
+    const uint32_t R = (uint32_t)min((unsigned long long)d.cap_entries, d.ctr->n_entries);
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < R; k += gridDim.x * blockDim.x)
+        d.ent_box[k] = float_box(load_box_nc(d.aabb + (d.entries[k] >> 3)));
 }
 
 }  // namespace rsv
