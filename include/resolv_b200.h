@@ -192,6 +192,67 @@ int32_t rsv_sync(rsv_space* s);
 int32_t rsv_timer_start(rsv_space* s);
 int32_t rsv_timer_stop(rsv_space* s, float* ms);
 
+/* ---- line tests ----------------------------------------------------------------------------------------- */
+/* Batched LineTest (utils.go:276-370): for every ray i,
+ *   LineTest(LineTestSettings{Start, End, TestAgainst: <iterator>[.ByTags(any)][.NotByTags(none)], OnIntersect: <record>})
+ * against the grid built by the last rsv_frame (use RSV_FRAME_GRID_ONLY to build the grid without shape tests).
+ * Iterator, default:  space.FilterCells(Bounds of the cast line).FilterShapes()  (space.go:181-195, cell.go:73-121),
+ * the cast line being (Start - 0.01 * Unit(End - Start)) -> End (utils.go:278-282).
+ * Iterator, RSV_LINE_DDA: the shapes registered in the cells a grid traversal of the cast line passes through (the
+ * reference never shipped its cell-walking line query, space.go:197-253; see rsv_lines.cuh for the exact rule and
+ * for the one documented deviation, "phantom" contacts of the +1 fudge on far-away near-parallel edges).
+ * ShapeLineTest (convexPolygon.go:322-415) is built on this by the host layer: one ray per selected vertex. */
+#define RSV_LINE_DDA 0x100u
+#define RSV_LINE_RESIDENT 0x200u /* rays of the previous call are still on the device: skip their upload */
+#define RSV_FRAME_GRID_ONLY 0x20u /* rsv_frame: rebuild the grid only (no candidate pairs, no narrowphase) */
+#define RSV_OVF_RAY_HITS 0x8u
+#define RSV_OVF_RAY_CONTACTS 0x10u
+
+/* One record per (ray, shape) with a non-empty contact set == one IntersectionSet of LineTest (contactSet.go:15-20).
+ * All records of a ray are contiguous (ray_first / ray_count) and in candidate generation order; OnIntersect order
+ * is ascending `key`, ties by generation rank (utils.go:355-357 with sort.Slice's insertion sort, n <= 12). */
+typedef struct rsv_ray_hit {
+    uint32_t ray;           /* index of the ray in the batch */
+    uint32_t b;             /* IntersectionSet.OtherShape slot */
+    uint32_t first_contact; /* index into the ray contact buffer; contacts sorted by distance to Start (utils.go:340-342) */
+    uint32_t count_rank;    /* n_contacts in bits 0..7, candidate generation rank in bits 8..31 */
+    double mtv_x, mtv_y;       /* IntersectionSet.MTV = contacts[0].Point - Start - 0.01 * vu (utils.go:344) */
+    double center_x, center_y; /* IntersectionSet.Center (utils.go:332-337) */
+    double key;                /* d2(contacts[0].Point, cast line start): the sort key of utils.go:355-357 */
+    double pad;
+} rsv_ray_hit;
+
+typedef struct rsv_ray_counts {
+    uint64_t n_rays;
+    uint64_t n_candidates; /* (ray, shape) pairs tested after dedupe + tag filters */
+    uint64_t n_hits;       /* IntersectionSets */
+    uint64_t n_contacts;
+    uint32_t overflow;     /* RSV_OVF_RAY_* */
+    uint32_t reserved;
+    float kernel_us;       /* device time of the line kernel (CUDA events on the space's stream) */
+    float reserved2;
+} rsv_ray_counts;
+
+typedef struct rsv_ray_results {
+    const rsv_ray_hit* hits;
+    uint64_t n_hits;
+    const rsv_contact* contacts;
+    uint64_t n_contacts;
+    const uint32_t* ray_first; /* per ray: first hit record */
+    const uint32_t* ray_count; /* per ray: number of hit records */
+    uint64_t n_rays;
+} rsv_ray_results;
+
+/* Pinned ray staging: which = 0: f64[4*max_rays] (Start.X, Start.Y, End.X, End.Y);
+ * which = 1: u64[3*max_rays] (ByTags mask, OR of NotByTags masks, bit0 = chain has ByTags | space index << 32). */
+void* rsv_ray_staging(rsv_space* s, int32_t which, size_t* bytes);
+int32_t rsv_ray_reserve(rsv_space* s, uint32_t max_hits, uint32_t max_contacts);
+/* flags: RSV_FRAME_DOWNLOAD | RSV_LINE_DDA | RSV_LINE_RESIDENT */
+int32_t rsv_linetest(rsv_space* s, uint32_t n_rays, uint32_t flags, rsv_ray_counts* out);
+int32_t rsv_linetest_launch(rsv_space* s, uint32_t n_rays, uint32_t flags);
+int32_t rsv_linetest_finish(rsv_space* s, rsv_ray_counts* out);
+int32_t rsv_ray_results_view(rsv_space* s, rsv_ray_results* out);
+
 /* ---- parity / debug dumps --------------------------------------------------------------------------------- */
 /* Cell membership after the last frame: cell_end[c] (exclusive end offset of cell c in `entries`, cells row-major,
  * spaces concatenated; start = cell_end[c-1] or 0) and the shape slots per cell in ascending slot order. Either

@@ -75,6 +75,8 @@ def lib():
     L.orc_intersection.argtypes = [vp, i32, i32, P(f64), P(f64), i32]
     L.orc_frame.argtypes = [vp, i32, P(C.c_uint8), P(C.c_uint8), P(u64), P(u64), i32, i32, P(FrameCounts)]
     L.orc_linetest.argtypes = [vp, P(f64), i32, P(C.c_uint8), P(u64), P(u64), i32, i32, P(FrameCounts)]
+    L.orc_linetest_ex.argtypes = [vp, P(f64), i32, P(C.c_uint8), P(u64), P(u64), i32, i32, P(FrameCounts), i32,
+                                  P(C.c_uint32), P(u64)]
     L.orc_shape_linetest.restype = i32
     L.orc_shape_linetest.argtypes = [vp, i32, f64, f64, f64, f64, i32, i32, i32, u64, u64]
     for n in ("orc_num_candidates", "orc_num_hits", "orc_num_contacts"):
@@ -251,16 +253,29 @@ class OracleSpace:
                      rank=_arr(L.orc_cand_rank(h), P, np.uint32), dist=_arr(L.orc_cand_dist(h), P, np.float64))
         return fc, cands, self._hits()
 
-    def linetest(self, rays, use_any=None, any_mask=None, none_mask=None, record=True, threads=1):
-        """Batched LineTest over space.FilterShapes() (brute force, as the reference has no line broadphase)."""
+    def linetest(self, rays, use_any=None, any_mask=None, none_mask=None, record=True, threads=1, mode="all",
+                 candidates=None):
+        """Batched LineTest. mode "all": TestAgainst = space.FilterShapes() (brute force, the reference has no line
+        broadphase); "rect": space.FilterCells(bounds of the cast line).FilterShapes(); "list": an explicit
+        ShapeCollection per ray (candidates = list of index arrays, iterated in the given order)."""
         rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 4)
         n = len(rays)
         use_any = None if use_any is None else np.ascontiguousarray(use_any, dtype=np.uint8)
         any_mask = np.zeros(n, dtype=np.uint64) if any_mask is None else np.ascontiguousarray(any_mask, dtype=np.uint64)
         none_mask = None if none_mask is None else np.ascontiguousarray(none_mask, dtype=np.uint64)
+        m = {"all": 0, "rect": 1, "list": 2}[mode]
+        cand = off = None
+        if m == 2:
+            off = np.zeros(n + 1, dtype=np.uint64)
+            off[1:] = np.cumsum([len(c) for c in candidates])
+            cand = np.ascontiguousarray(np.concatenate([np.asarray(c, dtype=np.uint32) for c in candidates] + [np.zeros(0, np.uint32)]),
+                                        dtype=np.uint32)
+            if cand.size == 0:
+                cand = np.zeros(1, dtype=np.uint32)
         fc = FrameCounts()
-        self.L.orc_linetest(self.h, _ptr(rays, C.c_double), n, _ptr(use_any, C.c_uint8), _ptr(any_mask, C.c_uint64),
-                            _ptr(none_mask, C.c_uint64), int(record), threads, C.byref(fc))
+        self.L.orc_linetest_ex(self.h, _ptr(rays, C.c_double), n, _ptr(use_any, C.c_uint8), _ptr(any_mask, C.c_uint64),
+                               _ptr(none_mask, C.c_uint64), int(record), threads, C.byref(fc), m, _ptr(cand, C.c_uint32),
+                               _ptr(off, C.c_uint64))
         return fc, (self._hits(with_center=True) if record else None)
 
     def shape_linetest(self, shape, vec, start_offset=(0.0, 0.0), include_all=False, margin=1, use_any=False,

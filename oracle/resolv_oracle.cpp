@@ -1069,8 +1069,21 @@ const double* orc_hit_center(void* p) { return ((OrcWorld*)p)->hitCenter.data();
 // (space.go:106-110: every shape in the Space's list, in insertion order; no broadphase).
 // rays = (sx,sy,ex,ey)*n. Results land in the hit* / contacts arrays with hitA = ray index,
 // hitOrder = callback index, hitDist = d2(first contact, pulled-back start), hitCenter = set.Center.
+// mode 0: TestAgainst = space.FilterShapes() (brute force). mode 1: TestAgainst =
+// space.FilterCells(Bounds{componentwise min/max of the cast line's end points}).FilterShapes() (space.go:181-195).
+// mode 2: TestAgainst = the explicit ShapeCollection cand[cand_off[r] .. cand_off[r+1]) (shapefilter.go:193-202).
+void orc_linetest_ex(void* p, const double* rays, int nrays, const uint8_t* use_any, const uint64_t* any,
+                     const uint64_t* none, int record, int threads, OrcFrameCounts* out, int mode,
+                     const uint32_t* cand, const uint64_t* cand_off);
+
 void orc_linetest(void* p, const double* rays, int nrays, const uint8_t* use_any, const uint64_t* any,
                   const uint64_t* none, int record, int threads, OrcFrameCounts* out) {
+    orc_linetest_ex(p, rays, nrays, use_any, any, none, record, threads, out, 0, nullptr, nullptr);
+}
+
+void orc_linetest_ex(void* p, const double* rays, int nrays, const uint8_t* use_any, const uint64_t* any,
+                     const uint64_t* none, int record, int threads, OrcFrameCounts* out, int mode,
+                     const uint32_t* cand, const uint64_t* cand_off) {
     OrcWorld* w = (OrcWorld*)p;
     if (threads < 1) threads = 1;
     if (record) threads = 1;
@@ -1093,6 +1106,27 @@ void orc_linetest(void* p, const double* rays, int nrays, const uint8_t* use_any
             line_test(
                 S, E, nullptr,
                 [&](auto fn) {
+                    if (mode == 1) {
+                        Bounds b;                                           // Space.FilterCells (space.go:181-195)
+                        b.min = Vec{pulled.x < E.x ? pulled.x : E.x, pulled.y < E.y ? pulled.y : E.y};
+                        b.max = Vec{pulled.x < E.x ? E.x : pulled.x, pulled.y < E.y ? E.y : pulled.y};
+                        b.space = &w->space;
+                        long long r[4];
+                        to_cell_space(b, r);
+                        CellSelection sel{r[0], r[1], r[2], r[3], &w->space, nullptr};
+                        Scratch walk;
+                        filter_for_each(sel, f, walk, [&](Shape* s) { c.candidates++; fn(s); });
+                        return;
+                    }
+                    if (mode == 2) {
+                        for (uint64_t k = cand_off[r]; k < cand_off[r + 1]; k++) {
+                            Shape* s = w->all[cand[k]];
+                            if (!f.pass(s->tags)) continue;
+                            c.candidates++;
+                            fn(s);
+                        }
+                        return;
+                    }
                     for (Shape* s : w->space.shapes) {                      // shapefilter.go:196-202
                         if (!f.pass(s->tags)) continue;
                         c.candidates++;

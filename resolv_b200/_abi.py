@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "rsv_reserve", "rsv_staging", "rsv_set_counts", "rsv_commit", "rsv_device_buffer", "rsv_frame",
     "rsv_frame_launch", "rsv_frame_finish", "rsv_results_view", "rsv_timing", "rsv_sync", "rsv_timer_start",
     "rsv_timer_stop", "rsv_debug_cells", "rsv_debug_cell_rects", "rsv_linetest", "rsv_linetest_launch",
-    "rsv_linetest_finish", "rsv_ray_staging", "rsv_ray_results_view",
+    "rsv_linetest_finish", "rsv_ray_staging", "rsv_ray_reserve", "rsv_ray_results_view",
 ]
 
 
@@ -68,13 +68,15 @@ class RayCounts(C.Structure):
 
 
 class RayResults(C.Structure):
-    _fields_ = [("hits", C.c_void_p), ("n_hits", C.c_uint64), ("contacts", C.c_void_p), ("n_contacts", C.c_uint64)]
+    _fields_ = [("hits", C.c_void_p), ("n_hits", C.c_uint64), ("contacts", C.c_void_p), ("n_contacts", C.c_uint64),
+                ("ray_first", C.c_void_p), ("ray_count", C.c_void_p), ("n_rays", C.c_uint64)]
 
 
+LINE_DDA, LINE_RESIDENT, FRAME_GRID_ONLY = 0x100, 0x200, 0x20
 HIT_DTYPE = np.dtype([("a", np.uint32), ("b", np.uint32), ("first_contact", np.uint32), ("count_rank", np.uint32),
                       ("mtv", np.float64, (2,))])
 CONTACT_DTYPE = np.dtype([("p", np.float64, (2,)), ("n", np.float64, (2,))])
-RAY_HIT_DTYPE = np.dtype([("ray", np.uint32), ("b", np.uint32), ("first_contact", np.uint32), ("count", np.uint32),
+RAY_HIT_DTYPE = np.dtype([("ray", np.uint32), ("b", np.uint32), ("first_contact", np.uint32), ("count_rank", np.uint32),
                           ("mtv", np.float64, (2,)), ("center", np.float64, (2,)), ("key", np.float64), ("pad", np.float64)])
 
 
@@ -140,6 +142,8 @@ def load():
     if hasattr(L, "rsv_linetest"):
         L.rsv_ray_staging.restype = vp
         L.rsv_ray_staging.argtypes = [vp, i32, C.POINTER(C.c_size_t)]
+        L.rsv_ray_reserve.restype = i32
+        L.rsv_ray_reserve.argtypes = [vp, u32, u32]
         L.rsv_linetest.restype = i32
         L.rsv_linetest.argtypes = [vp, u32, u32, C.POINTER(RayCounts)]
         L.rsv_linetest_launch.restype = i32
@@ -292,7 +296,7 @@ class DeviceSpace:
         return r
 
     # ---- line tests
-    def linetest(self, rays, use_any=None, any_mask=None, none_mask=None, flags=FRAME_DOWNLOAD):
+    def linetest(self, rays, use_any=None, any_mask=None, none_mask=None, flags=FRAME_DOWNLOAD, space_idx=None, grow=True):
         rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 4)
         n = len(rays)
         nb = C.c_size_t()
@@ -305,17 +309,27 @@ class DeviceSpace:
         msk = _view(p, nb.value, np.uint64)[:3 * n].reshape(-1, 3)
         msk[:, 0] = 0 if any_mask is None else any_mask
         msk[:, 1] = 0 if none_mask is None else none_mask
-        msk[:, 2] = 0 if use_any is None else np.asarray(use_any, dtype=np.uint64)
+        word = np.zeros(n, dtype=np.uint64) if use_any is None else np.asarray(use_any, dtype=np.uint64) & np.uint64(1)
+        if space_idx is not None:
+            word = word | (np.asarray(space_idx, dtype=np.uint64) << np.uint64(32))
+        msk[:, 2] = word
         c = RayCounts()
-        self._check(self.L.rsv_linetest(self.h, n, flags, C.byref(c)))
+        rc = self.L.rsv_linetest(self.h, n, flags, C.byref(c))
+        if rc == RSV_ERR_CAPACITY and grow:
+            self._check(self.L.rsv_ray_reserve(self.h, int(c.n_hits * 1.25) + 1024, int(c.n_contacts * 1.25) + 1024))
+            rc = self.L.rsv_linetest(self.h, n, flags, C.byref(c))
+        self._check(rc)
         return c
 
     def ray_results(self):
+        """(hits, contacts, ray_first, ray_count) views of the pinned mirrors of the last downloaded rsv_linetest."""
         r = RayResults()
         self._check(self.L.rsv_ray_results_view(self.h, C.byref(r)))
         hits = _view(r.hits, int(r.n_hits) * RAY_HIT_DTYPE.itemsize, RAY_HIT_DTYPE) if r.n_hits else np.zeros(0, RAY_HIT_DTYPE)
         con = _view(r.contacts, int(r.n_contacts) * CONTACT_DTYPE.itemsize, CONTACT_DTYPE) if r.n_contacts else np.zeros(0, CONTACT_DTYPE)
-        return hits, con
+        first = _view(r.ray_first, int(r.n_rays) * 4, np.uint32) if r.n_rays else np.zeros(0, np.uint32)
+        count = _view(r.ray_count, int(r.n_rays) * 4, np.uint32) if r.n_rays else np.zeros(0, np.uint32)
+        return hits, con, first, count
 
 
 def space_for_world(w, device=0, **kw) -> DeviceSpace:

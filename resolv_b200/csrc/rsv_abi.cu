@@ -145,8 +145,8 @@ int32_t rsv_create(const rsv_config* cfg, rsv_space** out) {
     *out = nullptr;
     if (cfg->space_w <= 0 || cfg->space_h <= 0 || cfg->cell_w <= 0 || cfg->cell_h <= 0)
         return fail(nullptr, RSV_ERR_BAD_ARG, "rsv_create: space and cell sizes must be positive");
-    if (cfg->max_shapes == 0 || cfg->max_shapes >= (1u << 29))
-        return fail(nullptr, RSV_ERR_BAD_ARG, "rsv_create: max_shapes must be in [1, 2^29)");
+    if (cfg->max_shapes == 0 || cfg->max_shapes >= (1u << 27))
+        return fail(nullptr, RSV_ERR_BAD_ARG, "rsv_create: max_shapes must be in [1, 2^27)");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -355,9 +355,10 @@ int32_t rsv_frame_launch(rsv_space* s, int32_t margin, uint32_t flags) {
     k_cellsort<<<blocks_for(d.n_cells, kGridBlock, gcap), kGridBlock, 0, st>>>(d);
     k_entboxes<<<gcap, kGridBlock, 0, st>>>(d);
     mark(RSV_K_PAIRS);
-    if (d.n_shapes) k_pairs<<<s->pairs_blocks, kPairsBlock, 0, st>>>(d, margin, flags);
+    const bool grid_only = (flags & RSV_FRAME_GRID_ONLY) != 0;
+    if (d.n_shapes && !grid_only) k_pairs<<<s->pairs_blocks, kPairsBlock, 0, st>>>(d, margin, flags);
     mark(RSV_K_NARROW);
-    k_narrow<<<s->narrow_blocks, kNarrowBlock, 0, st>>>(d);
+    if (!grid_only) k_narrow<<<s->narrow_blocks, kNarrowBlock, 0, st>>>(d);
     mark(RSV_K_COUNT);
     CU(s, cudaGetLastError());
     CU(s, cudaMemcpyAsync(s->h_ctr, d.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
@@ -477,7 +478,7 @@ int32_t rsv_debug_cells(rsv_space* s, uint32_t* cell_end, uint64_t n_cells, uint
         if (R > s->d.cap_entries) return fail(s, RSV_ERR_CAPACITY, "rsv_debug_cells: last frame overflowed the entry buffer");
         std::vector<uint32_t> tmp(R);
         if (R) CU(s, cudaMemcpy(tmp.data(), s->d.entries, (size_t)R * 4, cudaMemcpyDeviceToHost));
-        for (uint64_t k = 0; k < R; k++) entries[k] = tmp[k] >> 3;
+        for (uint64_t k = 0; k < R; k++) entries[k] = tmp[k] >> kEntShift;
     }
     return RSV_OK;
 }

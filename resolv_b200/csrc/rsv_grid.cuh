@@ -177,11 +177,12 @@ __global__ void __launch_bounds__(kScanBlock) k_scan(uint32_t* __restrict__ data
     }
 }
 
-// Entry encoding: slot << 3 | tester << 2 | firstCol << 1 | firstRow. firstCol / firstRow say that this cell is
+// Entry encoding: slot << 5 | lastCol << 4 | lastRow << 3 | tester << 2 | firstCol << 1 | firstRow. The first/last flags say that this cell is
 // the first in-grid column / row of the shape's own cell rect; with them the candidate walk can apply the
 // owner-cell rule (emit a shape only from the first cell it shares with the query rect, i.e. the first
 // occurrence in the reference's row-major walk, cell.go:86-121) without loading the other shape's rect.
-constexpr uint32_t kEntFirstRow = 1u, kEntFirstCol = 2u, kEntTester = 4u;
+constexpr uint32_t kEntFirstRow = 1u, kEntFirstCol = 2u, kEntTester = 4u, kEntLastRow = 8u, kEntLastCol = 16u;
+constexpr int kEntShift = 5;
 
 __global__ void __launch_bounds__(kGridBlock) k_scatter(DevView d) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < d.n_shapes; i += gridDim.x * blockDim.x) {
@@ -190,13 +191,14 @@ __global__ void __launch_bounds__(kGridBlock) k_scatter(DevView d) {
         if (!clamp_rect(d, r, x0, y0, x1, y1)) continue;
         uint32_t meta = __ldg(d.meta + i);
         uint32_t base = cell_base(d, i);
-        uint32_t tag = (i << 3) | ((meta & RSV_META_TESTER) ? kEntTester : 0u);
+        uint32_t tag = (i << kEntShift) | ((meta & RSV_META_TESTER) ? kEntTester : 0u);
         for (int y = y0; y <= y1; y++) {
             uint32_t row = base + (uint32_t)(y - d.row_lo) * (uint32_t)d.W;
             for (int x = x0; x <= x1; x++) {
                 uint32_t slot = atomicAdd(d.cell + row + x + 1, 1u);
                 if (slot < d.cap_entries)
-                    d.entries[slot] = tag | (x == x0 ? kEntFirstCol : 0u) | (y == y0 ? kEntFirstRow : 0u);
+                    d.entries[slot] = tag | (x == x0 ? kEntFirstCol : 0u) | (y == y0 ? kEntFirstRow : 0u) |
+                                      (x == x1 ? kEntLastCol : 0u) | (y == y1 ? kEntLastRow : 0u);
             }
         }
     }
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(kGridBlock) k_cellsort(DevView d) {
 __global__ void __launch_bounds__(kGridBlock) k_entboxes(DevView d) {
     const uint32_t R = (uint32_t)min((unsigned long long)d.cap_entries, d.ctr->n_entries);
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < R; k += gridDim.x * blockDim.x)
-        d.ent_box[k] = float_box(load_box_nc(d.aabb + (d.entries[k] >> 3)));
+        d.ent_box[k] = float_box(load_box_nc(d.aabb + (d.entries[k] >> kEntShift)));
 }
 
 }  // namespace rsv

@@ -1,8 +1,309 @@
-// rsv_lines.cuh — batched LineTest (ray versus cell grid). Filled in after the frame path is parity-green.
+// rsv_lines.cuh — batched LineTest: rays versus the cell grid.
+//
+// Replaces LineTest (utils.go:276-370) for a batch of rays at once:
+//   cast line = (Start - 0.01 * Unit(End - Start)) -> End                               utils.go:278-282
+//   Circle:  line.IntersectionPointsCircle, normals Unit(point - centre)                utils.go:300-311
+//   Polygon: line.IntersectionPointsLine against every line of the polygon,
+//            normal = that line's Normal()                                              utils.go:313-324
+//   per set: Center = mean of the contacts (summed in generation order), contacts sorted by d2 to settings.Start,
+//            MTV = contacts[0].Point - Start - 0.01 * vu                                utils.go:328-346
+//   sets are ordered by d2(contacts[0].Point, cast line start)                          utils.go:355-357
+// OnIntersect is replayed by the host from the compacted buffer (sort key and generation rank are stored).
+//
+// The reference has no spatial acceleration for rays (TestAgainst is whatever iterator the caller passes). Two
+// candidate iterators are offered; both read the grid of the last rsv_frame:
+//   RECT (default): every shape registered in the cell rectangle covering the cast line's bounds — exactly the
+//        reference-expressible  space.FilterCells(Bounds{cast line}).FilterShapes()  (space.go:181-195, cell.go:73-121),
+//        so results equal the reference's for that TestAgainst, bit for bit, in the same generation order.
+//   DDA  (RSV_LINE_DDA): only the cells a 4-connected grid traversal of the cast line (extended by kDdaSlack world
+//        units at both ends) passes through, in traversal order. This is the fast path for long rays. It visits every
+//        cell the segment geometrically crosses; it does NOT reproduce the reference's "phantom" contacts, where the
+//        "+1" fudge of IntersectionPointsLine (convexPolygon.go:721-726) reports a hit on a far-away, nearly parallel
+//        edge.
+// Dedupe (a shape registered in several visited cells is tested once, at its first visited cell) uses the
+// first/last row/column flags of the grid entries: no per-ray seen-set and no gather of the other shape's rect.
 #pragma once
 #include "rsv_device.cuh"
+#include "rsv_grid.cuh"
+#include "rsv_narrow.cuh"
 
 namespace rsv {
-struct LineState {};
-inline void lines_free(LineState&) {}
+
+constexpr int kLinesBlock = 128;
+constexpr double kDdaSlack = 1.0;
+
+struct LineState {
+    // pinned host staging
+    double* h_seg = nullptr;               // f64[4 * max_rays]: sx, sy, ex, ey
+    unsigned long long* h_mask = nullptr;  // u64[3 * max_rays]: ByTags mask, NotByTags mask, use-ByTags flag
+    // device
+    double* seg = nullptr;
+    unsigned long long* mask = nullptr;
+    uint32_t* ray_first = nullptr;  // first hit record of ray i
+    uint32_t* ray_count = nullptr;  // number of hit records of ray i
+    rsv_ray_hit* hits = nullptr;
+    rsv_contact* contacts = nullptr;
+    uint32_t max_rays = 0, cap_hits = 0, cap_contacts = 0;
+    // pinned result mirrors
+    rsv_ray_hit* h_hits = nullptr;
+    rsv_contact* h_contacts = nullptr;
+    uint32_t h_cap_hits = 0, h_cap_contacts = 0;
+    uint32_t* h_ray_first = nullptr;
+    uint32_t* h_ray_count = nullptr;
+    uint64_t last_hits = 0, last_contacts = 0;
+    uint32_t last_rays = 0, launched_flags = 0, launched_rays = 0;
+    bool pending = false;
+    cudaEvent_t ev[2] = {};
+};
+
+inline void lines_free(LineState& L) {
+    if (L.h_seg) cudaFreeHost(L.h_seg);
+    if (L.h_mask) cudaFreeHost(L.h_mask);
+    if (L.h_hits) cudaFreeHost(L.h_hits);
+    if (L.h_contacts) cudaFreeHost(L.h_contacts);
+    if (L.h_ray_first) cudaFreeHost(L.h_ray_first);
+    if (L.h_ray_count) cudaFreeHost(L.h_ray_count);
+    void* dev[] = {L.seg, L.mask, L.ray_first, L.ray_count, L.hits, L.contacts};
+    for (void* p : dev) if (p) cudaFree(p);
+    for (auto& e : L.ev) if (e) cudaEventDestroy(e);
+    L = LineState{};
+}
+
+struct LinesView {
+    const double* seg;
+    const unsigned long long* mask;
+    uint32_t* ray_first;
+    uint32_t* ray_count;
+    rsv_ray_hit* hits;
+    rsv_contact* contacts;
+    uint32_t n_rays, cap_hits, cap_contacts;
+};
+
+struct Ray {
+    V2 S, E;       // settings.Start / settings.End
+    V2 vu;         // Unit(End - Start)
+    V2 start;      // cast line start (pulled back by castMargin)
+    unsigned long long any, none;
+    bool useAny;
+};
+
+// Tests one shape against the cast line. PASS 0 counts contacts; PASS 1 writes them to out[0..n), sorts them and
+// fills the hit record. Returns the number of contacts.
+template <int PASS>
+__device__ __forceinline__ uint32_t ray_vs_shape(const DevView& d, const Ray& ray, uint32_t B, rsv_contact* out,
+                                                 rsv_ray_hit* rec) {
+    const uint32_t meta = __ldg(d.meta + B);
+    const double2 pb2 = __ldg(d.pos + B);
+    const V2 pb{pb2.x, pb2.y};
+    uint32_t n = 0;
+    V2 sum{0.0, 0.0};
+    if (!(meta & RSV_META_POLYGON)) {
+        const double rad = __ldg(d.radius + B);
+        V2 pts[2];
+        const int k = line_x_circle(ray.start, ray.E, pb, rad, pts);
+        for (int i = 0; i < k; i++) {
+            if (PASS == 1) {
+                store_contact(out + n, pts[i], vunit(vsub(pts[i], pb)));
+                sum = vadd(sum, pts[i]);
+            }
+            n++;
+        }
+    } else {
+        const int nv = (int)(meta >> RSV_META_NV_SHIFT);
+        const int nl = ((meta & RSV_META_CLOSED) && nv > 2) ? nv : max(nv - 1, 0);
+        const double2* lv = d.verts + __ldg(d.vert_off + B);
+        if (nl > 0) {
+            double2 q = __ldg(lv);
+            const V2 first{dadd(q.x, pb.x), dadd(q.y, pb.y)};
+            V2 s = first;
+            for (int i = 0; i < nl; i++) {
+                V2 e = first;
+                if (i + 1 < nv) {
+                    q = __ldg(lv + i + 1);
+                    e = V2{dadd(q.x, pb.x), dadd(q.y, pb.y)};
+                }
+                V2 pt;
+                if (line_x_line(ray.start, ray.E, s, e, pt)) {
+                    if (PASS == 1) {
+                        store_contact(out + n, pt, edge_normal(s, e));
+                        sum = vadd(sum, pt);
+                    }
+                    n++;
+                }
+                s = e;
+            }
+        }
+    }
+    if (PASS == 1 && n) {
+        // Center (utils.go:332-337), then sort by d2 to settings.Start (utils.go:340-342; n <= 12 -> insertion sort)
+        const V2 center{sum.x / (double)n, sum.y / (double)n};
+        sort_contacts(out, (int)n, ray.S);
+        const V2 p0{out[0].px, out[0].py};
+        const V2 mtv = vsub(vsub(p0, ray.S), vscale(ray.vu, 0.01));
+        rec->mtv_x = mtv.x; rec->mtv_y = mtv.y;
+        rec->center_x = center.x; rec->center_y = center.y;
+        rec->key = vdist2(p0, ray.start);
+    }
+    return n;
+}
+
+__device__ __forceinline__ bool ray_filter(const DevView& d, const Ray& ray, uint32_t B) {
+    if (!ray.useAny && ray.none == 0) return true;
+    const unsigned long long t = __ldg(d.tags + B);
+    if (ray.useAny && (t & ray.any) == 0) return false;   // ByTags (tags.go:29-31)
+    return (t & ray.none) == 0;                           // NotByTags
+}
+
+// Visits every candidate of the ray in generation order and calls f(B).
+template <class F>
+__device__ __forceinline__ void ray_candidates(const DevView& d, const Ray& ray, bool dda, uint32_t space, F f) {
+    const uint32_t base = space * d.cells_per_space;
+    if (!dda) {
+        // Space.FilterCells(bounds of the cast line) (space.go:181-195) walked like CellSelection.ForEach (cell.go:86-121)
+        const double minx = ray.start.x < ray.E.x ? ray.start.x : ray.E.x, maxx = ray.start.x < ray.E.x ? ray.E.x : ray.start.x;
+        const double miny = ray.start.y < ray.E.y ? ray.start.y : ray.E.y, maxy = ray.start.y < ray.E.y ? ray.E.y : ray.start.y;
+        const int qx0 = max(cell_of(minx, d.cell_w), 0), qx1 = min(cell_of(maxx, d.cell_w), d.W - 1);
+        const int qy0 = max(cell_of(miny, d.cell_h), d.row_lo), qy1 = min(cell_of(maxy, d.cell_h), d.row_hi - 1);
+        for (int y = qy0; y <= qy1; y++) {
+            const uint32_t* row = d.cell + base + (uint32_t)(y - d.row_lo) * (uint32_t)d.W;
+            if (qx0 > qx1) break;
+            const uint32_t s0 = row[qx0], s1 = row[qx0 + 1], e = min(row[qx1 + 1], d.cap_entries);
+            for (uint32_t k = s0; k < e; k++) {
+                const uint32_t ent = d.entries[k];
+                if (!((ent & kEntFirstCol) || k < s1)) continue;      // first occurrence in the row-major walk
+                if (!((ent & kEntFirstRow) || y == qy0)) continue;
+                f(ent >> kEntShift);
+            }
+        }
+        return;
+    }
+    // 4-connected traversal of the cast line, extended by kDdaSlack at both ends.
+    const V2 a{dsub(ray.start.x, dmul(ray.vu.x, kDdaSlack)), dsub(ray.start.y, dmul(ray.vu.y, kDdaSlack))};
+    const V2 b{dadd(ray.E.x, dmul(ray.vu.x, kDdaSlack)), dadd(ray.E.y, dmul(ray.vu.y, kDdaSlack))};
+    // clip the parameter range to the grid box grown by one cell (slab method; conservative)
+    const double gx0 = -d.cell_w, gx1 = (double)(d.W + 1) * d.cell_w;
+    const double gy0 = (double)(d.row_lo - 1) * d.cell_h, gy1 = (double)(d.row_hi + 1) * d.cell_h;
+    const double dx = b.x - a.x, dy = b.y - a.y;
+    double t0 = 0.0, t1 = 1.0;
+    if (dx != 0.0) {
+        double u0 = (gx0 - a.x) / dx, u1 = (gx1 - a.x) / dx;
+        if (u0 > u1) { double t = u0; u0 = u1; u1 = t; }
+        t0 = fmax(t0, u0); t1 = fmin(t1, u1);
+    } else if (a.x < gx0 || a.x > gx1) return;
+    if (dy != 0.0) {
+        double u0 = (gy0 - a.y) / dy, u1 = (gy1 - a.y) / dy;
+        if (u0 > u1) { double t = u0; u0 = u1; u1 = t; }
+        t0 = fmax(t0, u0); t1 = fmin(t1, u1);
+    } else if (a.y < gy0 || a.y > gy1) return;
+    if (!(t0 <= t1)) return;
+    const double ax = a.x + t0 * dx, ay = a.y + t0 * dy, bx = a.x + t1 * dx, by = a.y + t1 * dy;
+    int ix = cell_of(ax, d.cell_w), iy = cell_of(ay, d.cell_h);
+    const int ex = cell_of(bx, d.cell_w), ey = cell_of(by, d.cell_h);
+    const int stepx = ex > ix ? 1 : -1, stepy = ey > iy ? 1 : -1;
+    int nx = abs(ex - ix), ny = abs(ey - iy);
+    // parameter (along a->b clipped) at which the line crosses the next vertical / horizontal grid line
+    const double ddx = bx - ax, ddy = by - ay;
+    const double tdx = ddx != 0.0 ? d.cell_w / fabs(ddx) : 0.0, tdy = ddy != 0.0 ? d.cell_h / fabs(ddy) : 0.0;
+    double tmx = ddx != 0.0 ? (((double)(ix + (stepx > 0 ? 1 : 0)) * d.cell_w - ax) / ddx) : 0.0;
+    double tmy = ddy != 0.0 ? (((double)(iy + (stepy > 0 ? 1 : 0)) * d.cell_h - ay) / ddy) : 0.0;
+    int came = 0;  // how the current cell was entered: 0 start, 1 step in x, 2 step in y
+    for (;;) {
+        if (ix >= 0 && ix < d.W && iy >= d.row_lo && iy < d.row_hi) {
+            const uint32_t c = base + (uint32_t)(iy - d.row_lo) * (uint32_t)d.W + (uint32_t)ix;
+            const uint32_t s = d.cell[c], e = min(d.cell[c + 1], d.cap_entries);
+            // a shape is new here iff the cell we came from is outside its (in-grid) cell rect
+            const uint32_t need = came == 0 ? 0u : (came == 1 ? (stepx > 0 ? kEntFirstCol : kEntLastCol)
+                                                              : (stepy > 0 ? kEntFirstRow : kEntLastRow));
+            for (uint32_t k = s; k < e; k++) {
+                const uint32_t ent = d.entries[k];
+                if ((ent & need) != need) continue;
+                f(ent >> kEntShift);
+            }
+        }
+        if (nx == 0 && ny == 0) break;
+        if (ny == 0 || (nx != 0 && tmx < tmy)) { ix += stepx; tmx += tdx; nx--; came = 1; }
+        else { iy += stepy; tmy += tdy; ny--; came = 2; }
+    }
+}
+
+// One thread per ray, two passes around one warp-aggregated allocation, so that all hit records of a ray are
+// contiguous (ray_first / ray_count) and in candidate generation order.
+__global__ void __launch_bounds__(kLinesBlock) k_linetest(DevView d, LinesView L, uint32_t flags) {
+    const int lane = threadIdx.x & 31;
+    const bool dda = (flags & RSV_LINE_DDA) != 0;
+    unsigned long long my_cands = 0, my_hits = 0;
+    const uint32_t stride = gridDim.x * kLinesBlock;
+    for (uint32_t base = blockIdx.x * kLinesBlock; base < L.n_rays; base += stride) {
+        const uint32_t i = base + threadIdx.x;
+        const bool live = i < L.n_rays;
+        Ray ray{};
+        uint32_t space = 0;
+        uint32_t nh = 0, nc = 0;
+        if (live) {
+            const double2* sp = reinterpret_cast<const double2*>(L.seg + 4 * (size_t)i);
+            const double2 s = __ldg(sp), e = __ldg(sp + 1);
+            ray.S = V2{s.x, s.y}; ray.E = V2{e.x, e.y};
+            ray.vu = vunit(vsub(ray.E, ray.S));
+            ray.start = vsub(ray.S, vscale(ray.vu, 0.01));
+            ray.any = __ldg(L.mask + 3 * (size_t)i);
+            ray.none = __ldg(L.mask + 3 * (size_t)i + 1);
+            const unsigned long long w = __ldg(L.mask + 3 * (size_t)i + 2);
+            ray.useAny = (w & 1ull) != 0;
+            space = (uint32_t)(w >> 32);
+            if (space >= d.n_spaces) space = 0;
+            ray_candidates(d, ray, dda, space, [&](uint32_t B) {
+                if (!ray_filter(d, ray, B)) return;
+                my_cands++;
+                const uint32_t n = ray_vs_shape<0>(d, ray, B, nullptr, nullptr);
+                if (n) { nh++; nc += n; }
+            });
+        }
+        // warp-aggregated allocation of hit records and contacts
+        uint32_t ih = nh, ic = nc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t th = __shfl_up_sync(0xffffffffu, ih, o), tc = __shfl_up_sync(0xffffffffu, ic, o);
+            if (lane >= o) { ih += th; ic += tc; }
+        }
+        const uint32_t toth = __shfl_sync(0xffffffffu, ih, 31), totc = __shfl_sync(0xffffffffu, ic, 31);
+        uint32_t bh = 0, bc = 0;
+        if (lane == 0 && toth) {
+            bh = atomicAdd(&d.ctr->ray_hit_cursor, toth);
+            bc = atomicAdd(&d.ctr->ray_contact_cursor, totc);
+            if (bh + toth > L.cap_hits || bh + toth < bh) atomicOr(&d.ctr->overflow, RSV_OVF_RAY_HITS);
+            if (bc + totc > L.cap_contacts || bc + totc < bc) atomicOr(&d.ctr->overflow, RSV_OVF_RAY_CONTACTS);
+        }
+        bh = __shfl_sync(0xffffffffu, bh, 0) + (ih - nh);
+        bc = __shfl_sync(0xffffffffu, bc, 0) + (ic - nc);
+        if (!live) continue;
+        L.ray_first[i] = bh;
+        L.ray_count[i] = nh;
+        my_hits += nh;
+        if (nh && (unsigned long long)bh + nh <= L.cap_hits && (unsigned long long)bc + nc <= L.cap_contacts) {
+            uint32_t wh = 0, wc = 0, rank = 0;
+            ray_candidates(d, ray, dda, space, [&](uint32_t B) {
+                if (!ray_filter(d, ray, B)) return;
+                const uint32_t n = ray_vs_shape<0>(d, ray, B, nullptr, nullptr);
+                if (n) {
+                    rsv_ray_hit rec;
+                    rec.ray = i; rec.b = B; rec.first_contact = bc + wc; rec.count_rank = (n & 0xffu) | (rank << 8);
+                    rec.pad = 0.0;
+                    ray_vs_shape<1>(d, ray, B, L.contacts + bc + wc, &rec);
+                    L.hits[bh + wh] = rec;
+                    wh++; wc += n;
+                }
+                rank++;
+            });
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        my_cands += __shfl_down_sync(0xffffffffu, my_cands, o);
+        my_hits += __shfl_down_sync(0xffffffffu, my_hits, o);
+    }
+    if (lane == 0) {
+        if (my_cands) atomicAdd(&d.ctr->n_ray_candidates, my_cands);
+        if (my_hits) atomicAdd(&d.ctr->n_ray_hits, my_hits);
+    }
+}
+
 }  // namespace rsv

@@ -154,7 +154,7 @@ __device__ __forceinline__ uint32_t pairs_pass(const DevView& d, bool all, Pairs
                     const uint32_t ent = sm.itEnt[slot];
                     const uint32_t m = sm.itMeta[slot];
                     t = m & 31u;
-                    B = ent >> 3;
+                    B = ent >> kEntShift;
                     cand = B != sm.A[t]                                     // cell.go:101, shape.go:279
                            && ((ent & kEntFirstCol) || (m & 32u))           // owner-cell rule == cell.go:105
                            && ((ent & kEntFirstRow) || (m & 64u));
@@ -245,7 +245,7 @@ __device__ __forceinline__ void pairs_batch(const DevView& d, int margin, uint32
     const uint32_t* row0 = d.cell;
     if (have) {
         if (hk != kNoEntry) {
-            A = d.entries[hk] >> 3;
+            A = d.entries[hk] >> kEntShift;
             sm.fbox[lane] = d.ent_box[hk];
         } else {
             sm.fbox[lane] = float_box(load_box_nc(d.aabb + A));
