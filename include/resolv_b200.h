@@ -253,6 +253,30 @@ int32_t rsv_linetest_launch(rsv_space* s, uint32_t n_rays, uint32_t flags);
 int32_t rsv_linetest_finish(rsv_space* s, rsv_ray_counts* out);
 int32_t rsv_ray_results_view(rsv_space* s, rsv_ray_results* out);
 
+/* ---- strip partitioning of one large Space across GPUs -------------------------------------------------- */
+/* The reference has no distributed layer. One process per GPU creates an rsv_space whose stored rows
+ * (rsv_config.row_lo/row_hi) are its strip plus a halo; static shape data of its own and its neighbours' slot
+ * ranges is resident on every device; once per frame neighbours exchange (slot, position) records of the owned
+ * shapes that reach into each other's stored rows (NCCL send/recv of the buffers filled by rsv_halo_pack), then
+ * every device runs rsv_frame: a shape is a tester only on the device whose home rows contain its first cell row,
+ * so each ordered pair is tested exactly once and results land where the tester lives. */
+#define RSV_OVF_GHOSTS 0x20u
+/* Launch every kernel of this space on an externally owned CUDA stream (e.g. the stream the host framework
+ * issues its NCCL calls on) so that pack -> exchange -> apply -> frame need no host synchronisation. NULL
+ * restores the library's own stream. */
+int32_t rsv_set_stream(rsv_space* s, void* cuda_stream);
+/* own_lo/own_hi: slot range this device moves and packs; home_lo/home_hi: cell rows whose shapes are testers
+ * here; max_ghosts: capacity of the per-frame halo list. */
+int32_t rsv_strip_setup(rsv_space* s, uint32_t own_lo, uint32_t own_hi, int32_t home_lo, int32_t home_hi, uint32_t max_ghosts);
+/* Fill device buffers of (1 + cap_records) 24-byte records {u32 slot, u32 pad, f64 x, f64 y} (record 0: count)
+ * with the owned shapes whose first cell row <= up_row_max (for the upper neighbour) / last cell row >= dn_row_min
+ * (for the lower neighbour). Either buffer may be NULL. */
+int32_t rsv_halo_pack(rsv_space* s, int32_t up_row_max, int32_t dn_row_min, void* dev_send_up, void* dev_send_dn, uint32_t cap_records);
+/* Apply received buffers: positions are written to slot + slot_off (sender-to-receiver slot translation) and the
+ * slots become this frame's ghosts. Either buffer may be NULL. */
+int32_t rsv_halo_apply(rsv_space* s, const void* dev_recv_up, int32_t slot_off_up, const void* dev_recv_dn, int32_t slot_off_dn,
+                       uint32_t cap_records);
+
 /* ---- parity / debug dumps --------------------------------------------------------------------------------- */
 /* Cell membership after the last frame: cell_end[c] (exclusive end offset of cell c in `entries`, cells row-major,
  * spaces concatenated; start = cell_end[c-1] or 0) and the shape slots per cell in ascending slot order. Either

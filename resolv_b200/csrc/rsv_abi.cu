@@ -15,6 +15,7 @@
 #include "../../include/resolv_b200.h"
 #include "rsv_device.cuh"
 #include "rsv_grid.cuh"
+#include "rsv_halo.cuh"
 #include "rsv_lines.cuh"
 #include "rsv_narrow.cuh"
 #include "rsv_pairs.cuh"
@@ -27,7 +28,9 @@ struct rsv_space {
     rsv_config cfg{};
     int device = 0;
     int sm_count = 148;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // stream every kernel of this space is launched on
+    cudaStream_t own_stream = nullptr;  // the library-created stream (stream == own_stream unless rsv_set_stream)
+    bool strip_mode = false;
     DevView d{};
     // device allocations behind the const views
     void* dev_buf[RSV_BUF_COUNT] = {};
@@ -201,7 +204,8 @@ int32_t rsv_create(const rsv_config* cfg, rsv_space** out) {
     cudaDeviceProp prop;
     CUC(cudaGetDeviceProperties(&prop, s->device));
     s->sm_count = prop.multiProcessorCount;
-    CUC(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+    s->stream = s->own_stream;
     const uint32_t N = cfg->max_shapes;
     const uint32_t NV = cfg->max_verts ? cfg->max_verts : 1;
     for (int b = 0; b < RSV_BUF_COUNT; b++) {
@@ -251,7 +255,7 @@ int32_t rsv_destroy(rsv_space* s) {
         if (s->host_buf[b]) cudaFreeHost(s->host_buf[b]);
     }
     DevView& d = s->d;
-    void* dev[] = {d.aabb, d.crect, d.cell, d.entries, d.ent_box, d.tile_state, d.tester_start, d.tester_count, d.orphans, d.hits, d.contacts, d.ctr};
+    void* dev[] = {d.aabb, d.crect, d.cell, d.entries, d.ent_box, d.tile_state, d.tester_start, d.tester_count, d.orphans, d.ghosts, d.n_ghosts, d.hits, d.contacts, d.ctr};
     for (void* p : dev) if (p) cudaFree(p);
     if (s->h_ctr) cudaFreeHost(s->h_ctr);
     if (s->h_hits) cudaFreeHost(s->h_hits);
@@ -259,7 +263,7 @@ int32_t rsv_destroy(rsv_space* s) {
     lines_free(s->lines);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
     for (auto& e : s->ev_timer) if (e) cudaEventDestroy(e);
-    if (s->stream) cudaStreamDestroy(s->stream);
+    if (s->own_stream) cudaStreamDestroy(s->own_stream);
     cudaGetLastError();
     delete s;
     return RSV_OK;
@@ -297,6 +301,7 @@ int32_t rsv_set_counts(rsv_space* s, uint32_t n_shapes, uint32_t n_verts) {
     s->n_shapes = n_shapes;
     s->n_verts = n_verts;
     s->d.n_shapes = n_shapes;
+    if (!s->strip_mode) { s->d.own_lo = 0; s->d.own_hi = n_shapes; s->d.home_lo = 0; s->d.home_hi = s->d.H; }
     return RSV_OK;
 }
 
@@ -346,11 +351,12 @@ int32_t rsv_frame_launch(rsv_space* s, int32_t margin, uint32_t flags) {
     CU(s, cudaMemsetAsync(d.ctr, 0, offsetof(Counters, ray_hit_cursor), st));
     mark(RSV_K_BOUNDS);
     const int gcap = s->sm_count * 8;
-    if (d.n_shapes) k_bounds<<<blocks_for(d.n_shapes, kGridBlock, gcap), kGridBlock, 0, st>>>(d, margin);
+    const uint32_t max_items = (d.own_hi - d.own_lo) + (d.n_ghosts ? d.cap_ghosts : 0u);
+    if (d.n_shapes) k_bounds<<<blocks_for(max_items, kGridBlock, gcap), kGridBlock, 0, st>>>(d, margin);
     mark(RSV_K_SCAN);
     k_scan<<<(d.n_cells + 1 + kScanTile - 1) / kScanTile, kScanBlock, 0, st>>>(d.cell, d.n_cells + 1, d.tile_state, &d.ctr->scan_ticket);
     mark(RSV_K_SCATTER);
-    if (d.n_shapes) k_scatter<<<blocks_for(d.n_shapes, kGridBlock, gcap), kGridBlock, 0, st>>>(d);
+    if (d.n_shapes) k_scatter<<<blocks_for(max_items, kGridBlock, gcap), kGridBlock, 0, st>>>(d);
     mark(RSV_K_CELLSORT);
     k_cellsort<<<blocks_for(d.n_cells, kGridBlock, gcap), kGridBlock, 0, st>>>(d);
     k_entboxes<<<gcap, kGridBlock, 0, st>>>(d);
@@ -495,3 +501,4 @@ int32_t rsv_debug_cell_rects(rsv_space* s, int32_t* rects4, uint64_t n_shapes) {
 }  // extern "C"
 
 #include "rsv_lines_abi.inl"
+#include "rsv_halo_abi.inl"

@@ -56,6 +56,12 @@ struct DevView {
     uint32_t* tester_start;          // first pair record of tester i
     uint32_t* tester_count;          // number of pair records of tester i
     uint32_t* orphans;               // see Counters::n_orphans
+    // ---- strip partitioning (multi-GPU): which slots this device processes and which rows it tests
+    uint32_t own_lo, own_hi;         // owned slot range (default [0, n_shapes))
+    uint32_t* ghosts;                // halo slots received this frame
+    uint32_t* n_ghosts;              // device-side count of `ghosts` (nullptr: none)
+    uint32_t cap_ghosts;
+    int32_t home_lo, home_hi;        // rows whose shapes run IntersectionTest here (default [0, H))
     // ---- results
     rsv_hit* hits;
     rsv_contact* contacts;

@@ -24,6 +24,23 @@ __device__ __forceinline__ bool clamp_rect(const DevView& d, int4 r, int& x0, in
     return x0 <= x1 && y0 <= y1;
 }
 
+// The shapes a frame processes: the owned slot range plus the halo ("ghost") slots received this frame. For a
+// single-GPU Space the owned range is [0, n_shapes) and there are no ghosts.
+__device__ __forceinline__ uint32_t n_items(const DevView& d) {
+    uint32_t ng = d.n_ghosts ? min(*d.n_ghosts, d.cap_ghosts) : 0u;
+    return (d.own_hi - d.own_lo) + ng;
+}
+__device__ __forceinline__ uint32_t item_slot(const DevView& d, uint32_t j) {
+    const uint32_t n_own = d.own_hi - d.own_lo;
+    return j < n_own ? d.own_lo + j : d.ghosts[j - n_own];
+}
+// Strip partitioning: a shape runs its IntersectionTest on the device whose home rows contain its first cell row
+// (clamped into the grid), so every ordered pair is tested exactly once across devices.
+__device__ __forceinline__ bool is_home(const DevView& d, int4 r) {
+    const int hy = min(max(r.y, 0), d.H - 1);
+    return hy >= d.home_lo && hy < d.home_hi;
+}
+
 __device__ __forceinline__ uint32_t cell_base(const DevView& d, uint32_t i) {
     return d.n_spaces > 1 ? __ldg(d.space_idx + i) * d.cells_per_space : 0u;
 }
@@ -35,7 +52,11 @@ __device__ __forceinline__ uint32_t cell_base(const DevView& d, uint32_t i) {
 //   addToTouchingCells           shape.go:191-214     (cells outside the grid are skipped)
 __global__ void __launch_bounds__(kGridBlock) k_bounds(DevView d, int margin) {
     unsigned long long my_entries = 0, my_testers = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < d.n_shapes; i += gridDim.x * blockDim.x) {
+    const uint32_t n = n_items(d);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && d.n_ghosts && *d.n_ghosts > d.cap_ghosts)
+        atomicOr(&d.ctr->overflow, RSV_OVF_GHOSTS);
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const uint32_t i = item_slot(d, j);
         uint32_t meta = __ldg(d.meta + i);
         double2 p = __ldg(d.pos + i);
         Box lb = load_box(d.laabb + i);
@@ -49,7 +70,7 @@ __global__ void __launch_bounds__(kGridBlock) k_bounds(DevView d, int margin) {
         store_box(d.aabb + i, b);
         d.crect[i] = r;
         d.tester_count[i] = 0;
-        const bool tester = (meta & RSV_META_TESTER) && !(meta & RSV_META_ABSENT);
+        const bool tester = (meta & RSV_META_TESTER) && !(meta & RSV_META_ABSENT) && is_home(d, r);
         if (tester) my_testers++;
         int x0, y0, x1, y1;
         const bool in_grid = clamp_rect(d, r, x0, y0, x1, y1);
@@ -185,13 +206,15 @@ constexpr uint32_t kEntFirstRow = 1u, kEntFirstCol = 2u, kEntTester = 4u, kEntLa
 constexpr int kEntShift = 5;
 
 __global__ void __launch_bounds__(kGridBlock) k_scatter(DevView d) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < d.n_shapes; i += gridDim.x * blockDim.x) {
+    const uint32_t n = n_items(d);
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const uint32_t i = item_slot(d, j);
         int4 r = d.crect[i];
         int x0, y0, x1, y1;
         if (!clamp_rect(d, r, x0, y0, x1, y1)) continue;
         uint32_t meta = __ldg(d.meta + i);
         uint32_t base = cell_base(d, i);
-        uint32_t tag = (i << kEntShift) | ((meta & RSV_META_TESTER) ? kEntTester : 0u);
+        uint32_t tag = (i << kEntShift) | (((meta & RSV_META_TESTER) && is_home(d, r)) ? kEntTester : 0u);
         for (int y = y0; y <= y1; y++) {
             uint32_t row = base + (uint32_t)(y - d.row_lo) * (uint32_t)d.W;
             for (int x = x0; x <= x1; x++) {

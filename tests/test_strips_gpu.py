@@ -1,0 +1,70 @@
+"""Strip partitioning on ONE GPU: two ranks emulated in one process (two rsv_spaces on cuda:0, the neighbour
+exchange replaced by device copies). The union of both ranks' results must equal the single-Space result on the
+concatenated world: same candidate counts, same hit set with the same generation ranks, bit-identical MTV/contacts."""
+import numpy as np
+import pytest
+
+from resolv_b200 import _abi, space_for_world, strips
+from tests.util import bits
+
+pytestmark = pytest.mark.gpu
+
+
+def _hits_table(hits, con, to_global):
+    live = (hits["count_rank"] & 0x7f) > 0
+    h = hits[live]
+    a, b = to_global(h["a"]), to_global(h["b"])
+    n = (h["count_rank"] & 0x7f).astype(np.int64)
+    rank = (h["count_rank"] >> 8).astype(np.int64)
+    cons = [np.concatenate([con["p"][f:f + k], con["n"][f:f + k]], -1) for f, k in zip(h["first_contact"], n)]
+    return a, b, n, rank, h["mtv"].copy(), cons
+
+
+@pytest.mark.parametrize("kind", ["cfg2", "cfg3"])
+def test_two_strips_equal_one_space(kind):
+    import torch
+    n, size, world = 20000, 9280, 2
+    ranks = [strips.StripRank(kind, n, r, world, 0, size=size, cap_halo=8192) for r in range(world)]
+    ref_world = strips.concat_worlds([strips.tile_world(kind, n, t, size=size) for t in range(world)], size * world)
+    ref = space_for_world(ref_world)
+    try:
+        for frame in range(3):
+            if frame:   # every rank moves the shapes it owns; the reference moves everything
+                ref_world.pos += ref_world.vel
+                ref.set_positions(ref_world.pos)
+                for r, sr in enumerate(ranks):
+                    sr.ds.buf[_abi.BUF_POS][2 * n:4 * n] = ref_world.pos[r * n:(r + 1) * n].reshape(-1)
+                    sr.ds.commit(1 << _abi.BUF_POS, n, 2 * n)
+            for sr in ranks:
+                sr.pack()
+            torch.cuda.synchronize()
+            ranks[1].recv_up.copy_(ranks[0].send_dn)
+            ranks[0].recv_dn.copy_(ranks[1].send_up)
+            torch.cuda.synchronize()
+            tables, P = [], 0
+            for sr in ranks:
+                sr.apply()
+                c = sr.ds.frame(1, sr.flags | _abi.FRAME_DOWNLOAD, grow=True)
+                P += c.n_candidates
+                hits, con = sr.ds.results()
+                tables.append(_hits_table(hits, con, sr.global_slot))
+            cr = ref.frame(1, _abi.FRAME_DOWNLOAD, grow=True)
+            rh, rc = ref.results()
+            ra, rb, rn, rrank, rmtv, rcons = _hits_table(rh, rc, lambda x: np.asarray(x, dtype=np.int64))
+            assert P == cr.n_candidates
+            a = np.concatenate([t[0] for t in tables]); b = np.concatenate([t[1] for t in tables])
+            nn = np.concatenate([t[2] for t in tables]); rk = np.concatenate([t[3] for t in tables])
+            mtv = np.concatenate([t[4] for t in tables]); cons = sum((t[5] for t in tables), [])
+            o, ro = np.lexsort((b, a)), np.lexsort((rb, ra))
+            assert np.array_equal(a[o], ra[ro]) and np.array_equal(b[o], rb[ro]), "hit sets differ"
+            assert np.array_equal(nn[o], rn[ro]) and np.array_equal(rk[o], rrank[ro]), "contact counts / generation ranks differ"
+            assert np.array_equal(bits(mtv[o]), bits(rmtv[ro]))
+            dc = np.concatenate([cons[i] for i in o]); rcc = np.concatenate([rcons[i] for i in ro])
+            assert np.array_equal(bits(dc), bits(rcc))
+            assert len(a) > 1000
+            # the halo really is a small boundary layer
+            assert int(ranks[0].send_dn[0].item() & 0xffffffff) < n // 20
+    finally:
+        for sr in ranks:
+            sr.close()
+        ref.close()
