@@ -267,3 +267,23 @@ def run_bench(args, rank, world, local_rank):
         "roofline": {"bound": "hbm", "kernel": "frame", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
                      "traffic": None, "peak_source": peak_src, "note": "per-kernel roofline is reported by the N=1 run"},
     }
+
+
+HALO_DTYPE = np.dtype([("slot", np.uint32), ("pad", np.uint32), ("x", np.float64), ("y", np.float64)])
+
+
+def encode_records(slots, pos, cap):
+    """Host-side builder of a halo buffer in the device layout (record 0 = count); used by the CPU tests."""
+    buf = np.zeros(cap + 1, dtype=HALO_DTYPE)
+    k = min(len(slots), cap)
+    buf["slot"][0] = len(slots)
+    buf["slot"][1:1 + k] = slots[:k]
+    buf["x"][1:1 + k] = pos[slots[:k], 0]
+    buf["y"][1:1 + k] = pos[slots[:k], 1]
+    return buf.view(np.int64)
+
+
+def decode_records(words):
+    rec = np.asarray(words).view(HALO_DTYPE)
+    k = int(rec["slot"][0])
+    return rec["slot"][1:1 + k].astype(np.int64), np.stack([rec["x"][1:1 + k], rec["y"][1:1 + k]], -1)
