@@ -63,52 +63,55 @@ def workload_name(args, n_gpus):
 
 # ----------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clocks and throttle reasons DURING the timed regions (B200_PROFILING.md): NVML in a background
+    thread every few milliseconds (the timed regions are only tens of milliseconds long)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index=0):
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.t = None
+        self.err = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[0].isdigit() else self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._run, daemon=True)
             self.t.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception as e:  # noqa: BLE001
+                self.err = repr(e)
+                return
+            time.sleep(0.004)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for k, nm in enumerate(names):
-                if f[3 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop.set()
+        if self.t:
+            self.t.join(timeout=1)
+        out = {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+               "reasons": sorted(self.reasons), "samples": len(self.sm)}
+        if self.err:
+            out["error"] = self.err
+        return out
 
 
 def measured_peaks():
@@ -122,23 +125,33 @@ def measured_peaks():
 
 
 def kernel_algorithmic_bytes(c, w, n_cells):
-    """Algorithmic bytes each kernel must move per launch: every datum counted once per
-    producer/consumer hand-off, caches assumed perfect within a kernel."""
-    N, R, P, G, K = c.n_shapes, c.n_entries, c.n_candidates, c.n_gated, c.n_contacts
-    poly = int((w.kind == 1).sum())
-    nv_touch = 16 * float(w.nv.sum()) / max(N, 1)  # average vertex bytes per shape
+    """Algorithmic bytes each kernel must move per launch: every datum counted once per kernel
+    (caches assumed perfect within a kernel), gathers counted at the size of the datum, atomics as 8 B (RMW)."""
+    N, R, G, K = c.n_shapes, c.n_entries, c.n_gated, c.n_contacts
+    vb = 16.0 * float(w.nv.sum()) / max(N, 1)   # average vertex bytes per shape
+    C1 = n_cells + 1
     return {
-        "clear": 4 * (n_cells + 1),
-        "bounds": N * (16 + 32 + 4) + N * (32 + 16) + 4 * R,            # pos+laabb+meta in, aabb+crect out, one RED per entry
-        "scan": 8 * (n_cells + 1),                                       # read + write cell offsets
-        "scatter": N * (16 + 4) + 8 * R,                                 # crect+meta in, cursor RMW + entry out
-        "cellsort": 4 * (n_cells + 1) + 8 * R,                           # offsets in, entries in/out
-        "pairs": N * (4 + 16 + 32 + 16) + 4 * (n_cells + 1) + 4 * R + 32 * N + 16 * G + 8 * N,
-        # meta+crect+aabb+qmask per tester, every cell offset and entry once, every shape's aabb once as a candidate,
-        # pair record out, tester table out
-        "narrow": G * (16 + 2 * (16 + 4 + 4)) + G * 2 * nv_touch + 32 * G + 32 * K,
-        # record in, pos/meta/vert_off of both, vertices of both, hit header out, contacts out
+        "clear": 4 * C1,                                   # zero the per-cell counters
+        "bounds": N * (16 + 32 + 4) + N * (32 + 16 + 4) + 8 * R,   # pos, local AABB, meta -> AABB, cell rect, table reset; one RED per entry
+        "scan": 8 * C1,                                    # counters in, offsets out
+        "scatter": N * (16 + 4) + 8 * R + 4 * R,           # cell rect, meta; cursor RMW per entry; entry word out
+        "cellsort": 4 * C1 + 8 * R + (4 * R + 32 * N + 16 * R),    # offsets, entries in/out; k_entboxes: entries, each AABB once, float boxes out
+        "pairs": 4 * R + N * (4 + 16 + 4 + 16) + 4 * C1 + (4 + 16) * R + 64 * G + 16 * G,
+        # entry scan; per tester home entry + float box, meta, cell rect; every cell offset once; every entry + float box once;
+        # exact fp64 gate on the survivors (two AABBs); record out
+        "narrow": G * (16 + 2 * (16 + 4 + 4 + 32)) + G * 2 * vb + 32 * G + 32 * K,
+        # record in; pos, meta, vertex offset / radius, AABB of both; vertices of both; hit record out; contacts out
     }
+
+
+def survey_frame_bytes(c, w, n_cells):
+    """SURVEY.md §8(d) compulsory-traffic formula for one frame (the figure BASELINE.md quotes the 60 % target on)."""
+    N, R, P, H, K = c.n_shapes, c.n_entries, c.n_candidates, c.n_hits, c.n_contacts
+    circ = int((w.kind == 0).sum())
+    poly = N - circ
+    s_bp = 24 * circ + 48 * poly
+    s_np = 32 * circ + 28 * poly + 16 * int(w.nv.sum())
+    return s_bp + 16 * R + 8 * (n_cells + 1) + 16 * P + s_np + 32 * H + 32 * K
 
 
 def run_b200(args):
@@ -222,12 +235,14 @@ def run_b200(args):
         "clocks": clocks,
         "e2e": {"value": N * K / e2e_t, "unit": UNIT, "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K,
                 "ms_per_step": 1e3 * e2e_t / K},
-        "gpu_launches": K * 6,
+        "gpu_launches": K * 7,
         "kernels_us": {k: round(v, 2) for k, v in acc.items()},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "frame_algorithmic_bytes": int(frame_bytes),
-                     "frame_frac": frame_bytes / (ms_per_step * 1e-3) / 1e9 / peak},
+                     "frame_frac": frame_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                     "survey_frame_bytes": int(survey_frame_bytes(c, w, n_cells)),
+                     "survey_frame_frac": survey_frame_bytes(c, w, n_cells) / (ms_per_step * 1e-3) / 1e9 / peak},
     }
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, budget_s=20.0)
@@ -299,6 +314,12 @@ def main():
     out = run_reference(args) if args.impl == "reference" else run_b200(args)
     if out is not None and int(os.environ.get("RANK", "0")) == 0:
         print(json.dumps(out), flush=True)
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
 
 
 if __name__ == "__main__":

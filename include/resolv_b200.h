@@ -183,6 +183,9 @@ int32_t rsv_frame(rsv_space* s, int32_t margin, uint32_t flags, rsv_counts* out)
 int32_t rsv_frame_launch(rsv_space* s, int32_t margin, uint32_t flags);
 int32_t rsv_frame_finish(rsv_space* s, rsv_counts* out);
 int32_t rsv_results_view(rsv_space* s, rsv_results* out);
+/* Per tester slot: first record and number of records in the hit buffer of the last frame run with
+ * RSV_FRAME_TESTER_TABLE (random access for a single Shape.IntersectionTest call); non-testers have count 0. */
+int32_t rsv_tester_table(rsv_space* s, uint32_t* first, uint32_t* count, uint64_t n_shapes);
 int32_t rsv_timing(rsv_space* s, rsv_timing_info* out);
 /* Block until all work queued on the space's stream is done. */
 int32_t rsv_sync(rsv_space* s);

@@ -29,7 +29,8 @@ ABI_SYMBOLS = [
     "rsv_reserve", "rsv_staging", "rsv_set_counts", "rsv_commit", "rsv_device_buffer", "rsv_frame",
     "rsv_frame_launch", "rsv_frame_finish", "rsv_results_view", "rsv_timing", "rsv_sync", "rsv_timer_start",
     "rsv_timer_stop", "rsv_debug_cells", "rsv_debug_cell_rects", "rsv_linetest", "rsv_linetest_launch",
-    "rsv_linetest_finish", "rsv_ray_staging", "rsv_ray_reserve", "rsv_ray_results_view",
+    "rsv_linetest_finish", "rsv_ray_staging", "rsv_ray_reserve", "rsv_ray_results_view", "rsv_tester_table",
+    "rsv_set_stream", "rsv_strip_setup", "rsv_halo_pack", "rsv_halo_apply",
 ]
 
 
@@ -135,6 +136,8 @@ def load():
     L.rsv_timer_start.argtypes = [vp]
     L.rsv_timer_stop.restype = i32
     L.rsv_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
+    L.rsv_tester_table.restype = i32
+    L.rsv_tester_table.argtypes = [vp, vp, vp, u64]
     L.rsv_debug_cells.restype = i32
     L.rsv_debug_cells.argtypes = [vp, vp, u64, vp, u64]
     L.rsv_debug_cell_rects.restype = i32
@@ -266,6 +269,13 @@ class DeviceSpace:
         hits = _view(r.hits, int(r.n_hit_records) * HIT_DTYPE.itemsize, HIT_DTYPE) if r.n_hit_records else np.zeros(0, HIT_DTYPE)
         con = _view(r.contacts, int(r.n_contacts) * CONTACT_DTYPE.itemsize, CONTACT_DTYPE) if r.n_contacts else np.zeros(0, CONTACT_DTYPE)
         return hits, con
+
+    def tester_table(self):
+        """(first, count) per slot of the last frame run with FRAME_TESTER_TABLE."""
+        first = np.zeros(self.n_shapes, dtype=np.uint32)
+        count = np.zeros(self.n_shapes, dtype=np.uint32)
+        self._check(self.L.rsv_tester_table(self.h, first.ctypes.data, count.ctypes.data, self.n_shapes))
+        return first, count
 
     def timing(self):
         t = TimingInfo()

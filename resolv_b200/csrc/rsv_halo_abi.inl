@@ -65,4 +65,18 @@ int32_t rsv_halo_apply(rsv_space* s, const void* dev_recv_up, int32_t slot_off_u
     return RSV_OK;
 }
 
+// Per-tester (first record, record count) of the last RSV_FRAME_TESTER_TABLE frame, copied to host arrays.
+int32_t rsv_tester_table(rsv_space* s, uint32_t* first, uint32_t* count, uint64_t n_shapes) {
+    if (!s || !first || !count) return RSV_ERR_BAD_ARG;
+    if (n_shapes != s->d.n_shapes) return fail(s, RSV_ERR_BAD_ARG, "rsv_tester_table: expected %u shapes", s->d.n_shapes);
+    if (!(s->launched_flags & RSV_FRAME_TESTER_TABLE)) return fail(s, RSV_ERR_BAD_ARG, "rsv_tester_table: last frame ran without RSV_FRAME_TESTER_TABLE");
+    CU(s, cudaSetDevice(s->device));
+    CU(s, cudaStreamSynchronize(s->stream));
+    if (n_shapes) {
+        CU(s, cudaMemcpy(first, s->d.tester_start, (size_t)n_shapes * 4, cudaMemcpyDeviceToHost));
+        CU(s, cudaMemcpy(count, s->d.tester_count, (size_t)n_shapes * 4, cudaMemcpyDeviceToHost));
+    }
+    return RSV_OK;
+}
+
 }  // extern "C"

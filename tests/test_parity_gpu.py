@@ -176,3 +176,21 @@ def test_kat_pairs_through_the_device():
         assert np.abs(con["p"][f:f + 2] - np.array([[402.9, 205.0], [405.0, 196.9]])).max() < 1e-9
     finally:
         ds.close()
+
+
+def test_tester_table_indexes_the_records_of_each_tester():
+    w = worlds.make_mixed(6000, space=4000, cell=32, filtered=False)
+    ds = space_for_world(w)
+    try:
+        c = ds.frame(1, _abi.FRAME_DOWNLOAD | _abi.FRAME_TESTER_TABLE, grow=True)
+        hits, con = ds.results()
+        first, count = ds.tester_table()
+        assert int(count.sum()) == len(hits) == c.n_gated
+        cnt = count.astype(np.int64)
+        idx = np.repeat(first.astype(np.int64), cnt) + (np.arange(int(cnt.sum())) - np.repeat(np.cumsum(cnt) - cnt, cnt))
+        assert np.array_equal(hits["a"][idx], np.repeat(np.arange(w.n), cnt))
+        rk = (hits["count_rank"][idx] >> 8).astype(np.int64)
+        same = hits["a"][idx][1:] == hits["a"][idx][:-1]
+        assert np.all(rk[1:][same] > rk[:-1][same]), "records of a tester are not in generation order"
+    finally:
+        ds.close()
