@@ -131,7 +131,10 @@ static int32_t alloc_outputs(rsv_space* s, uint32_t cap_entries, uint32_t cap_pa
     if (cap_pairs > d.cap_pairs) {
         if (d.hits) cudaFree(d.hits);
         d.hits = nullptr; d.cap_pairs = 0;
+        if (d.kind_queue) cudaFree(d.kind_queue);
+        d.kind_queue = nullptr;
         CU(s, cudaMalloc(&d.hits, (size_t)cap_pairs * sizeof(rsv_hit)));
+        CU(s, cudaMalloc(&d.kind_queue, (size_t)cap_pairs * 4 * sizeof(uint32_t)));
         d.cap_pairs = cap_pairs;
     }
     if (cap_contacts > d.cap_contacts) {
@@ -255,7 +258,7 @@ int32_t rsv_destroy(rsv_space* s) {
         if (s->host_buf[b]) cudaFreeHost(s->host_buf[b]);
     }
     DevView& d = s->d;
-    void* dev[] = {d.aabb, d.crect, d.cell, d.entries, d.ent_box, d.tile_state, d.tester_start, d.tester_count, d.orphans, d.ghosts, d.n_ghosts, d.hits, d.contacts, d.ctr};
+    void* dev[] = {d.aabb, d.crect, d.cell, d.entries, d.ent_box, d.tile_state, d.tester_start, d.tester_count, d.orphans, d.ghosts, d.n_ghosts, d.hits, d.kind_queue, d.contacts, d.ctr};
     for (void* p : dev) if (p) cudaFree(p);
     if (s->h_ctr) cudaFreeHost(s->h_ctr);
     if (s->h_hits) cudaFreeHost(s->h_hits);
@@ -364,7 +367,10 @@ int32_t rsv_frame_launch(rsv_space* s, int32_t margin, uint32_t flags) {
     const bool grid_only = (flags & RSV_FRAME_GRID_ONLY) != 0;
     if (d.n_shapes && !grid_only) k_pairs<<<s->pairs_blocks, kPairsBlock, 0, st>>>(d, margin, flags);
     mark(RSV_K_NARROW);
-    if (!grid_only) k_narrow<<<s->narrow_blocks, kNarrowBlock, 0, st>>>(d);
+    if (!grid_only) {
+        k_bin<<<s->sm_count * 4, 256, 0, st>>>(d);
+        k_narrow<<<s->narrow_blocks, kNarrowBlock, 0, st>>>(d);
+    }
     mark(RSV_K_COUNT);
     CU(s, cudaGetLastError());
     CU(s, cudaMemcpyAsync(s->h_ctr, d.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));

@@ -23,6 +23,9 @@ namespace rsv {
 
 constexpr int kNarrowBlock = 128;
 constexpr int kStageVerts = 8;  // polygons with more vertices are read through L1 instead of shared memory
+#ifndef RSV_NARROW_MIN_BLOCKS
+#define RSV_NARROW_MIN_BLOCKS 4
+#endif
 
 struct Poly {
     const double2* sm;  // staged transformed vertices of this thread (stride kNarrowBlock) or nullptr
@@ -231,49 +234,77 @@ __device__ __forceinline__ Poly make_poly(const DevView& d, uint32_t slot, uint3
     return p;
 }
 
-__global__ void __launch_bounds__(kNarrowBlock) k_narrow(DevView d) {
-    __shared__ double2 s_va[kStageVerts][kNarrowBlock];
-    __shared__ double2 s_vb[kStageVerts][kNarrowBlock];
-    const int lane = threadIdx.x & 31;
+// Pair kinds: bit 1 = tester is a ConvexPolygon, bit 0 = other is a ConvexPolygon (circle.go:69-82, convexPolygon.go:288-300).
+enum { kCircleCircle = 0, kCircleConvex = 1, kConvexCircle = 2, kConvexConvex = 3 };
+
+// Bins the gated records by pair kind so that every warp of k_narrow runs ONE of the four pair tests (a mixed
+// world otherwise diverges four ways, times the spread of polygon sizes: 3 active lanes per warp were measured).
+// Records that failed the Bounds gate (RSV_FRAME_ALL_CANDIDATES dumps) are finalised here as empty sets.
+__global__ void __launch_bounds__(256) k_bin(DevView d) {
     if (d.ctr->overflow & RSV_OVF_PAIRS) return;  // records past the capacity were never written: frame is retried
     const uint32_t n_rec = min(d.ctr->pair_cursor, d.cap_pairs);
-    const uint32_t stride = gridDim.x * kNarrowBlock;
-    for (uint32_t base = blockIdx.x * kNarrowBlock; base < n_rec; base += stride) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n_rec; base += stride) {
         const uint32_t p = base + threadIdx.x;
-        const bool live = p < n_rec;
-        uint32_t A = 0, B = 0, cr = 0;
+        int kind = -1;
+        if (p < n_rec) {
+            const uint4 rec = *reinterpret_cast<const uint4*>(d.hits + p);
+            if (rec.w & RSV_HIT_NOT_GATED) {
+                reinterpret_cast<double2*>(d.hits + p)[1] = make_double2(0.0, 0.0);
+            } else {
+                kind = ((__ldg(d.meta + rec.x) & RSV_META_POLYGON) ? 2 : 0) | ((__ldg(d.meta + rec.y) & RSV_META_POLYGON) ? 1 : 0);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t m = __ballot_sync(0xffffffffu, kind == k);
+            if (m == 0) continue;
+            uint32_t at = 0;
+            if (lane == __ffs(m) - 1) at = atomicAdd(&d.ctr->kind_count[k], __popc(m));
+            at = __shfl_sync(0xffffffffu, at, __ffs(m) - 1);
+            if (kind == k) d.kind_queue[(size_t)k * d.cap_pairs + at + __popc(m & ((1u << lane) - 1u))] = p;
+        }
+    }
+}
+
+// One ordered pair of kind KIND, owned by one lane. Two passes around the warp-aggregated contact allocation.
+template <int KIND>
+__device__ __forceinline__ void narrow_kind(const DevView& d, double2* sva, double2* svb, uint32_t n_q,
+                                            const uint32_t* queue) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t stride = gridDim.x * kNarrowBlock;
+    for (uint32_t base = blockIdx.x * kNarrowBlock; base < n_q; base += stride) {
+        const uint32_t qi = base + threadIdx.x;
+        const bool live = qi < n_q;
+        uint32_t p = 0, A = 0, B = 0, cr = 0;
         if (live) {
-            uint4 rec = *reinterpret_cast<const uint4*>(d.hits + p);
+            p = queue[qi];
+            const uint4 rec = *reinterpret_cast<const uint4*>(d.hits + p);
             A = rec.x; B = rec.y; cr = rec.w;
         }
-        const bool run = live && !(cr & RSV_HIT_NOT_GATED);
-        uint32_t metaA = 0, metaB = 0;
         V2 pa{0, 0}, pb{0, 0};
         double ra = 0, rb = 0;
         Poly PA, PB;
-        PA.n = PB.n = 0;
-        int kind = -1;  // 0 circle-circle, 1 circle-convex, 2 convex-circle, 3 convex-convex
+        PA.n = PB.n = PA.nl = PB.nl = 0;
         uint32_t n = 0;
         unsigned long long xmask = 0;  // crossing edge pairs (bit j*nlA + i) when nlA*nlB <= 64
         bool use_mask = false;
-        if (run) {
-            metaA = __ldg(d.meta + A); metaB = __ldg(d.meta + B);
+        if (live) {
             double2 t = __ldg(d.pos + A); pa = V2{t.x, t.y};
             t = __ldg(d.pos + B); pb = V2{t.x, t.y};
-            const bool polyA = metaA & RSV_META_POLYGON, polyB = metaB & RSV_META_POLYGON;
-            kind = (polyA ? 2 : 0) | (polyB ? 1 : 0);
-            if (polyA) PA = make_poly(d, A, metaA, pa, &s_va[0][threadIdx.x]); else ra = __ldg(d.radius + A);
-            if (polyB) PB = make_poly(d, B, metaB, pb, &s_vb[0][threadIdx.x]); else rb = __ldg(d.radius + B);
+            if (KIND & 2) PA = make_poly(d, A, __ldg(d.meta + A), pa, sva); else ra = __ldg(d.radius + A);
+            if (KIND & 1) PB = make_poly(d, B, __ldg(d.meta + B), pb, svb); else rb = __ldg(d.radius + B);
             // ---- pass 1: count contacts
-            if (kind == 3) {
+            if (KIND == kConvexConvex) {
                 use_mask = PA.nl * PB.nl <= 64;
                 visit_poly_poly(PA, PB, [&](V2, int j, int i) {
                     n++;
                     if (use_mask) xmask |= 1ull << (j * PA.nl + i);
                 });
-            } else if (kind == 2) {
+            } else if (KIND == kConvexCircle) {
                 visit_poly_circle(PA, pb, rb, [&](V2, int) { n++; });
-            } else if (kind == 1) {
+            } else if (KIND == kCircleConvex) {
                 visit_poly_circle(PB, pa, ra, [&](V2, int) { n++; });
             } else {
                 // circleCircleTest (shape.go:407-411)
@@ -305,7 +336,7 @@ __global__ void __launch_bounds__(kNarrowBlock) k_narrow(DevView d) {
         if (n && (unsigned long long)first + n <= d.cap_contacts) {
             rsv_contact* out = d.contacts + first;
             uint32_t w = 0;
-            if (kind == 3) {
+            if (KIND == kConvexConvex) {
                 // convexConvexTest (shape.go:438-479)
                 if (use_mask) {
                     // second pass only over the edge pairs that crossed in the first
@@ -328,7 +359,7 @@ __global__ void __launch_bounds__(kNarrowBlock) k_narrow(DevView d) {
                 sort_contacts(out, (int)n, ca);
                 V2 m;
                 if (mtv_poly_poly(PA, PB, ca, box_center(bb), m)) mtv = m;
-            } else if (kind == 2) {
+            } else if (KIND == kConvexCircle) {
                 // convexCircleTest (shape.go:356-397)
                 visit_poly_circle(PA, pb, rb, [&](V2 pt, int) {
                     if (w < n) store_contact(out + w, pt, vunit(vsub(pt, pb)));
@@ -337,7 +368,7 @@ __global__ void __launch_bounds__(kNarrowBlock) k_narrow(DevView d) {
                 sort_contacts(out, (int)n, pb);
                 V2 m;
                 if (mtv_poly_circle(PA, box_center(load_box_nc(d.aabb + A)), pb, rb, m)) mtv = m;
-            } else if (kind == 1) {
+            } else if (KIND == kCircleConvex) {
                 // circleConvexTest (shape.go:318-354): edge normals, unsorted, inverted MTV
                 visit_poly_circle(PB, pa, ra, [&](V2 pt, int i) {
                     if (w < n) store_contact(out + w, pt, edge_normal(PB.get(i), PB.line_end(i)));
@@ -364,14 +395,24 @@ __global__ void __launch_bounds__(kNarrowBlock) k_narrow(DevView d) {
         } else if (n) {
             n = 0;  // contact buffer overflow: report as capacity error, never write out of bounds
         }
-        rsv_hit hrec;
-        hrec.a = A; hrec.b = B; hrec.first_contact = first;
-        hrec.count_rank = (cr & ~0x7fu) | n;
-        hrec.mtv_x = mtv.x; hrec.mtv_y = mtv.y;
         uint4* hp = reinterpret_cast<uint4*>(d.hits + p);
-        hp[0] = make_uint4(hrec.a, hrec.b, hrec.first_contact, hrec.count_rank);
-        reinterpret_cast<double2*>(hp)[1] = make_double2(hrec.mtv_x, hrec.mtv_y);
+        hp[0] = make_uint4(A, B, first, (cr & ~0x7fu) | n);
+        reinterpret_cast<double2*>(hp)[1] = make_double2(mtv.x, mtv.y);
     }
+}
+
+__global__ void __launch_bounds__(kNarrowBlock, RSV_NARROW_MIN_BLOCKS) k_narrow(DevView d) {
+    __shared__ double2 s_va[kStageVerts][kNarrowBlock];
+    __shared__ double2 s_vb[kStageVerts][kNarrowBlock];
+    if (d.ctr->overflow & RSV_OVF_PAIRS) return;
+    double2* sva = &s_va[0][threadIdx.x];
+    double2* svb = &s_vb[0][threadIdx.x];
+    const uint32_t* q = d.kind_queue;
+    // heaviest kind first so that the light ones fill the tail
+    narrow_kind<kConvexConvex>(d, sva, svb, min(d.ctr->kind_count[3], d.cap_pairs), q + (size_t)3 * d.cap_pairs);
+    narrow_kind<kConvexCircle>(d, sva, svb, min(d.ctr->kind_count[2], d.cap_pairs), q + (size_t)2 * d.cap_pairs);
+    narrow_kind<kCircleConvex>(d, sva, svb, min(d.ctr->kind_count[1], d.cap_pairs), q + (size_t)1 * d.cap_pairs);
+    narrow_kind<kCircleCircle>(d, sva, svb, min(d.ctr->kind_count[0], d.cap_pairs), q);
 }
 
 }  // namespace rsv
