@@ -134,7 +134,7 @@ static int32_t alloc_outputs(rsv_space* s, uint32_t cap_entries, uint32_t cap_pa
         if (d.kind_queue) cudaFree(d.kind_queue);
         d.kind_queue = nullptr;
         CU(s, cudaMalloc(&d.hits, (size_t)cap_pairs * sizeof(rsv_hit)));
-        CU(s, cudaMalloc(&d.kind_queue, (size_t)cap_pairs * 4 * sizeof(uint32_t)));
+        CU(s, cudaMalloc(&d.kind_queue, (size_t)cap_pairs * kNarrowBins * sizeof(uint32_t)));
         d.cap_pairs = cap_pairs;
     }
     if (cap_contacts > d.cap_contacts) {
@@ -349,9 +349,13 @@ int32_t rsv_frame_launch(rsv_space* s, int32_t margin, uint32_t flags) {
     const bool timing = (flags & RSV_FRAME_TIMING) != 0;
     auto mark = [&](int k) { if (timing) cudaEventRecord(s->ev[k], st); };
     mark(RSV_K_CLEAR);
-    CU(s, cudaMemsetAsync(d.cell, 0, ((size_t)d.n_cells + 1) * 4, st));
-    CU(s, cudaMemsetAsync(d.tile_state, 0, (size_t)s->n_tiles * 8, st));
-    CU(s, cudaMemsetAsync(d.ctr, 0, offsetof(Counters, ray_hit_cursor), st));
+    {
+        // the cell array is allocated in whole scan tiles, so it can be cleared 16 B at a time past n_cells + 1
+        const uint32_t n4 = (uint32_t)(((size_t)d.n_cells + 1 + 3) / 4);
+        k_clear<<<blocks_for(n4, kGridBlock, s->sm_count * 8), kGridBlock, 0, st>>>(
+            reinterpret_cast<uint4*>(d.cell), n4, d.tile_state, s->n_tiles, reinterpret_cast<uint32_t*>(d.ctr),
+            (uint32_t)(offsetof(Counters, ray_hit_cursor) / 4));
+    }
     mark(RSV_K_BOUNDS);
     const int gcap = s->sm_count * 8;
     const uint32_t max_items = (d.own_hi - d.own_lo) + (d.n_ghosts ? d.cap_ghosts : 0u);

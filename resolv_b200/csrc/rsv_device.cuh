@@ -26,7 +26,7 @@ struct Counters {
     unsigned int contact_cursor;           // allocation cursor of the contact buffer
     unsigned int overflow;                 // RSV_OVF_*
     unsigned int scan_ticket;              // dynamic tile ids of the chained scan
-    unsigned int kind_count[4];            // gated records per pair kind (k_bin)
+    unsigned int kind_count[8];            // gated records per narrowphase bin (k_bin)
     // line tests
     unsigned int ray_hit_cursor;
     unsigned int ray_contact_cursor;
@@ -65,7 +65,7 @@ struct DevView {
     int32_t home_lo, home_hi;        // rows whose shapes run IntersectionTest here (default [0, H))
     // ---- results
     rsv_hit* hits;
-    uint32_t* kind_queue;            // [4][cap_pairs]: record indices binned by pair kind
+    uint32_t* kind_queue;            // [8][cap_pairs]: record indices binned by pair kind / staging class
     rsv_contact* contacts;
     Counters* ctr;
     // ---- geometry of the grid

@@ -107,6 +107,15 @@ __global__ void __launch_bounds__(kGridBlock) k_bounds(DevView d, int margin) {
     }
 }
 
+// Zeroes everything a frame accumulates into: per-cell counters, scan tile states, frame counters. One launch.
+__global__ void __launch_bounds__(kGridBlock) k_clear(uint4* __restrict__ cell4, uint32_t n4, unsigned long long* __restrict__ state,
+                                                      uint32_t n_tiles, uint32_t* __restrict__ ctr_words, uint32_t n_ctr_words) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    for (uint32_t i = tid; i < n4; i += stride) cell4[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (uint32_t i = tid; i < n_tiles; i += stride) state[i] = 0ull;
+    for (uint32_t i = tid; i < n_ctr_words; i += stride) ctr_words[i] = 0u;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Single-pass chained ("decoupled look-back") exclusive scan of uint32, in place: one read and one write of the
 // array. Tiles take their id from an atomic ticket so a tile only ever waits on tiles that already started.
@@ -160,23 +169,32 @@ __global__ void __launch_bounds__(kScanBlock) k_scan(uint32_t* __restrict__ data
         if (w < warp) warp_excl += t;
         block_sum += t;
     }
-    if (threadIdx.x == 0) {
+    if (warp == 0) {
+        // warp-parallel look-back: 32 predecessor tiles per step
         uint32_t excl = 0;
         if (tile == 0) {
-            st_state(state, (2ull << 32) | block_sum);
+            if (lane == 0) st_state(state, (2ull << 32) | block_sum);
         } else {
-            st_state(state + tile, (1ull << 32) | block_sum);
-            int t = (int)tile - 1;
+            if (lane == 0) st_state(state + tile, (1ull << 32) | block_sum);
+            int base = (int)tile - 1;
             for (;;) {
-                unsigned long long s;
-                do { s = ld_state(state + t); } while ((s >> 32) == 0);
-                excl += (uint32_t)s;
-                if ((s >> 32) == 2) break;
-                t--;
+                const int idx = base - lane;
+                unsigned long long sv = 2ull << 32;  // tiles before tile 0: inclusive prefix 0
+                if (idx >= 0) {
+                    do { sv = ld_state(state + idx); } while ((sv >> 32) == 0);
+                }
+                const uint32_t pm = __ballot_sync(0xffffffffu, (sv >> 32) == 2);
+                const int stop = pm ? __ffs(pm) - 1 : 31;  // nearest tile that already knows its inclusive prefix
+                uint32_t v = lane <= stop ? (uint32_t)sv : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                excl += v;
+                if (pm) break;
+                base -= 32;
             }
-            st_state(state + tile, (2ull << 32) | (unsigned long long)(excl + block_sum));
+            if (lane == 0) st_state(state + tile, (2ull << 32) | (unsigned long long)(excl + block_sum));
         }
-        s_prefix = excl;
+        if (lane == 0) s_prefix = excl;
     }
     __syncthreads();
     uint32_t run = s_prefix + warp_excl + (inc - sum);

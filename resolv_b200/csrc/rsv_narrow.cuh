@@ -27,14 +27,17 @@ constexpr int kStageVerts = 8;  // polygons with more vertices are read through 
 #define RSV_NARROW_MIN_BLOCKS 4
 #endif
 
-struct Poly {
-    const double2* sm;  // staged transformed vertices of this thread (stride kNarrowBlock) or nullptr
+// STAGED: the transformed vertices of this thread's polygon sit in shared memory (n <= kStageVerts); otherwise they
+// are re-derived from the local vertices in global memory on every access (same bits: one add per coordinate).
+template <bool STAGED>
+struct PolyT {
+    const double2* sm;  // staged transformed vertices of this thread (stride kNarrowBlock)
     const double2* gl;  // local vertices in global memory
     V2 pos;
     int n;   // vertices
     int nl;  // lines: n if Closed and n > 2, else n-1 (convexPolygon.go:117-141)
     __device__ __forceinline__ V2 get(int i) const {
-        if (sm) {
+        if (STAGED) {
             double2 v = sm[i * kNarrowBlock];
             return V2{v.x, v.y};
         }
@@ -49,6 +52,7 @@ struct Proj {
 };
 
 // ConvexPolygon.Project after axis.Unit() (convexPolygon.go:218-232); u is already normalised.
+template <class Poly>
 __device__ __forceinline__ Proj project_poly(const Poly& p, V2 u) {
     double mn = vdot(u, p.get(0)), mx = mn;
     for (int i = 1; i < p.n; i++) {
@@ -125,7 +129,7 @@ __device__ __forceinline__ V2 box_center(const Box& b) {
 }
 
 // One SAT axis step of calculateMTV (convexPolygon.go:430-441 and twins). axis is a line normal.
-template <class ProjOther>
+template <class Poly, class ProjOther>
 __device__ __forceinline__ bool sat_axis(const Poly& cp, V2 axis, ProjOther projOther, V2& smallest) {
     V2 u = vunit(axis);  // Project() re-normalises its argument
     double ov = overlap(project_poly(cp, u), projOther(u));
@@ -135,6 +139,7 @@ __device__ __forceinline__ bool sat_axis(const Poly& cp, V2 axis, ProjOther proj
 }
 
 // ConvexPolygon.calculateMTV, *ConvexPolygon case (convexPolygon.go:426-465, 503-513).
+template <class Poly>
 __device__ __forceinline__ bool mtv_poly_poly(const Poly& cp, const Poly& other, V2 centerCp, V2 centerOther, V2& out) {
     V2 smallest{DBL_MAX, 0.0};
     auto projOther = [&](V2 u) { return project_poly(other, u); };
@@ -152,6 +157,7 @@ __device__ __forceinline__ bool mtv_poly_poly(const Poly& cp, const Poly& other,
 // ConvexPolygon.calculateMTV, *Circle case (convexPolygon.go:467-513). The reference sorts a copy of the
 // vertices by distance to the circle centre only to take element 0; under its (stable, n <= 12) insertion sort
 // that is the first vertex attaining the strict minimum.
+template <class Poly>
 __device__ __forceinline__ bool mtv_poly_circle(const Poly& cp, V2 centerCp, V2 cpos, double radius, V2& out) {
     V2 closest = cp.get(0);
     double best = vmag(vsub(closest, cpos));
@@ -195,7 +201,7 @@ __device__ __forceinline__ void store_contact(rsv_contact* p, V2 pt, V2 nrm) {
 
 // Visits the contacts of convexConvexTest in generation order: for otherLine in B.Lines(): for line in A.Lines()
 // (shape.go:446-461). f(point, j, i) with j the index of B's line and i of A's.
-template <class F>
+template <class Poly, class F>
 __device__ __forceinline__ void visit_poly_poly(const Poly& A, const Poly& B, F f) {
     for (int j = 0; j < B.nl; j++) {
         V2 os = B.get(j), oe = B.line_end(j);
@@ -207,7 +213,7 @@ __device__ __forceinline__ void visit_poly_poly(const Poly& A, const Poly& B, F 
 }
 
 // Visits line/circle contacts for each line of the polygon (shape.go:328-341, 366-383). f(point, lineIndex).
-template <class F>
+template <class Poly, class F>
 __device__ __forceinline__ void visit_poly_circle(const Poly& P, V2 cpos, double radius, F f) {
     for (int i = 0; i < P.nl; i++) {
         V2 pts[2];
@@ -217,25 +223,26 @@ __device__ __forceinline__ void visit_poly_circle(const Poly& P, V2 cpos, double
     }
 }
 
-__device__ __forceinline__ Poly make_poly(const DevView& d, uint32_t slot, uint32_t meta, V2 pos, double2* stage) {
-    Poly p;
+template <bool STAGED>
+__device__ __forceinline__ PolyT<STAGED> make_poly(const DevView& d, uint32_t slot, uint32_t meta, V2 pos, double2* stage) {
+    PolyT<STAGED> p;
     p.n = (int)(meta >> RSV_META_NV_SHIFT);
     p.nl = ((meta & RSV_META_CLOSED) && p.n > 2) ? p.n : max(p.n - 1, 0);
     p.pos = pos;
     p.gl = d.verts + __ldg(d.vert_off + slot);
-    p.sm = nullptr;
-    if (p.n <= kStageVerts) {
+    p.sm = stage;
+    if (STAGED) {
         for (int i = 0; i < p.n; i++) {
             double2 v = __ldg(p.gl + i);
             stage[i * kNarrowBlock] = make_double2(dadd(v.x, pos.x), dadd(v.y, pos.y));
         }
-        p.sm = stage;
     }
     return p;
 }
 
 // Pair kinds: bit 1 = tester is a ConvexPolygon, bit 0 = other is a ConvexPolygon (circle.go:69-82, convexPolygon.go:288-300).
 enum { kCircleCircle = 0, kCircleConvex = 1, kConvexCircle = 2, kConvexConvex = 3 };
+constexpr int kNarrowBins = 8;  // pair kind, + 4 when a polygon exceeds kStageVerts
 
 // Bins the gated records by pair kind so that every warp of k_narrow runs ONE of the four pair tests (a mixed
 // world otherwise diverges four ways, times the spread of polygon sizes: 3 active lanes per warp were measured).
@@ -253,11 +260,15 @@ __global__ void __launch_bounds__(256) k_bin(DevView d) {
             if (rec.w & RSV_HIT_NOT_GATED) {
                 reinterpret_cast<double2*>(d.hits + p)[1] = make_double2(0.0, 0.0);
             } else {
-                kind = ((__ldg(d.meta + rec.x) & RSV_META_POLYGON) ? 2 : 0) | ((__ldg(d.meta + rec.y) & RSV_META_POLYGON) ? 1 : 0);
+                const uint32_t ma = __ldg(d.meta + rec.x), mb = __ldg(d.meta + rec.y);
+                kind = ((ma & RSV_META_POLYGON) ? 2 : 0) | ((mb & RSV_META_POLYGON) ? 1 : 0);
+                // bins 4..7: some polygon has too many vertices for the shared-memory stage
+                if (((ma & RSV_META_POLYGON) && (ma >> RSV_META_NV_SHIFT) > kStageVerts) ||
+                    ((mb & RSV_META_POLYGON) && (mb >> RSV_META_NV_SHIFT) > kStageVerts)) kind += 4;
             }
         }
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < kNarrowBins; k++) {
             const uint32_t m = __ballot_sync(0xffffffffu, kind == k);
             if (m == 0) continue;
             uint32_t at = 0;
@@ -269,7 +280,7 @@ __global__ void __launch_bounds__(256) k_bin(DevView d) {
 }
 
 // One ordered pair of kind KIND, owned by one lane. Two passes around the warp-aggregated contact allocation.
-template <int KIND>
+template <int KIND, bool STAGED>
 __device__ __forceinline__ void narrow_kind(const DevView& d, double2* sva, double2* svb, uint32_t n_q,
                                             const uint32_t* queue) {
     const int lane = threadIdx.x & 31;
@@ -285,7 +296,7 @@ __device__ __forceinline__ void narrow_kind(const DevView& d, double2* sva, doub
         }
         V2 pa{0, 0}, pb{0, 0};
         double ra = 0, rb = 0;
-        Poly PA, PB;
+        PolyT<STAGED> PA, PB;
         PA.n = PB.n = PA.nl = PB.nl = 0;
         uint32_t n = 0;
         unsigned long long xmask = 0;  // crossing edge pairs (bit j*nlA + i) when nlA*nlB <= 64
@@ -293,8 +304,8 @@ __device__ __forceinline__ void narrow_kind(const DevView& d, double2* sva, doub
         if (live) {
             double2 t = __ldg(d.pos + A); pa = V2{t.x, t.y};
             t = __ldg(d.pos + B); pb = V2{t.x, t.y};
-            if (KIND & 2) PA = make_poly(d, A, __ldg(d.meta + A), pa, sva); else ra = __ldg(d.radius + A);
-            if (KIND & 1) PB = make_poly(d, B, __ldg(d.meta + B), pb, svb); else rb = __ldg(d.radius + B);
+            if (KIND & 2) PA = make_poly<STAGED>(d, A, __ldg(d.meta + A), pa, sva); else ra = __ldg(d.radius + A);
+            if (KIND & 1) PB = make_poly<STAGED>(d, B, __ldg(d.meta + B), pb, svb); else rb = __ldg(d.radius + B);
             // ---- pass 1: count contacts
             if (KIND == kConvexConvex) {
                 use_mask = PA.nl * PB.nl <= 64;
@@ -408,11 +419,16 @@ __global__ void __launch_bounds__(kNarrowBlock, RSV_NARROW_MIN_BLOCKS) k_narrow(
     double2* sva = &s_va[0][threadIdx.x];
     double2* svb = &s_vb[0][threadIdx.x];
     const uint32_t* q = d.kind_queue;
+    const uint32_t* kc = d.ctr->kind_count;
+    const size_t cap = d.cap_pairs;
     // heaviest kind first so that the light ones fill the tail
-    narrow_kind<kConvexConvex>(d, sva, svb, min(d.ctr->kind_count[3], d.cap_pairs), q + (size_t)3 * d.cap_pairs);
-    narrow_kind<kConvexCircle>(d, sva, svb, min(d.ctr->kind_count[2], d.cap_pairs), q + (size_t)2 * d.cap_pairs);
-    narrow_kind<kCircleConvex>(d, sva, svb, min(d.ctr->kind_count[1], d.cap_pairs), q + (size_t)1 * d.cap_pairs);
-    narrow_kind<kCircleCircle>(d, sva, svb, min(d.ctr->kind_count[0], d.cap_pairs), q);
+    narrow_kind<kConvexConvex, true>(d, sva, svb, min(kc[3], d.cap_pairs), q + 3 * cap);
+    narrow_kind<kConvexCircle, true>(d, sva, svb, min(kc[2], d.cap_pairs), q + 2 * cap);
+    narrow_kind<kCircleConvex, true>(d, sva, svb, min(kc[1], d.cap_pairs), q + 1 * cap);
+    narrow_kind<kCircleCircle, true>(d, sva, svb, min(kc[0], d.cap_pairs), q);
+    narrow_kind<kConvexConvex, false>(d, sva, svb, min(kc[7], d.cap_pairs), q + 7 * cap);
+    narrow_kind<kConvexCircle, false>(d, sva, svb, min(kc[6], d.cap_pairs), q + 6 * cap);
+    narrow_kind<kCircleConvex, false>(d, sva, svb, min(kc[5], d.cap_pairs), q + 5 * cap);
 }
 
 }  // namespace rsv
