@@ -45,7 +45,24 @@ constexpr int kPairsChunk = 256;  // entries per grabbed chunk
 constexpr int kPairStage = 128;   // staged records per warp batch
 constexpr int kRowGroup = 4;      // query-rect rows flattened together
 constexpr int kItemRound = 160;   // items staged through shared memory per round
+constexpr int kCandWords = 60;    // super-round = kCandWords * 32 items = 12 rounds
+constexpr uint32_t kSuper = kCandWords * 32;
+static_assert(kSuper % kItemRound == 0, "super-rounds are whole rounds");
 constexpr uint32_t kNoEntry = 0xffffffffu;
+
+// Number of set bits of the candidate words in the item range [lo, hi) (indices relative to the super-round).
+__device__ __forceinline__ uint32_t popc_range(const uint32_t* cw, uint32_t lo, uint32_t hi) {
+    if (hi <= lo) return 0;
+    const uint32_t wl = lo >> 5, wh = (hi - 1) >> 5;
+    uint32_t n = 0;
+    for (uint32_t w = wl; w <= wh; w++) {
+        uint32_t m = cw[w];
+        if (w == wl) m &= 0xffffffffu << (lo & 31u);
+        if (w == wh) m &= 0xffffffffu >> (31u - ((hi - 1) & 31u));
+        n += __popc(m);
+    }
+    return n;
+}
 
 struct PairsWarpSmem {
     float4 itBox[kItemRound];   // cp.async landing zone: entry float boxes
@@ -64,6 +81,8 @@ struct PairsWarpSmem {
     uint32_t stB[kPairStage];   // staged records: other slot
     uint32_t stR[kPairStage];   // rank << 8 | flags
     uint32_t stT[kPairStage];   // tester lane << 24 | index within the tester's records
+    uint32_t cw[kCandWords];    // one candidate-bit word per 32 items of the current super-round (lazy ranks)
+    uint2 rng[32];              // per tester: its item range [first, last) in the current row group
 };
 
 enum PairsMode { kStage = 0, kCount = 1, kWrite = 2 };
@@ -112,9 +131,13 @@ __device__ __forceinline__ uint32_t pairs_pass(const DevView& d, bool all, Pairs
             if (lane >= o) incl += t;
         }
         const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        sm.rng[lane] = make_uint2(incl - c, incl);
         __syncwarp();
-        for (uint32_t rbeg = 0; rbeg < total; rbeg += kItemRound) {
-            const uint32_t rend = min(rbeg + (uint32_t)kItemRound, total);
+        for (uint32_t sbeg = 0; sbeg < total; sbeg += kSuper) {
+        const uint32_t send = min(sbeg + kSuper, total);
+        const uint32_t stage0 = produced;  // records staged before this super-round already carry their rank
+        for (uint32_t rbeg = sbeg; rbeg < send; rbeg += kItemRound) {
+            const uint32_t rend = min(rbeg + (uint32_t)kItemRound, send);
             // ---- issue: locate every item of the round and start its copy into shared memory
             for (uint32_t it = rbeg; it < rend; it += 32) {
                 const uint32_t i = min(it + lane, total - 1);  // (clamped lanes search too: shuffles need the full warp)
@@ -169,36 +192,61 @@ __device__ __forceinline__ uint32_t pairs_pass(const DevView& d, bool all, Pairs
                     maybe = cand && !(fb.z < fa.x || fb.x > fa.z || fb.w < fa.y || fb.y > fa.w);
                     if (MODE != kStage && maybe) gate = exact_gate(d, sm.A[t], B);
                 }
-                const uint32_t peers = __match_any_sync(0xffffffffu, valid ? t : 32 + lane);
-                const uint32_t cmask = __ballot_sync(0xffffffffu, cand);
-                const uint32_t rank = sm.cand[t] + __popc(cmask & peers & lt);
-                const bool rec = MODE == kStage ? (maybe || (all && cand)) : (gate || (all && cand));
-                const uint32_t rmask = __ballot_sync(0xffffffffu, rec);
-                uint32_t gidx = 0;
-                if (MODE != kStage) gidx = sm.gated[t] + __popc(rmask & peers & lt);
-                __syncwarp();
-                if (valid && (peers & lt) == 0) {  // first lane of each tester's run updates its counters
-                    sm.cand[t] += __popc(cmask & peers);
-                    if (MODE != kStage) sm.gated[t] += __popc(rmask & peers);
-                }
-                if (rec) {
-                    if (MODE == kStage) {
+                if (MODE == kStage) {
+                    // slim path: no per-item rank. One candidate-bit word per step; ranks are derived from the words at
+                    // the end of the super-round, and only for the few staged survivors.
+                    const uint32_t cmask = __ballot_sync(0xffffffffu, cand);
+                    const bool rec = maybe || (all && cand);
+                    const uint32_t rmask = __ballot_sync(0xffffffffu, rec);
+                    if (lane == 0) sm.cw[(it - sbeg) >> 5] = cmask;
+                    if (rec) {
                         const uint32_t slot = produced + __popc(rmask & lt);
                         if (slot < kPairStage) {
                             sm.stB[slot] = B;
-                            sm.stR[slot] = (rank << 8) | (maybe ? 0u : RSV_HIT_NOT_GATED);
+                            sm.stR[slot] = ((i - sbeg) << 8) | (maybe ? 0u : RSV_HIT_NOT_GATED);  // item index for now
                             sm.stT[slot] = t << 24;
                         }
-                    } else if (MODE == kWrite) {
-                        const unsigned long long pos = (unsigned long long)chunk + sm.excl[t] + gidx;
-                        if (pos < d.cap_pairs)
-                            *reinterpret_cast<uint4*>(d.hits + pos) =
-                                make_uint4(sm.A[t], B, 0u, (rank << 8) | (gate ? 0u : RSV_HIT_NOT_GATED));
                     }
+                    produced += __popc(rmask);
+                    continue;
+                }
+                const uint32_t peers = __match_any_sync(0xffffffffu, valid ? t : 32 + lane);
+                const uint32_t cmask = __ballot_sync(0xffffffffu, cand);
+                const uint32_t rank = sm.cand[t] + __popc(cmask & peers & lt);
+                const bool rec = gate || (all && cand);
+                const uint32_t rmask = __ballot_sync(0xffffffffu, rec);
+                const uint32_t gidx = sm.gated[t] + __popc(rmask & peers & lt);
+                __syncwarp();
+                if (valid && (peers & lt) == 0) {  // first lane of each tester's run updates its counters
+                    sm.cand[t] += __popc(cmask & peers);
+                    sm.gated[t] += __popc(rmask & peers);
+                }
+                if (rec && MODE == kWrite) {
+                    const unsigned long long pos = (unsigned long long)chunk + sm.excl[t] + gidx;
+                    if (pos < d.cap_pairs)
+                        *reinterpret_cast<uint4*>(d.hits + pos) =
+                            make_uint4(sm.A[t], B, 0u, (rank << 8) | (gate ? 0u : RSV_HIT_NOT_GATED));
                 }
                 produced += __popc(rmask);
                 __syncwarp();
             }
+        }
+        if (MODE == kStage) {
+            // ---- end of the super-round: ranks of the survivors staged in it, then fold its candidates into the bases
+            __syncwarp();
+            const uint32_t stage1 = min(produced, (uint32_t)kPairStage);
+            for (uint32_t r = stage0 + lane; r < stage1; r += 32) {
+                const uint32_t t = sm.stT[r] >> 24, w = sm.stR[r];
+                const uint2 rg = sm.rng[t];
+                const uint32_t lo = max(rg.x, sbeg) - sbeg;
+                sm.stR[r] = ((sm.cand[t] + popc_range(sm.cw, lo, w >> 8)) << 8) | (w & 0xffu);
+            }
+            __syncwarp();
+            const uint2 rg = sm.rng[lane];
+            const uint32_t lo = max(rg.x, sbeg), hi = min(rg.y, send);
+            if (hi > lo) sm.cand[lane] += popc_range(sm.cw, lo - sbeg, hi - sbeg);
+            __syncwarp();
+        }
         }
     }
     return produced;
