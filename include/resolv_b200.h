@@ -166,6 +166,11 @@ int32_t rsv_set_counts(rsv_space* s, uint32_t n_shapes, uint32_t n_verts);
 /* Upload slots [lo,hi) of every buffer in `which_mask` (bit RSV_BUF_x); RSV_BUF_VERTS uploads the whole live
  * vertex pool. Replaces the write side of ShapeBase.update (shape.go:239-242): the host only marks dirty ranges. */
 int32_t rsv_commit(rsv_space* s, uint32_t which_mask, uint32_t lo, uint32_t hi);
+/* Double-buffered position staging for pipelined hosts: page 0 is rsv_staging(RSV_BUF_POS), page 1 a second pinned
+ * buffer of the same size. The host writes frame f+1's positions into one page while frame f's upload (queued by
+ * rsv_commit_pos_page) still reads the other. Only RSV_BUF_POS has pages. */
+void* rsv_staging_page(rsv_space* s, int32_t which, int32_t page, size_t* bytes);
+int32_t rsv_commit_pos_page(rsv_space* s, int32_t page, uint32_t lo, uint32_t hi);
 /* Device address of buffer `which` (for device-side producers such as the multi-GPU halo unpack). */
 void* rsv_device_buffer(rsv_space* s, int32_t which);
 
@@ -178,8 +183,11 @@ void* rsv_device_buffer(rsv_space* s, int32_t which);
  * OnIntersect is replayed by the host from rsv_results. */
 int32_t rsv_frame(rsv_space* s, int32_t margin, uint32_t flags, rsv_counts* out);
 /* The same frame split in two so that a host can queue work without blocking: rsv_frame_launch enqueues every
- * kernel on the space's stream and returns; rsv_frame_finish waits, fills the counters and (RSV_FRAME_DOWNLOAD)
- * the result mirrors. rsv_frame == launch + finish. */
+ * kernel on the space's stream and returns; rsv_frame_finish waits for the OLDEST launched frame, fills the counters
+ * and (RSV_FRAME_DOWNLOAD) the result mirrors. rsv_frame == launch + finish. Two frames may be in flight: results
+ * live in two buffer sets and the download of frame f runs on a separate copy stream, so calling
+ * rsv_frame_launch(f+1) before rsv_frame_finish(f) overlaps f's device-to-host copy with f+1's upload and kernels.
+ * Launching a third frame without finishing drops the oldest frame's results. */
 int32_t rsv_frame_launch(rsv_space* s, int32_t margin, uint32_t flags);
 int32_t rsv_frame_finish(rsv_space* s, rsv_counts* out);
 int32_t rsv_results_view(rsv_space* s, rsv_results* out);

@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "rsv_frame_launch", "rsv_frame_finish", "rsv_results_view", "rsv_timing", "rsv_sync", "rsv_timer_start",
     "rsv_timer_stop", "rsv_debug_cells", "rsv_debug_cell_rects", "rsv_linetest", "rsv_linetest_launch",
     "rsv_linetest_finish", "rsv_ray_staging", "rsv_ray_reserve", "rsv_ray_results_view", "rsv_tester_table",
-    "rsv_set_stream", "rsv_strip_setup", "rsv_halo_pack", "rsv_halo_apply",
+    "rsv_set_stream", "rsv_strip_setup", "rsv_halo_pack", "rsv_halo_apply", "rsv_staging_page", "rsv_commit_pos_page",
 ]
 
 
@@ -136,6 +136,10 @@ def load():
     L.rsv_timer_start.argtypes = [vp]
     L.rsv_timer_stop.restype = i32
     L.rsv_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
+    L.rsv_staging_page.restype = vp
+    L.rsv_staging_page.argtypes = [vp, i32, i32, C.POINTER(C.c_size_t)]
+    L.rsv_commit_pos_page.restype = i32
+    L.rsv_commit_pos_page.argtypes = [vp, i32, u32, u32]
     L.rsv_tester_table.restype = i32
     L.rsv_tester_table.argtypes = [vp, vp, vp, u64]
     L.rsv_debug_cells.restype = i32
@@ -231,6 +235,17 @@ class DeviceSpace:
 
     def commit(self, mask, lo=0, hi=None):
         self._check(self.L.rsv_commit(self.h, mask, lo, self.n_shapes if hi is None else hi))
+
+    def pos_page(self, page):
+        """numpy view of position staging page 0 / 1 (double-buffered uploads)."""
+        nb = C.c_size_t()
+        p = self.L.rsv_staging_page(self.h, BUF_POS, page, C.byref(nb))
+        if not p:
+            raise RsvError(RSV_ERR_OOM, "rsv_staging_page failed")
+        return _view(p, nb.value, np.float64)
+
+    def commit_pos_page(self, page, lo=0, hi=None):
+        self._check(self.L.rsv_commit_pos_page(self.h, page, lo, self.n_shapes if hi is None else hi))
 
     def sync(self):
         self._check(self.L.rsv_sync(self.h))

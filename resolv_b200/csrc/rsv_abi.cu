@@ -39,14 +39,25 @@ struct rsv_space {
     size_t elem_bytes[RSV_BUF_COUNT] = {};
     uint32_t n_shapes = 0, n_verts = 0;
     uint32_t n_tiles = 0;
-    // pinned mirrors
-    Counters* h_ctr = nullptr;
-    rsv_hit* h_hits = nullptr;
-    rsv_contact* h_contacts = nullptr;
-    uint32_t h_cap_pairs = 0, h_cap_contacts = 0;
-    // frame state
-    uint32_t launched_flags = 0;
-    bool frame_pending = false;
+    // Two frames can be in flight: frame f's results are copied to the host on `copy_stream` while frame f+1's
+    // upload and kernels run on `stream`, so each slot has its own result buffers, pinned mirrors and counters.
+    struct FrameSlot {
+        rsv_hit* hits = nullptr;
+        rsv_contact* contacts = nullptr;
+        uint32_t* kind_queue = nullptr;
+        Counters* h_ctr = nullptr;  // pinned
+        rsv_hit* h_hits = nullptr;  // pinned mirrors, allocated on first download
+        rsv_contact* h_contacts = nullptr;
+        uint32_t h_cap_pairs = 0, h_cap_contacts = 0;
+        cudaEvent_t ev_done = nullptr;
+        uint32_t flags = 0;
+        bool pending = false;
+    } slot[2];
+    int launch_slot = 0, finish_slot = 0, last_slot = 0;
+    cudaStream_t copy_stream = nullptr;
+    Counters* h_ctr = nullptr;       // pinned counters of the line tests
+    void* host_pos_page1 = nullptr;  // second pinned staging page for RSV_BUF_POS (rsv_staging_page)
+    uint32_t launched_flags = 0;     // flags of the last finished frame
     rsv_counts last_counts{};
     uint64_t last_records = 0, last_contacts = 0;
     cudaEvent_t ev[RSV_K_COUNT + 1] = {};
@@ -129,20 +140,26 @@ static int32_t alloc_outputs(rsv_space* s, uint32_t cap_entries, uint32_t cap_pa
         d.cap_entries = cap_entries;
     }
     if (cap_pairs > d.cap_pairs) {
-        if (d.hits) cudaFree(d.hits);
-        d.hits = nullptr; d.cap_pairs = 0;
-        if (d.kind_queue) cudaFree(d.kind_queue);
-        d.kind_queue = nullptr;
-        CU(s, cudaMalloc(&d.hits, (size_t)cap_pairs * sizeof(rsv_hit)));
-        CU(s, cudaMalloc(&d.kind_queue, (size_t)cap_pairs * kNarrowBins * sizeof(uint32_t)));
+        d.cap_pairs = 0;
+        for (auto& sl : s->slot) {
+            if (sl.hits) cudaFree(sl.hits);
+            if (sl.kind_queue) cudaFree(sl.kind_queue);
+            sl.hits = nullptr; sl.kind_queue = nullptr;
+            CU(s, cudaMalloc(&sl.hits, (size_t)cap_pairs * sizeof(rsv_hit)));
+            CU(s, cudaMalloc(&sl.kind_queue, (size_t)cap_pairs * kNarrowBins * sizeof(uint32_t)));
+        }
         d.cap_pairs = cap_pairs;
     }
     if (cap_contacts > d.cap_contacts) {
-        if (d.contacts) cudaFree(d.contacts);
-        d.contacts = nullptr; d.cap_contacts = 0;
-        CU(s, cudaMalloc(&d.contacts, (size_t)cap_contacts * sizeof(rsv_contact)));
+        d.cap_contacts = 0;
+        for (auto& sl : s->slot) {
+            if (sl.contacts) cudaFree(sl.contacts);
+            sl.contacts = nullptr;
+            CU(s, cudaMalloc(&sl.contacts, (size_t)cap_contacts * sizeof(rsv_contact)));
+        }
         d.cap_contacts = cap_contacts;
     }
+    d.hits = s->slot[0].hits; d.kind_queue = s->slot[0].kind_queue; d.contacts = s->slot[0].contacts;
     return RSV_OK;
 }
 
@@ -232,6 +249,11 @@ int32_t rsv_create(const rsv_config* cfg, rsv_space** out) {
     CUC(cudaMalloc(&d.orphans, (size_t)N * 4));
     CUC(cudaMalloc(&d.ctr, sizeof(Counters)));
     CUC(cudaHostAlloc(&s->h_ctr, sizeof(Counters), cudaHostAllocDefault));
+    CUC(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    for (auto& sl : s->slot) {
+        CUC(cudaHostAlloc(&sl.h_ctr, sizeof(Counters), cudaHostAllocDefault));
+        CUC(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+    }
     uint32_t ce = cfg->max_entries ? cfg->max_entries : (uint32_t)std::min<unsigned long long>(4ull * N + 4096, 0xfffffff0ull);
     uint32_t cp = cfg->max_pairs ? cfg->max_pairs : (uint32_t)std::min<unsigned long long>(2ull * N + 4096, 0xfffffff0ull);
     uint32_t cc = cfg->max_contacts ? cfg->max_contacts : (uint32_t)std::min<unsigned long long>(2ull * N + 4096, 0xfffffff0ull);
@@ -258,11 +280,19 @@ int32_t rsv_destroy(rsv_space* s) {
         if (s->host_buf[b]) cudaFreeHost(s->host_buf[b]);
     }
     DevView& d = s->d;
-    void* dev[] = {d.aabb, d.crect, d.cell, d.entries, d.ent_box, d.tile_state, d.tester_start, d.tester_count, d.orphans, d.ghosts, d.n_ghosts, d.hits, d.kind_queue, d.contacts, d.ctr};
+    void* dev[] = {d.aabb, d.crect, d.cell, d.entries, d.ent_box, d.tile_state, d.tester_start, d.tester_count, d.orphans, d.ghosts, d.n_ghosts, d.ctr};
     for (void* p : dev) if (p) cudaFree(p);
     if (s->h_ctr) cudaFreeHost(s->h_ctr);
-    if (s->h_hits) cudaFreeHost(s->h_hits);
-    if (s->h_contacts) cudaFreeHost(s->h_contacts);
+    if (s->host_pos_page1) cudaFreeHost(s->host_pos_page1);
+    for (auto& sl : s->slot) {
+        void* dv[] = {sl.hits, sl.contacts, sl.kind_queue};
+        for (void* p : dv) if (p) cudaFree(p);
+        if (sl.h_ctr) cudaFreeHost(sl.h_ctr);
+        if (sl.h_hits) cudaFreeHost(sl.h_hits);
+        if (sl.h_contacts) cudaFreeHost(sl.h_contacts);
+        if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+    }
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     lines_free(s->lines);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
     for (auto& e : s->ev_timer) if (e) cudaEventDestroy(e);
@@ -283,6 +313,9 @@ int32_t rsv_reserve(rsv_space* s, uint32_t max_entries, uint32_t max_pairs, uint
     if (!s) return RSV_ERR_BAD_ARG;
     CU(s, cudaSetDevice(s->device));
     CU(s, cudaStreamSynchronize(s->stream));
+    CU(s, cudaStreamSynchronize(s->copy_stream));
+    for (auto& sl : s->slot) sl.pending = false;  // frames in flight are dropped: their buffers are about to move
+    s->launch_slot = s->finish_slot = 0;
     return alloc_outputs(s, max_entries, max_pairs, max_contacts);
 }
 
@@ -290,6 +323,32 @@ void* rsv_staging(rsv_space* s, int32_t which, size_t* bytes) {
     if (!s || which < 0 || which >= RSV_BUF_COUNT) return nullptr;
     if (bytes) *bytes = s->buf_bytes[which];
     return s->host_buf[which];
+}
+
+// Second pinned page for the positions: the host writes frame f+1 into one page while frame f's upload reads the
+// other. page 0 is rsv_staging(RSV_BUF_POS).
+void* rsv_staging_page(rsv_space* s, int32_t which, int32_t page, size_t* bytes) {
+    if (!s || which != RSV_BUF_POS || page < 0 || page > 1) return nullptr;
+    if (bytes) *bytes = s->buf_bytes[which];
+    if (page == 0) return s->host_buf[which];
+    if (!s->host_pos_page1) {
+        if (cudaSetDevice(s->device) != cudaSuccess) return nullptr;
+        if (cudaHostAlloc(&s->host_pos_page1, s->buf_bytes[which], cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        memcpy(s->host_pos_page1, s->host_buf[which], s->buf_bytes[which]);
+    }
+    return s->host_pos_page1;
+}
+
+int32_t rsv_commit_pos_page(rsv_space* s, int32_t page, uint32_t lo, uint32_t hi) {
+    if (!s || page < 0 || page > 1) return RSV_ERR_BAD_ARG;
+    if (page == 1 && !s->host_pos_page1) return fail(s, RSV_ERR_BAD_ARG, "rsv_commit_pos_page: page 1 was never requested");
+    if (hi > s->n_shapes) hi = s->n_shapes;
+    if (lo >= hi) return RSV_OK;
+    CU(s, cudaSetDevice(s->device));
+    const char* src = (const char*)(page ? s->host_pos_page1 : s->host_buf[RSV_BUF_POS]);
+    CU(s, cudaMemcpyAsync((char*)s->dev_buf[RSV_BUF_POS] + (size_t)lo * 16, src + (size_t)lo * 16, (size_t)(hi - lo) * 16,
+                          cudaMemcpyHostToDevice, s->stream));
+    return RSV_OK;
 }
 
 void* rsv_device_buffer(rsv_space* s, int32_t which) {
@@ -346,6 +405,12 @@ int32_t rsv_frame_launch(rsv_space* s, int32_t margin, uint32_t flags) {
     CU(s, cudaSetDevice(s->device));
     DevView& d = s->d;
     cudaStream_t st = s->stream;
+    rsv_space::FrameSlot& sl = s->slot[s->launch_slot];
+    if (sl.pending) {  // both slots busy: the oldest frame was never finished -> its results are dropped
+        sl.pending = false;
+        if (s->finish_slot == s->launch_slot) s->finish_slot ^= 1;
+    }
+    d.hits = sl.hits; d.contacts = sl.contacts; d.kind_queue = sl.kind_queue;
     const bool timing = (flags & RSV_FRAME_TIMING) != 0;
     auto mark = [&](int k) { if (timing) cudaEventRecord(s->ev[k], st); };
     mark(RSV_K_CLEAR);
@@ -377,35 +442,41 @@ int32_t rsv_frame_launch(rsv_space* s, int32_t margin, uint32_t flags) {
     }
     mark(RSV_K_COUNT);
     CU(s, cudaGetLastError());
-    CU(s, cudaMemcpyAsync(s->h_ctr, d.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-    s->launched_flags = flags;
-    s->frame_pending = true;
+    CU(s, cudaMemcpyAsync(sl.h_ctr, d.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CU(s, cudaEventRecord(sl.ev_done, st));
+    sl.flags = flags;
+    sl.pending = true;
+    s->launch_slot ^= 1;
     return RSV_OK;
 }
 
-static int32_t ensure_mirrors(rsv_space* s) {
-    if (s->h_cap_pairs < s->d.cap_pairs) {
-        if (s->h_hits) cudaFreeHost(s->h_hits);
-        s->h_hits = nullptr; s->h_cap_pairs = 0;
-        CU(s, cudaHostAlloc(&s->h_hits, (size_t)s->d.cap_pairs * sizeof(rsv_hit), cudaHostAllocDefault));
-        s->h_cap_pairs = s->d.cap_pairs;
+static int32_t ensure_mirrors(rsv_space* s, rsv_space::FrameSlot& sl) {
+    if (sl.h_cap_pairs < s->d.cap_pairs) {
+        if (sl.h_hits) cudaFreeHost(sl.h_hits);
+        sl.h_hits = nullptr; sl.h_cap_pairs = 0;
+        CU(s, cudaHostAlloc(&sl.h_hits, (size_t)s->d.cap_pairs * sizeof(rsv_hit), cudaHostAllocDefault));
+        sl.h_cap_pairs = s->d.cap_pairs;
     }
-    if (s->h_cap_contacts < s->d.cap_contacts) {
-        if (s->h_contacts) cudaFreeHost(s->h_contacts);
-        s->h_contacts = nullptr; s->h_cap_contacts = 0;
-        CU(s, cudaHostAlloc(&s->h_contacts, (size_t)s->d.cap_contacts * sizeof(rsv_contact), cudaHostAllocDefault));
-        s->h_cap_contacts = s->d.cap_contacts;
+    if (sl.h_cap_contacts < s->d.cap_contacts) {
+        if (sl.h_contacts) cudaFreeHost(sl.h_contacts);
+        sl.h_contacts = nullptr; sl.h_cap_contacts = 0;
+        CU(s, cudaHostAlloc(&sl.h_contacts, (size_t)s->d.cap_contacts * sizeof(rsv_contact), cudaHostAllocDefault));
+        sl.h_cap_contacts = s->d.cap_contacts;
     }
     return RSV_OK;
 }
 
 int32_t rsv_frame_finish(rsv_space* s, rsv_counts* out) {
     if (!s) return RSV_ERR_BAD_ARG;
-    if (!s->frame_pending) return fail(s, RSV_ERR_BAD_ARG, "rsv_frame_finish: no frame launched");
+    rsv_space::FrameSlot& sl = s->slot[s->finish_slot];
+    if (!sl.pending) return fail(s, RSV_ERR_BAD_ARG, "rsv_frame_finish: no frame launched");
     CU(s, cudaSetDevice(s->device));
-    CU(s, cudaStreamSynchronize(s->stream));
-    s->frame_pending = false;
-    const Counters& c = *s->h_ctr;
+    CU(s, cudaEventSynchronize(sl.ev_done));  // this frame's kernels and counters are done; a newer frame may still run
+    sl.pending = false;
+    s->last_slot = s->finish_slot;
+    s->finish_slot ^= 1;
+    s->launched_flags = sl.flags;
+    const Counters& c = *sl.h_ctr;
     rsv_counts rc{};
     rc.n_shapes = s->d.n_shapes;
     rc.n_testers = c.n_testers;
@@ -432,11 +503,12 @@ int32_t rsv_frame_finish(rsv_space* s, rsv_counts* out) {
                     (unsigned long long)rc.n_entries, (unsigned long long)rc.n_gated, (unsigned long long)rc.n_contacts,
                     s->d.cap_entries, s->d.cap_pairs, s->d.cap_contacts);
     if (s->launched_flags & RSV_FRAME_DOWNLOAD) {
-        int32_t rcode = ensure_mirrors(s);
+        int32_t rcode = ensure_mirrors(s, sl);
         if (rcode != RSV_OK) return rcode;
-        if (rc.n_gated) CU(s, cudaMemcpyAsync(s->h_hits, s->d.hits, (size_t)rc.n_gated * sizeof(rsv_hit), cudaMemcpyDeviceToHost, s->stream));
-        if (rc.n_contacts) CU(s, cudaMemcpyAsync(s->h_contacts, s->d.contacts, (size_t)rc.n_contacts * sizeof(rsv_contact), cudaMemcpyDeviceToHost, s->stream));
-        CU(s, cudaStreamSynchronize(s->stream));
+        // on the copy stream: overlaps the upload and kernels of a newer frame already queued on `stream`
+        if (rc.n_gated) CU(s, cudaMemcpyAsync(sl.h_hits, sl.hits, (size_t)rc.n_gated * sizeof(rsv_hit), cudaMemcpyDeviceToHost, s->copy_stream));
+        if (rc.n_contacts) CU(s, cudaMemcpyAsync(sl.h_contacts, sl.contacts, (size_t)rc.n_contacts * sizeof(rsv_contact), cudaMemcpyDeviceToHost, s->copy_stream));
+        CU(s, cudaStreamSynchronize(s->copy_stream));
         s->last_records = rc.n_gated;
         s->last_contacts = rc.n_contacts;
     }
@@ -444,6 +516,10 @@ int32_t rsv_frame_finish(rsv_space* s, rsv_counts* out) {
 }
 
 int32_t rsv_frame(rsv_space* s, int32_t margin, uint32_t flags, rsv_counts* out) {
+    if (!s) return RSV_ERR_BAD_ARG;
+    // launch + finish of THIS frame: frames launched earlier and never finished are dropped
+    for (auto& sl : s->slot) sl.pending = false;
+    s->finish_slot = s->launch_slot;
     int32_t rc = rsv_frame_launch(s, margin, flags);
     if (rc != RSV_OK) return rc;
     return rsv_frame_finish(s, out);
@@ -451,9 +527,9 @@ int32_t rsv_frame(rsv_space* s, int32_t margin, uint32_t flags, rsv_counts* out)
 
 int32_t rsv_results_view(rsv_space* s, rsv_results* out) {
     if (!s || !out) return RSV_ERR_BAD_ARG;
-    out->hits = s->h_hits;
+    out->hits = s->slot[s->last_slot].h_hits;
     out->n_hit_records = s->last_records;
-    out->contacts = s->h_contacts;
+    out->contacts = s->slot[s->last_slot].h_contacts;
     out->n_contacts = s->last_contacts;
     return RSV_OK;
 }

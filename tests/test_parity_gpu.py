@@ -194,3 +194,40 @@ def test_tester_table_indexes_the_records_of_each_tester():
         assert np.all(rk[1:][same] > rk[:-1][same]), "records of a tester are not in generation order"
     finally:
         ds.close()
+
+
+def test_two_frames_in_flight_give_the_same_results_as_sequential_frames():
+    w = worlds.make_mixed(8000, space=4600, cell=32, filtered=False)
+    p0 = w.pos.copy()
+    worlds.advance(w, 1)
+    p1 = w.pos.copy()
+    ds = space_for_world(w)
+    try:
+        seq = []
+        for p in (p0, p1):
+            ds.set_positions(p)
+            c = ds.frame(1, _abi.FRAME_DOWNLOAD, grow=True)
+            h, k = ds.results()
+            seq.append((c.as_dict(), h.copy(), k.copy()))
+        pages = [ds.pos_page(0), ds.pos_page(1)]
+        pages[0][:2 * w.n] = p0.reshape(-1)
+        pages[1][:2 * w.n] = p1.reshape(-1)
+        ds.commit_pos_page(0)
+        ds.frame_launch(1, _abi.FRAME_DOWNLOAD)
+        ds.commit_pos_page(1)
+        ds.frame_launch(1, _abi.FRAME_DOWNLOAD)      # second frame queued before the first is finished
+        for i in range(2):
+            c = ds.frame_finish()
+            h, k = ds.results()
+            assert c.as_dict() == seq[i][0]
+            o, so = np.lexsort((h["b"], h["a"])), np.lexsort((seq[i][1]["b"], seq[i][1]["a"]))
+            assert np.array_equal(h["a"][o], seq[i][1]["a"][so]) and np.array_equal(h["b"][o], seq[i][1]["b"][so])
+            assert np.array_equal(h["count_rank"][o], seq[i][1]["count_rank"][so])
+            assert np.array_equal(h["mtv"][o].view(np.uint64), seq[i][1]["mtv"][so].view(np.uint64))
+            n = h["count_rank"][o] & 0x7f
+            dc = np.concatenate([k["p"][f:f + m] for f, m in zip(h["first_contact"][o], n)])
+            sc = np.concatenate([seq[i][2]["p"][f:f + m] for f, m in zip(seq[i][1]["first_contact"][so], n)])
+            assert np.array_equal(dc.view(np.uint64), sc.view(np.uint64))
+        assert seq[0][0] != seq[1][0]
+    finally:
+        ds.close()
