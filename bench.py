@@ -329,7 +329,17 @@ def run_reference(args):
 
 def main():
     args = parse()
-    out = run_reference(args) if args.impl == "reference" else run_b200(args)
+    # Exactly ONE line may reach stdout (the JSON): libraries that chat on fd 1 (NCCL prints its version there) are
+    # diverted to stderr while the benchmark runs.
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        out = run_reference(args) if args.impl == "reference" else run_b200(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
     if out is not None and int(os.environ.get("RANK", "0")) == 0:
         print(json.dumps(out), flush=True)
     try:
