@@ -134,9 +134,11 @@ static int32_t alloc_outputs(rsv_space* s, uint32_t cap_entries, uint32_t cap_pa
     if (cap_entries > d.cap_entries) {
         if (d.entries) cudaFree(d.entries);
         if (d.ent_box) cudaFree(d.ent_box);
-        d.entries = nullptr; d.ent_box = nullptr; d.cap_entries = 0;
+        if (d.ent_home) cudaFree(d.ent_home);
+        d.entries = nullptr; d.ent_box = nullptr; d.ent_home = nullptr; d.cap_entries = 0;
         CU(s, cudaMalloc(&d.entries, (size_t)cap_entries * 4));
         CU(s, cudaMalloc(&d.ent_box, (size_t)cap_entries * sizeof(float4)));
+        CU(s, cudaMalloc(&d.ent_home, (size_t)cap_entries * sizeof(uint2)));
         d.cap_entries = cap_entries;
     }
     if (cap_pairs > d.cap_pairs) {
@@ -168,8 +170,8 @@ int32_t rsv_create(const rsv_config* cfg, rsv_space** out) {
     *out = nullptr;
     if (cfg->space_w <= 0 || cfg->space_h <= 0 || cfg->cell_w <= 0 || cfg->cell_h <= 0)
         return fail(nullptr, RSV_ERR_BAD_ARG, "rsv_create: space and cell sizes must be positive");
-    if (cfg->max_shapes == 0 || cfg->max_shapes >= (1u << 27))
-        return fail(nullptr, RSV_ERR_BAD_ARG, "rsv_create: max_shapes must be in [1, 2^27)");
+    if (cfg->max_shapes == 0 || cfg->max_shapes >= (1u << 26))
+        return fail(nullptr, RSV_ERR_BAD_ARG, "rsv_create: max_shapes must be in [1, 2^26)");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -280,7 +282,7 @@ int32_t rsv_destroy(rsv_space* s) {
         if (s->host_buf[b]) cudaFreeHost(s->host_buf[b]);
     }
     DevView& d = s->d;
-    void* dev[] = {d.aabb, d.crect, d.cell, d.entries, d.ent_box, d.tile_state, d.tester_start, d.tester_count, d.orphans, d.ghosts, d.n_ghosts, d.ctr};
+    void* dev[] = {d.aabb, d.crect, d.cell, d.entries, d.ent_box, d.ent_home, d.tile_state, d.tester_start, d.tester_count, d.orphans, d.ghosts, d.n_ghosts, d.ctr};
     for (void* p : dev) if (p) cudaFree(p);
     if (s->h_ctr) cudaFreeHost(s->h_ctr);
     if (s->host_pos_page1) cudaFreeHost(s->host_pos_page1);

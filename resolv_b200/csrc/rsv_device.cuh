@@ -51,8 +51,9 @@ struct DevView {
     Box* aabb;            // world Bounds() per shape (circle.go:33-39, convexPolygon.go:158-161)
     int4* crect;          // Bounds.toCellSpace() per shape (utils.go:90-98), clamped to +-2^30
     uint32_t* cell;       // [n_cells+1]: after the frame, cell c holds entries[cell[c] .. cell[c+1])
-    uint32_t* entries;    // shape slot << 5 | flag bits (rsv_grid.cuh), ascending per cell
+    uint32_t* entries;    // shape slot << 6 | flag bits (rsv_grid.cuh), ascending per cell
     float4* ent_box;      // per entry: outward-rounded float32 copy of the shape's world AABB (minx,miny,maxx,maxy)
+    uint2* ent_home;      // per HOME entry: (global index of the home cell, columns-1 | rows-1 << 16 of the clamped rect)
     unsigned long long* tile_state;  // chained-scan tile descriptors
     uint32_t* tester_start;          // first pair record of tester i
     uint32_t* tester_count;          // number of pair records of tester i

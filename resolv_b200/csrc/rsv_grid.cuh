@@ -216,12 +216,12 @@ __global__ void __launch_bounds__(kScanBlock) k_scan(uint32_t* __restrict__ data
     }
 }
 
-// Entry encoding: slot << 5 | lastCol << 4 | lastRow << 3 | tester << 2 | firstCol << 1 | firstRow. The first/last flags say that this cell is
+// Entry encoding: slot << 6 | useAny << 5 | lastCol << 4 | lastRow << 3 | tester << 2 | firstCol << 1 | firstRow. The first/last flags say that this cell is
 // the first in-grid column / row of the shape's own cell rect; with them the candidate walk can apply the
 // owner-cell rule (emit a shape only from the first cell it shares with the query rect, i.e. the first
 // occurrence in the reference's row-major walk, cell.go:86-121) without loading the other shape's rect.
-constexpr uint32_t kEntFirstRow = 1u, kEntFirstCol = 2u, kEntTester = 4u, kEntLastRow = 8u, kEntLastCol = 16u;
-constexpr int kEntShift = 5;
+constexpr uint32_t kEntFirstRow = 1u, kEntFirstCol = 2u, kEntTester = 4u, kEntLastRow = 8u, kEntLastCol = 16u, kEntUseAny = 32u;
+constexpr int kEntShift = 6;
 
 __global__ void __launch_bounds__(kGridBlock) k_scatter(DevView d) {
     const uint32_t n = n_items(d);
@@ -232,7 +232,8 @@ __global__ void __launch_bounds__(kGridBlock) k_scatter(DevView d) {
         if (!clamp_rect(d, r, x0, y0, x1, y1)) continue;
         uint32_t meta = __ldg(d.meta + i);
         uint32_t base = cell_base(d, i);
-        uint32_t tag = (i << kEntShift) | (((meta & RSV_META_TESTER) && is_home(d, r)) ? kEntTester : 0u);
+        uint32_t tag = (i << kEntShift) | (((meta & RSV_META_TESTER) && is_home(d, r)) ? kEntTester : 0u) |
+                       ((meta & RSV_META_USE_ANY) ? kEntUseAny : 0u);
         for (int y = y0; y <= y1; y++) {
             uint32_t row = base + (uint32_t)(y - d.row_lo) * (uint32_t)d.W;
             for (int x = x0; x <= x1; x++) {
@@ -262,11 +263,23 @@ __global__ void __launch_bounds__(kGridBlock) k_cellsort(DevView d) {
 }
 
 // Fills the per-entry float32 boxes in final (sorted) entry order: one gather of the shape's AABB per entry,
-// coalesced 16 B stores. (Writing them from k_scatter instead would be 16 B stores to random slots.)
+// coalesced 16 B stores. (Writing them from k_scatter instead would be 16 B stores to random slots.) For a shape's
+// "home" entry (first row and first column of its cell rect) it also records where that cell is and how many
+// columns / rows the clamped rect spans, so that k_pairs can build the tester's query rect from coalesced loads
+// instead of gathering crect[] / space_idx[] by shape slot inside its latency-critical prologue.
 __global__ void __launch_bounds__(kGridBlock) k_entboxes(DevView d) {
     const uint32_t R = (uint32_t)min((unsigned long long)d.cap_entries, d.ctr->n_entries);
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < R; k += gridDim.x * blockDim.x)
-        d.ent_box[k] = float_box(load_box_nc(d.aabb + (d.entries[k] >> kEntShift)));
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < R; k += gridDim.x * blockDim.x) {
+        const uint32_t ent = d.entries[k];
+        const uint32_t i = ent >> kEntShift;
+        d.ent_box[k] = float_box(load_box_nc(d.aabb + i));
+        if ((ent & (kEntFirstRow | kEntFirstCol)) == (kEntFirstRow | kEntFirstCol)) {
+            int x0, y0, x1, y1;
+            clamp_rect(d, d.crect[i], x0, y0, x1, y1);
+            const uint32_t c = cell_base(d, i) + (uint32_t)(y0 - d.row_lo) * (uint32_t)d.W + (uint32_t)x0;
+            d.ent_home[k] = make_uint2(c, (uint32_t)(x1 - x0) | ((uint32_t)(y1 - y0) << 16));
+        }
+    }
 }
 
 }  // namespace rsv

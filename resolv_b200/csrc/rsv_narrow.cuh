@@ -257,7 +257,14 @@ __global__ void __launch_bounds__(256) k_bin(DevView d) {
         int kind = -1;
         if (p < n_rec) {
             const uint4 rec = *reinterpret_cast<const uint4*>(d.hits + p);
-            if (rec.w & RSV_HIT_NOT_GATED) {
+            bool gated = !(rec.w & RSV_HIT_NOT_GATED);
+            if (gated) {
+                // exact float64 Bounds gate (utils.go:146-173): k_pairs only applied the conservative float32 one
+                const Box a = load_box_nc(d.aabb + rec.x), o = load_box_nc(d.aabb + rec.y);
+                gated = bounds_gate(a.minx, a.miny, a.maxx, a.maxy, o.minx, o.miny, o.maxx, o.maxy);
+                if (!gated) d.hits[p].count_rank = rec.w | RSV_HIT_NOT_GATED;
+            }
+            if (!gated) {
                 reinterpret_cast<double2*>(d.hits + p)[1] = make_double2(0.0, 0.0);
             } else {
                 const uint32_t ma = __ldg(d.meta + rec.x), mb = __ldg(d.meta + rec.y);

@@ -27,8 +27,9 @@
 //    loads of a round are in flight together (the kernel is latency-bound otherwise) — then tests them from shared
 //    memory, every lane one item per step no matter how entries are distributed over testers.
 //  * Each entry carries an outward-rounded float32 copy of its shape's AABB. Disjoint float boxes imply disjoint
-//    float64 boxes, so ~90 % of candidates are rejected without touching the other shape's data; survivors are
-//    staged and take the exact float64 Bounds gate (utils.go:146-173) densely, one record per lane.
+//    float64 boxes, so ~90 % of candidates are rejected without touching the other shape's data; survivors become
+//    records, and the exact float64 Bounds gate (utils.go:146-173) is applied per record by k_bin, where the two
+//    AABB gathers are fully parallel instead of sitting in this kernel's serial chain.
 //  * Records are written with one allocation per batch, 16 B per lane, grouped by tester in generation order. A
 //    batch that overflows the stage falls back to an inline count pass + direct-write pass.
 #pragma once
@@ -190,7 +191,7 @@ __device__ __forceinline__ uint32_t pairs_pass(const DevView& d, bool all, Pairs
                     const float4 fb = sm.itBox[slot], fa = sm.fbox[t];
                     // float boxes are rounded outward, so "disjoint in float" implies the exact reject of utils.go:156
                     maybe = cand && !(fb.z < fa.x || fb.x > fa.z || fb.w < fa.y || fb.y > fa.w);
-                    if (MODE != kStage && maybe) gate = exact_gate(d, sm.A[t], B);
+                    gate = maybe;  // the exact float64 gate runs per record in k_bin
                 }
                 if (MODE == kStage) {
                     // slim path: no per-item rank. One candidate-bit word per step; ranks are derived from the words at
@@ -252,36 +253,25 @@ __device__ __forceinline__ uint32_t pairs_pass(const DevView& d, bool all, Pairs
     return produced;
 }
 
-// Exact float64 Bounds gate over the staged records, one record per lane, in stage order (which is rank order
-// within every tester). Assigns each surviving record its index within its tester.
-__device__ __forceinline__ uint32_t pairs_exact_gate(const DevView& d, bool all, PairsWarpSmem& sm, uint32_t staged) {
+// Assigns every staged record its index within its tester's records (stage order is generation order within a
+// tester), one record per lane.
+__device__ __forceinline__ uint32_t pairs_assign(PairsWarpSmem& sm, uint32_t staged) {
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
-    uint32_t produced = 0;
     for (uint32_t base = 0; base < staged; base += 32) {
         const uint32_t r = base + lane;
         const bool valid = r < staged;
-        uint32_t t = 0, word = 0;
-        bool gate = false;
-        if (valid) {
-            t = sm.stT[r] >> 24;
-            word = sm.stR[r];
-            if (!(word & RSV_HIT_NOT_GATED)) gate = exact_gate(d, sm.A[t], sm.stB[r]);
-        }
-        const bool rec = valid && (gate || all);
+        const uint32_t t = valid ? (sm.stT[r] >> 24) : 0u;
         const uint32_t peers = __match_any_sync(0xffffffffu, valid ? t : 32 + lane);
-        const uint32_t rmask = __ballot_sync(0xffffffffu, rec);
-        const uint32_t gidx = sm.gated[t] + __popc(rmask & peers & lt);
+        const uint32_t gidx = sm.gated[t] + __popc(peers & lt);
         __syncwarp();
         if (valid) {
-            if ((peers & lt) == 0) sm.gated[t] += __popc(rmask & peers);
-            sm.stR[r] = (word & ~(uint32_t)RSV_HIT_NOT_GATED) | (gate ? 0u : RSV_HIT_NOT_GATED);
-            sm.stT[r] = rec ? ((t << 24) | (gidx & 0xffffffu)) : 0xffffffffu;
+            if ((peers & lt) == 0) sm.gated[t] += __popc(peers);
+            sm.stT[r] = (t << 24) | (gidx & 0xffffffu);
         }
-        produced += __popc(rmask);
         __syncwarp();
     }
-    return produced;
+    return staged;
 }
 
 // One batch: lane `lane` owns a tester, given by its home entry index `hk` (or, for orphans, directly by slot A).
@@ -290,25 +280,40 @@ __device__ __forceinline__ void pairs_batch(const DevView& d, int margin, uint32
     const int lane = threadIdx.x & 31;
     const bool all = (flags & RSV_FRAME_ALL_CANDIDATES) != 0;
     int rows = 0, ncols = 0;
+    bool useAnyBit = false;
     const uint32_t* row0 = d.cell;
     if (have) {
+        const bool filters0 = !(flags & RSV_FRAME_NO_TAG_FILTERS);
+        int qx0, qx1, qy0, qy1;
+        uint32_t base_cell;
         if (hk != kNoEntry) {
-            A = d.entries[hk] >> kEntShift;
+            // everything about the tester comes from its home entry: three coalesced loads, no gather by slot
+            const uint32_t ent = d.entries[hk];
+            A = ent >> kEntShift;
+            useAnyBit = (ent & kEntUseAny) != 0;
             sm.fbox[lane] = d.ent_box[hk];
+            const uint2 hm = d.ent_home[hk];
+            const uint32_t local = hm.x % d.cells_per_space;
+            base_cell = hm.x - local;
+            const int x0 = (int)(local % (uint32_t)d.W), y0 = d.row_lo + (int)(local / (uint32_t)d.W);
+            // max(cx - m, 0) == max(x0 - m, 0) and min(ex + m, W-1) == min(x1 + m, W-1) for the clamped x0, x1
+            qx0 = max(x0 - margin, 0); qx1 = min(x0 + (int)(hm.y & 0xffffu) + margin, d.W - 1);
+            qy0 = max(y0 - margin, d.row_lo); qy1 = min(y0 + (int)(hm.y >> 16) + margin, d.row_hi - 1);
         } else {
             sm.fbox[lane] = float_box(load_box_nc(d.aabb + A));
+            useAnyBit = filters0 && (__ldg(d.meta + A) & RSV_META_USE_ANY) != 0;
+            const int4 r = d.crect[A];
+            qx0 = max(r.x - margin, 0); qx1 = min(r.z + margin, d.W - 1);
+            qy0 = max(r.y - margin, d.row_lo); qy1 = min(r.w + margin, d.row_hi - 1);
+            base_cell = cell_base(d, A);
         }
-        const uint32_t metaA = __ldg(d.meta + A);
-        const int4 r = d.crect[A];
-        const int qx0 = max(r.x - margin, 0), qx1 = min(r.z + margin, d.W - 1);
-        const int qy0 = max(r.y - margin, d.row_lo), qy1 = min(r.w + margin, d.row_hi - 1);
         if (qx0 <= qx1 && qy0 <= qy1) {
             rows = qy1 - qy0 + 1;
             ncols = qx1 - qx0 + 1;
-            row0 = d.cell + cell_base(d, A) + (size_t)(qy0 - d.row_lo) * (size_t)d.W + qx0;
+            row0 = d.cell + base_cell + (size_t)(qy0 - d.row_lo) * (size_t)d.W + qx0;
         }
         const bool filters = !(flags & RSV_FRAME_NO_TAG_FILTERS);
-        const bool useAny = filters && (metaA & RSV_META_USE_ANY) != 0;
+        const bool useAny = filters && useAnyBit;
         ulonglong2 qm = make_ulonglong2(0ull, 0ull);
         if (filters) qm = __ldg(d.qmask + A);
         sm.any[lane] = qm.x; sm.none[lane] = qm.y;
@@ -322,7 +327,7 @@ __device__ __forceinline__ void pairs_batch(const DevView& d, int margin, uint32
     const bool fits = staged <= kPairStage;
     uint32_t total;
     if (fits) {
-        total = pairs_exact_gate(d, all, sm, staged);
+        total = pairs_assign(sm, staged);
     } else {
         sm.cand[lane] = 0;
         __syncwarp();
