@@ -135,7 +135,9 @@ static int32_t alloc_outputs(rsv_space* s, uint32_t cap_entries, uint32_t cap_pa
         if (d.entries) cudaFree(d.entries);
         if (d.ent_box) cudaFree(d.ent_box);
         if (d.ent_home) cudaFree(d.ent_home);
-        d.entries = nullptr; d.ent_box = nullptr; d.ent_home = nullptr; d.cap_entries = 0;
+        if (d.ent_tags) cudaFree(d.ent_tags);
+        d.entries = nullptr; d.ent_box = nullptr; d.ent_home = nullptr; d.ent_tags = nullptr; d.cap_entries = 0;
+        CU(s, cudaMalloc(&d.ent_tags, (size_t)cap_entries * 8));
         CU(s, cudaMalloc(&d.entries, (size_t)cap_entries * 4));
         CU(s, cudaMalloc(&d.ent_box, (size_t)cap_entries * sizeof(float4)));
         CU(s, cudaMalloc(&d.ent_home, (size_t)cap_entries * sizeof(uint2)));
@@ -282,7 +284,7 @@ int32_t rsv_destroy(rsv_space* s) {
         if (s->host_buf[b]) cudaFreeHost(s->host_buf[b]);
     }
     DevView& d = s->d;
-    void* dev[] = {d.aabb, d.crect, d.cell, d.entries, d.ent_box, d.ent_home, d.tile_state, d.tester_start, d.tester_count, d.orphans, d.ghosts, d.n_ghosts, d.ctr};
+    void* dev[] = {d.aabb, d.crect, d.cell, d.entries, d.ent_box, d.ent_home, d.ent_tags, d.tile_state, d.tester_start, d.tester_count, d.orphans, d.ghosts, d.n_ghosts, d.ctr};
     for (void* p : dev) if (p) cudaFree(p);
     if (s->h_ctr) cudaFreeHost(s->h_ctr);
     if (s->host_pos_page1) cudaFreeHost(s->host_pos_page1);
@@ -433,7 +435,7 @@ int32_t rsv_frame_launch(rsv_space* s, int32_t margin, uint32_t flags) {
     if (d.n_shapes) k_scatter<<<blocks_for(max_items, kGridBlock, gcap), kGridBlock, 0, st>>>(d);
     mark(RSV_K_CELLSORT);
     k_cellsort<<<blocks_for(d.n_cells, kGridBlock, gcap), kGridBlock, 0, st>>>(d);
-    k_entboxes<<<gcap, kGridBlock, 0, st>>>(d);
+    k_entboxes<<<gcap, kGridBlock, 0, st>>>(d, flags);
     mark(RSV_K_PAIRS);
     const bool grid_only = (flags & RSV_FRAME_GRID_ONLY) != 0;
     if (d.n_shapes && !grid_only) k_pairs<<<s->pairs_blocks, kPairsBlock, 0, st>>>(d, margin, flags);

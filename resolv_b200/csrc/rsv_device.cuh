@@ -53,6 +53,7 @@ struct DevView {
     uint32_t* cell;       // [n_cells+1]: after the frame, cell c holds entries[cell[c] .. cell[c+1])
     uint32_t* entries;    // shape slot << 6 | flag bits (rsv_grid.cuh), ascending per cell
     float4* ent_box;      // per entry: outward-rounded float32 copy of the shape's world AABB (minx,miny,maxx,maxy)
+    unsigned long long* ent_tags;  // per entry: the shape's tags (written only in frames that use tag filters)
     uint2* ent_home;      // per HOME entry: (global index of the home cell, columns-1 | rows-1 << 16 of the clamped rect)
     unsigned long long* tile_state;  // chained-scan tile descriptors
     uint32_t* tester_start;          // first pair record of tester i

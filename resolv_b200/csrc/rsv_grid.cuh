@@ -267,12 +267,14 @@ __global__ void __launch_bounds__(kGridBlock) k_cellsort(DevView d) {
 // "home" entry (first row and first column of its cell rect) it also records where that cell is and how many
 // columns / rows the clamped rect spans, so that k_pairs can build the tester's query rect from coalesced loads
 // instead of gathering crect[] / space_idx[] by shape slot inside its latency-critical prologue.
-__global__ void __launch_bounds__(kGridBlock) k_entboxes(DevView d) {
+__global__ void __launch_bounds__(kGridBlock) k_entboxes(DevView d, uint32_t flags) {
+    const bool filters = !(flags & RSV_FRAME_NO_TAG_FILTERS);
     const uint32_t R = (uint32_t)min((unsigned long long)d.cap_entries, d.ctr->n_entries);
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < R; k += gridDim.x * blockDim.x) {
         const uint32_t ent = d.entries[k];
         const uint32_t i = ent >> kEntShift;
         d.ent_box[k] = float_box(load_box_nc(d.aabb + i));
+        if (filters) d.ent_tags[k] = __ldg(d.tags + i);  // so that k_pairs filters on a coalesced stream
         if ((ent & (kEntFirstRow | kEntFirstCol)) == (kEntFirstRow | kEntFirstCol)) {
             int x0, y0, x1, y1;
             clamp_rect(d, d.crect[i], x0, y0, x1, y1);

@@ -43,7 +43,7 @@ namespace rsv {
 constexpr int kPairsBlock = 128;
 constexpr int kPairsWarps = kPairsBlock / 32;
 constexpr int kPairsChunk = 256;  // entries per grabbed chunk
-constexpr int kPairStage = 128;   // staged records per warp batch
+constexpr int kPairStage = 96;    // staged records per warp batch
 constexpr int kRowGroup = 4;      // query-rect rows flattened together
 constexpr int kItemRound = 160;   // items staged through shared memory per round
 constexpr int kCandWords = 60;    // super-round = kCandWords * 32 items = 12 rounds
@@ -70,7 +70,7 @@ struct PairsWarpSmem {
     float4 fbox[32];            // outward-rounded float AABB of each tester of the batch
     uint4 cum[32];              // per tester: cumulative run lengths of the current row group
     uint2 run[kRowGroup][32];   // per (row, tester): (start of run, end of the run's first cell)
-    unsigned long long any[32], none[32];
+    unsigned long long itTags[kItemRound];  // cp.async landing zone: entry tags (frames with tag filters only)
     uint32_t itEnt[kItemRound]; // cp.async landing zone: entry words
     uint16_t itMeta[kItemRound];  // tester lane | first-column-cell << 5 | first-row << 6
     uint32_t queue[64];         // home entries waiting for a full batch
@@ -98,7 +98,8 @@ __device__ __forceinline__ bool exact_gate(const DevView& d, uint32_t A, uint32_
 //  kCount: count candidates and records with the exact gate inline.   kWrite: same walk, records written in place.
 // Returns the number of staged (kStage) or produced (kCount/kWrite) records; uniform across the warp.
 template <int MODE>
-__device__ __forceinline__ uint32_t pairs_pass(const DevView& d, bool all, PairsWarpSmem& sm, bool have, int rows,
+__device__ __forceinline__ uint32_t pairs_pass(const DevView& d, bool all, bool filters, unsigned long long myAny,
+                                               unsigned long long myNone, PairsWarpSmem& sm, bool have, int rows,
                                                const uint32_t* row0, int ncols, uint32_t chunk) {
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
@@ -161,6 +162,7 @@ __device__ __forceinline__ uint32_t pairs_pass(const DevView& d, bool all, Pairs
                     const uint32_t slot = i - rbeg;
                     __pipeline_memcpy_async(&sm.itEnt[slot], d.entries + k, 4);
                     __pipeline_memcpy_async(&sm.itBox[slot], d.ent_box + k, 16);
+                    if (filters) __pipeline_memcpy_async(&sm.itTags[slot], d.ent_tags + k, 8);
                     sm.itMeta[slot] = (uint16_t)(t | (k < rn.y ? 32 : 0) | ((g + r) == 0 ? 64 : 0));
                 }
             }
@@ -172,7 +174,9 @@ __device__ __forceinline__ uint32_t pairs_pass(const DevView& d, bool all, Pairs
                 const uint32_t i = it + lane;
                 const bool valid = i < rend;
                 bool cand = false, maybe = false, gate = false;
-                uint32_t B = 0, t = 0;
+                uint32_t B = 0, t = 0, fl = 0;
+                unsigned long long tg = 0;
+                float4 fb = make_float4(0.f, 0.f, 0.f, 0.f), fa = fb;
                 if (valid) {
                     const uint32_t slot = i - rbeg;
                     const uint32_t ent = sm.itEnt[slot];
@@ -182,17 +186,22 @@ __device__ __forceinline__ uint32_t pairs_pass(const DevView& d, bool all, Pairs
                     cand = B != sm.A[t]                                     // cell.go:101, shape.go:279
                            && ((ent & kEntFirstCol) || (m & 32u))           // owner-cell rule == cell.go:105
                            && ((ent & kEntFirstRow) || (m & 64u));
-                    const uint32_t fl = sm.flags[t];
-                    if (cand && (fl & 2u)) {
-                        const unsigned long long tg = __ldg(d.tags + B);
-                        if ((fl & 1u) && (tg & sm.any[t]) == 0) cand = false;   // ByTags: Has == any bit, tags.go:29-31
-                        if ((tg & sm.none[t]) != 0) cand = false;              // NotByTags
-                    }
-                    const float4 fb = sm.itBox[slot], fa = sm.fbox[t];
-                    // float boxes are rounded outward, so "disjoint in float" implies the exact reject of utils.go:156
-                    maybe = cand && !(fb.z < fa.x || fb.x > fa.z || fb.w < fa.y || fb.y > fa.w);
-                    gate = maybe;  // the exact float64 gate runs per record in k_bin
+                    fl = sm.flags[t];
+                    if (filters) tg = sm.itTags[slot];
+                    fb = sm.itBox[slot];
+                    fa = sm.fbox[t];
                 }
+                if (filters) {
+                    // the tester's masks live in its lane's registers (ByTags: Has == any bit, tags.go:29-31; NotByTags)
+                    const unsigned long long tAny = __shfl_sync(0xffffffffu, myAny, t), tNone = __shfl_sync(0xffffffffu, myNone, t);
+                    if (cand && (fl & 2u)) {
+                        if ((fl & 1u) && (tg & tAny) == 0) cand = false;
+                        if ((tg & tNone) != 0) cand = false;
+                    }
+                }
+                // float boxes are rounded outward, so "disjoint in float" implies the exact reject of utils.go:156
+                maybe = cand && !(fb.z < fa.x || fb.x > fa.z || fb.w < fa.y || fb.y > fa.w);
+                gate = maybe;  // the exact float64 gate runs per record in k_bin
                 if (MODE == kStage) {
                     // slim path: no per-item rank. One candidate-bit word per step; ranks are derived from the words at
                     // the end of the super-round, and only for the few staged survivors.
@@ -281,6 +290,8 @@ __device__ __forceinline__ void pairs_batch(const DevView& d, int margin, uint32
     const bool all = (flags & RSV_FRAME_ALL_CANDIDATES) != 0;
     int rows = 0, ncols = 0;
     bool useAnyBit = false;
+    unsigned long long myAny = 0, myNone = 0;
+    const bool filtersOn = !(flags & RSV_FRAME_NO_TAG_FILTERS);
     const uint32_t* row0 = d.cell;
     if (have) {
         const bool filters0 = !(flags & RSV_FRAME_NO_TAG_FILTERS);
@@ -316,14 +327,14 @@ __device__ __forceinline__ void pairs_batch(const DevView& d, int margin, uint32
         const bool useAny = filters && useAnyBit;
         ulonglong2 qm = make_ulonglong2(0ull, 0ull);
         if (filters) qm = __ldg(d.qmask + A);
-        sm.any[lane] = qm.x; sm.none[lane] = qm.y;
+        myAny = qm.x; myNone = qm.y;
         sm.flags[lane] = (useAny ? 1u : 0u) | ((useAny || qm.y != 0) ? 2u : 0u);
     }
     sm.A[lane] = A;
     sm.cand[lane] = 0;
     sm.gated[lane] = 0;
     __syncwarp();
-    const uint32_t staged = pairs_pass<kStage>(d, all, sm, have, rows, row0, ncols, 0u);
+    const uint32_t staged = pairs_pass<kStage>(d, all, filtersOn, myAny, myNone, sm, have, rows, row0, ncols, 0u);
     const bool fits = staged <= kPairStage;
     uint32_t total;
     if (fits) {
@@ -331,7 +342,7 @@ __device__ __forceinline__ void pairs_batch(const DevView& d, int margin, uint32
     } else {
         sm.cand[lane] = 0;
         __syncwarp();
-        total = pairs_pass<kCount>(d, all, sm, have, rows, row0, ncols, 0u);
+        total = pairs_pass<kCount>(d, all, filtersOn, myAny, myNone, sm, have, rows, row0, ncols, 0u);
     }
     const uint32_t cnt = sm.gated[lane];
     my_cands += sm.cand[lane];
@@ -366,7 +377,7 @@ __device__ __forceinline__ void pairs_batch(const DevView& d, int margin, uint32
         sm.cand[lane] = 0;
         sm.gated[lane] = 0;
         __syncwarp();
-        pairs_pass<kWrite>(d, all, sm, have, rows, row0, ncols, chunk);
+        pairs_pass<kWrite>(d, all, filtersOn, myAny, myNone, sm, have, rows, row0, ncols, chunk);
     }
     __syncwarp();
 }
