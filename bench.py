@@ -239,6 +239,13 @@ def run_b200(args):
     peak, peak_src = measured_peaks()
     algo = kernel_algorithmic_bytes(c, w, n_cells)
     dom = max(acc, key=lambda k: acc[k])
+    traffic = None   # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_kernel_traffic.json")))
+        if args.workload == "cfg2" and args.shapes == 1_000_000:
+            traffic = tj["dram_bytes_per_launch"].get(dom)
+    except Exception:
+        pass
     achieved = algo[dom] / (acc[dom] * 1e-6) / 1e9 if acc[dom] > 0 else 0.0
     frame_bytes = sum(algo.values())
     out = {
@@ -256,7 +263,7 @@ def run_b200(args):
         "gpu_launches": K * 7,
         "kernels_us": {k: round(v, 2) for k, v in acc.items()},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": int(algo[dom]), "peak_source": peak_src,
                      "frame_algorithmic_bytes": int(frame_bytes),
                      "frame_frac": frame_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
                      "survey_frame_bytes": int(survey_frame_bytes(c, w, n_cells)),
