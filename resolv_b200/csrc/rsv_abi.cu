@@ -138,6 +138,10 @@ static int32_t alloc_outputs(rsv_space* s, uint32_t cap_entries, uint32_t cap_pa
         if (d.ent_tags) cudaFree(d.ent_tags);
         d.entries = nullptr; d.ent_box = nullptr; d.ent_home = nullptr; d.ent_tags = nullptr; d.cap_entries = 0;
         CU(s, cudaMalloc(&d.ent_tags, (size_t)cap_entries * 8));
+        if (d.multi) cudaFree(d.multi);
+        d.multi = nullptr;
+        d.cap_multi = cap_entries / 2 + 1;  // a cell with >= 2 entries uses up at least two registrations
+        CU(s, cudaMalloc(&d.multi, (size_t)d.cap_multi * 4));
         CU(s, cudaMalloc(&d.entries, (size_t)cap_entries * 4));
         CU(s, cudaMalloc(&d.ent_box, (size_t)cap_entries * sizeof(float4)));
         CU(s, cudaMalloc(&d.ent_home, (size_t)cap_entries * sizeof(uint2)));
@@ -284,7 +288,7 @@ int32_t rsv_destroy(rsv_space* s) {
         if (s->host_buf[b]) cudaFreeHost(s->host_buf[b]);
     }
     DevView& d = s->d;
-    void* dev[] = {d.aabb, d.crect, d.cell, d.entries, d.ent_box, d.ent_home, d.ent_tags, d.tile_state, d.tester_start, d.tester_count, d.orphans, d.ghosts, d.n_ghosts, d.ctr};
+    void* dev[] = {d.aabb, d.crect, d.cell, d.entries, d.ent_box, d.ent_home, d.ent_tags, d.multi, d.tile_state, d.tester_start, d.tester_count, d.orphans, d.ghosts, d.n_ghosts, d.ctr};
     for (void* p : dev) if (p) cudaFree(p);
     if (s->h_ctr) cudaFreeHost(s->h_ctr);
     if (s->host_pos_page1) cudaFreeHost(s->host_pos_page1);
@@ -430,11 +434,12 @@ int32_t rsv_frame_launch(rsv_space* s, int32_t margin, uint32_t flags) {
     const uint32_t max_items = (d.own_hi - d.own_lo) + (d.n_ghosts ? d.cap_ghosts : 0u);
     if (d.n_shapes) k_bounds<<<blocks_for(max_items, kGridBlock, gcap), kGridBlock, 0, st>>>(d, margin);
     mark(RSV_K_SCAN);
-    k_scan<<<(d.n_cells + 1 + kScanTile - 1) / kScanTile, kScanBlock, 0, st>>>(d.cell, d.n_cells + 1, d.tile_state, &d.ctr->scan_ticket);
+    k_scan<<<(d.n_cells + 1 + kScanTile - 1) / kScanTile, kScanBlock, 0, st>>>(d.cell, d.n_cells + 1, d.tile_state, &d.ctr->scan_ticket,
+                                                                              d.multi, &d.ctr->n_multi, d.cap_multi);
     mark(RSV_K_SCATTER);
     if (d.n_shapes) k_scatter<<<blocks_for(max_items, kGridBlock, gcap), kGridBlock, 0, st>>>(d);
     mark(RSV_K_CELLSORT);
-    k_cellsort<<<blocks_for(d.n_cells, kGridBlock, gcap), kGridBlock, 0, st>>>(d);
+    k_cellsort<<<blocks_for(std::min<uint32_t>(d.n_cells, d.cap_multi), kGridBlock, gcap), kGridBlock, 0, st>>>(d);
     k_entboxes<<<gcap, kGridBlock, 0, st>>>(d, flags);
     mark(RSV_K_PAIRS);
     const bool grid_only = (flags & RSV_FRAME_GRID_ONLY) != 0;

@@ -26,6 +26,7 @@ struct Counters {
     unsigned int contact_cursor;           // allocation cursor of the contact buffer
     unsigned int overflow;                 // RSV_OVF_*
     unsigned int scan_ticket;              // dynamic tile ids of the chained scan
+    unsigned int n_multi;                  // cells holding two or more entries (k_scan -> k_cellsort)
     unsigned int kind_count[8];            // gated records per narrowphase bin (k_bin)
     // line tests
     unsigned int ray_hit_cursor;
@@ -56,6 +57,8 @@ struct DevView {
     unsigned long long* ent_tags;  // per entry: the shape's tags (written only in frames that use tag filters)
     uint2* ent_home;      // per HOME entry: (global index of the home cell, columns-1 | rows-1 << 16 of the clamped rect)
     unsigned long long* tile_state;  // chained-scan tile descriptors
+    uint32_t* multi;                 // cells with >= 2 entries
+    uint32_t cap_multi;
     uint32_t* tester_start;          // first pair record of tester i
     uint32_t* tester_count;          // number of pair records of tester i
     uint32_t* orphans;               // see Counters::n_orphans

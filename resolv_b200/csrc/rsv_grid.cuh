@@ -120,8 +120,10 @@ __global__ void __launch_bounds__(kGridBlock) k_clear(uint4* __restrict__ cell4,
 // Single-pass chained ("decoupled look-back") exclusive scan of uint32, in place: one read and one write of the
 // array. Tiles take their id from an atomic ticket so a tile only ever waits on tiles that already started.
 constexpr int kScanBlock = 256;
-constexpr int kScanItems = 16;
+constexpr int kScanItems = 64;  // per thread, as 16 lane-striped uint4 (every load instruction reads 512 contiguous bytes)
 constexpr int kScanTile = kScanBlock * kScanItems;
+// Tiles are large on purpose: all tiles of a frame are resident at once, so a tile's look-back finds only
+// aggregates (no finished prefixes) behind it and needs ~tile_index/32 serial rounds; 16 K-item tiles keep that short.
 
 __device__ __forceinline__ unsigned long long ld_state(const unsigned long long* p) {
     return *reinterpret_cast<const volatile unsigned long long*>(p);
@@ -130,37 +132,73 @@ __device__ __forceinline__ void st_state(unsigned long long* p, unsigned long lo
     *reinterpret_cast<volatile unsigned long long*>(p) = v;
 }
 
+// In-place exclusive scan of the per-cell counters (data[c + 1] = count of cell c on entry, = first entry of cell c on
+// exit; data[0] = 0). Also appends every cell that holds two or more entries to `multi` — the only cells whose
+// entries k_cellsort has to order.
 __global__ void __launch_bounds__(kScanBlock) k_scan(uint32_t* __restrict__ data, uint32_t n,
-                                                     unsigned long long* __restrict__ state, unsigned int* ticket) {
+                                                     unsigned long long* __restrict__ state, unsigned int* ticket,
+                                                     uint32_t* __restrict__ multi, unsigned int* n_multi, uint32_t cap_multi) {
     __shared__ uint32_t s_tile, s_prefix, s_warp[kScanBlock / 32];
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
     const uint32_t tile = s_tile;
-    const uint32_t base = tile * kScanTile + threadIdx.x * kScanItems;
-    uint32_t v[kScanItems];
-    if (base + kScanItems <= n) {
-        const uint4* p = reinterpret_cast<const uint4*>(data + base);
-#pragma unroll
-        for (int k = 0; k < kScanItems / 4; k++) {
-            uint4 q = p[k];
-            v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < kScanItems; k++) v[k] = (base + k < n) ? data[base + k] : 0u;
-    }
-    uint32_t sum = 0;
-#pragma unroll
-    for (int k = 0; k < kScanItems; k++) sum += v[k];
-    // inclusive warp scan of the per-thread sums
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t inc = sum;
+    constexpr int kGroups = kScanItems / 4;                  // uint4 groups per lane
+    constexpr uint32_t kWarpItems = 32 * kScanItems;         // items per warp
+    const uint32_t wbase = tile * kScanTile + warp * kWarpItems;
+    // group g of lane l covers items wbase + (g * 32 + l) * 4 .. + 3 (the array is allocated in whole tiles)
+    uint4 q[kGroups];
+    const uint4* src = reinterpret_cast<const uint4*>(data + wbase) + lane;
+#pragma unroll
+    for (int g = 0; g < kGroups; g++) {
+        const uint32_t e0 = wbase + (g * 32 + lane) * 4;
+        q[g] = e0 < n ? src[g * 32] : make_uint4(0u, 0u, 0u, 0u);
+        if (e0 < n && e0 + 4 > n) {  // last, partial group
+            if (e0 + 1 >= n) q[g].y = 0u;
+            if (e0 + 2 >= n) q[g].z = 0u;
+            q[g].w = 0u;
+        }
+    }
+    // cells with >= 2 entries (array index e holds the count of cell e - 1)
+    uint32_t m = 0;
+#pragma unroll
+    for (int g = 0; g < kGroups; g++) m += (q[g].x >= 2u) + (q[g].y >= 2u) + (q[g].z >= 2u) + (q[g].w >= 2u);
+    uint32_t minc = m;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
+        uint32_t t = __shfl_up_sync(0xffffffffu, minc, o);
+        if (lane >= o) minc += t;
     }
-    if (lane == 31) s_warp[warp] = inc;
+    uint32_t mbase = 0;
+    const uint32_t mtotal = __shfl_sync(0xffffffffu, minc, 31);
+    if (lane == 31 && mtotal) mbase = atomicAdd(n_multi, mtotal);
+    mbase = __shfl_sync(0xffffffffu, mbase, 31) + (minc - m);
+    if (m) {
+#pragma unroll
+        for (int g = 0; g < kGroups; g++) {
+            const uint32_t e0 = wbase + (g * 32 + lane) * 4;
+            if (q[g].x >= 2u) { if (mbase < cap_multi) multi[mbase] = e0 - 1; mbase++; }
+            if (q[g].y >= 2u) { if (mbase < cap_multi) multi[mbase] = e0; mbase++; }
+            if (q[g].z >= 2u) { if (mbase < cap_multi) multi[mbase] = e0 + 1; mbase++; }
+            if (q[g].w >= 2u) { if (mbase < cap_multi) multi[mbase] = e0 + 2; mbase++; }
+        }
+    }
+    // warp-level exclusive scan in memory order: groups are g-major, lanes within a group
+    uint32_t excl[kGroups];
+    uint32_t carry = 0;
+#pragma unroll
+    for (int g = 0; g < kGroups; g++) {
+        const uint32_t s4 = q[g].x + q[g].y + q[g].z + q[g].w;
+        uint32_t inc = s4;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        excl[g] = carry + inc - s4;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) s_warp[warp] = carry;  // warp total
     __syncthreads();
     uint32_t warp_excl = 0, block_sum = 0;
 #pragma unroll
@@ -171,7 +209,7 @@ __global__ void __launch_bounds__(kScanBlock) k_scan(uint32_t* __restrict__ data
     }
     if (warp == 0) {
         // warp-parallel look-back: 32 predecessor tiles per step
-        uint32_t excl = 0;
+        uint32_t ex = 0;
         if (tile == 0) {
             if (lane == 0) st_state(state, (2ull << 32) | block_sum);
         } else {
@@ -188,31 +226,29 @@ __global__ void __launch_bounds__(kScanBlock) k_scan(uint32_t* __restrict__ data
                 uint32_t v = lane <= stop ? (uint32_t)sv : 0u;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                excl += v;
+                ex += v;
                 if (pm) break;
                 base -= 32;
             }
-            if (lane == 0) st_state(state + tile, (2ull << 32) | (unsigned long long)(excl + block_sum));
+            if (lane == 0) st_state(state + tile, (2ull << 32) | (unsigned long long)(ex + block_sum));
         }
-        if (lane == 0) s_prefix = excl;
+        if (lane == 0) s_prefix = ex;
     }
     __syncthreads();
-    uint32_t run = s_prefix + warp_excl + (inc - sum);
-    if (base + kScanItems <= n) {
-        uint4* p = reinterpret_cast<uint4*>(data + base);
+    const uint32_t pre = s_prefix + warp_excl;
+    uint4* dst = reinterpret_cast<uint4*>(data + wbase) + lane;
 #pragma unroll
-        for (int k = 0; k < kScanItems / 4; k++) {
-            uint4 q;
-            q.x = run; run += v[4 * k];
-            q.y = run; run += v[4 * k + 1];
-            q.z = run; run += v[4 * k + 2];
-            q.w = run; run += v[4 * k + 3];
-            p[k] = q;
+    for (int g = 0; g < kGroups; g++) {
+        const uint32_t e0 = wbase + (g * 32 + lane) * 4;
+        if (e0 < n) {  // (elements past n inside the last group belong to the allocation's padding)
+            uint32_t run = pre + excl[g];
+            uint4 o;
+            o.x = run; run += q[g].x;
+            o.y = run; run += q[g].y;
+            o.z = run; run += q[g].z;
+            o.w = run;
+            dst[g * 32] = o;
         }
-    } else {
-#pragma unroll
-        for (int k = 0; k < kScanItems; k++)
-            if (base + k < n) { data[base + k] = run; run += v[k]; }
     }
 }
 
@@ -246,9 +282,12 @@ __global__ void __launch_bounds__(kGridBlock) k_scatter(DevView d) {
     }
 }
 
-// Orders every cell's entries by shape slot (the atomics above place them in arrival order).
+// Orders the entries of every cell that holds two or more by shape slot (the atomics above place them in arrival
+// order). The list of such cells comes from k_scan.
 __global__ void __launch_bounds__(kGridBlock) k_cellsort(DevView d) {
-    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < d.n_cells; c += gridDim.x * blockDim.x) {
+    const uint32_t nm = min(d.ctr->n_multi, d.cap_multi);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nm; i += gridDim.x * blockDim.x) {
+        const uint32_t c = d.multi[i];
         uint32_t s = d.cell[c], e = d.cell[c + 1];
         if (e - s < 2 || e > d.cap_entries) continue;
         uint32_t* a = d.entries + s;
