@@ -55,6 +55,8 @@ struct rsv_space {
     } slot[2];
     int launch_slot = 0, finish_slot = 0, last_slot = 0;
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t side_stream = nullptr;  // second narrowphase kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     Counters* h_ctr = nullptr;       // pinned counters of the line tests
     void* host_pos_page1 = nullptr;  // second pinned staging page for RSV_BUF_POS (rsv_staging_page)
     uint32_t launched_flags = 0;     // flags of the last finished frame
@@ -64,6 +66,7 @@ struct rsv_space {
     cudaEvent_t ev_timer[2] = {};
     rsv_timing_info timing{};
     int narrow_blocks = 148 * 4;
+    int narrow_blocks1 = 148 * 4;
     int pairs_blocks = 148 * 8;
     // line tests
     LineState lines{};
@@ -154,7 +157,7 @@ static int32_t alloc_outputs(rsv_space* s, uint32_t cap_entries, uint32_t cap_pa
             if (sl.kind_queue) cudaFree(sl.kind_queue);
             sl.hits = nullptr; sl.kind_queue = nullptr;
             CU(s, cudaMalloc(&sl.hits, (size_t)cap_pairs * sizeof(rsv_hit)));
-            CU(s, cudaMalloc(&sl.kind_queue, (size_t)cap_pairs * kNarrowBins * sizeof(uint32_t)));
+            CU(s, cudaMalloc(&sl.kind_queue, (size_t)cap_pairs * sizeof(uint32_t)));
         }
         d.cap_pairs = cap_pairs;
     }
@@ -258,6 +261,9 @@ int32_t rsv_create(const rsv_config* cfg, rsv_space** out) {
     CUC(cudaMalloc(&d.ctr, sizeof(Counters)));
     CUC(cudaHostAlloc(&s->h_ctr, sizeof(Counters), cudaHostAllocDefault));
     CUC(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&s->side_stream, cudaStreamNonBlocking));
+    CUC(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+    CUC(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
     for (auto& sl : s->slot) {
         CUC(cudaHostAlloc(&sl.h_ctr, sizeof(Counters), cudaHostAllocDefault));
         CUC(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
@@ -269,8 +275,10 @@ int32_t rsv_create(const rsv_config* cfg, rsv_space** out) {
     for (auto& e : s->ev) CUC(cudaEventCreate(&e));
     for (auto& e : s->ev_timer) CUC(cudaEventCreate(&e));
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_narrow, kNarrowBlock, 0) == cudaSuccess && occ > 0)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_narrow<0>, kNarrowBlock, 0) == cudaSuccess && occ > 0)
         s->narrow_blocks = s->sm_count * occ;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_narrow<1>, kNarrowBlock, 0) == cudaSuccess && occ > 0)
+        s->narrow_blocks1 = s->sm_count * occ;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pairs, kPairsBlock, 0) == cudaSuccess && occ > 0)
         s->pairs_blocks = s->sm_count * occ;
     CUC(cudaStreamSynchronize(s->stream));
@@ -301,6 +309,9 @@ int32_t rsv_destroy(rsv_space* s) {
         if (sl.ev_done) cudaEventDestroy(sl.ev_done);
     }
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+    if (s->side_stream) cudaStreamDestroy(s->side_stream);
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->ev_join) cudaEventDestroy(s->ev_join);
     lines_free(s->lines);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
     for (auto& e : s->ev_timer) if (e) cudaEventDestroy(e);
@@ -447,7 +458,14 @@ int32_t rsv_frame_launch(rsv_space* s, int32_t margin, uint32_t flags) {
     mark(RSV_K_NARROW);
     if (!grid_only) {
         k_bin<<<s->sm_count * 4, 256, 0, st>>>(d);
-        k_narrow<<<s->narrow_blocks, kNarrowBlock, 0, st>>>(d);
+        k_bin_scatter<<<s->sm_count * 4, 256, 0, st>>>(d);
+        // the two narrowphase kernels touch disjoint records: run them side by side (their tails overlap)
+        CU(s, cudaEventRecord(s->ev_fork, st));
+        CU(s, cudaStreamWaitEvent(s->side_stream, s->ev_fork, 0));
+        k_narrow<1><<<s->narrow_blocks1, kNarrowBlock, 0, s->side_stream>>>(d);
+        CU(s, cudaEventRecord(s->ev_join, s->side_stream));
+        k_narrow<0><<<s->narrow_blocks, kNarrowBlock, 0, st>>>(d);
+        CU(s, cudaStreamWaitEvent(st, s->ev_join, 0));
     }
     mark(RSV_K_COUNT);
     CU(s, cudaGetLastError());

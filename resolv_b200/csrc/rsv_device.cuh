@@ -27,7 +27,8 @@ struct Counters {
     unsigned int overflow;                 // RSV_OVF_*
     unsigned int scan_ticket;              // dynamic tile ids of the chained scan
     unsigned int n_multi;                  // cells holding two or more entries (k_scan -> k_cellsort)
-    unsigned int kind_count[8];            // gated records per narrowphase bin (k_bin)
+    unsigned int kind_count[20];           // gated records per narrowphase bin (k_bin)
+    unsigned int kind_cursor[20];          // fill cursors of the bins (k_bin_scatter)
     // line tests
     unsigned int ray_hit_cursor;
     unsigned int ray_contact_cursor;
@@ -70,7 +71,7 @@ struct DevView {
     int32_t home_lo, home_hi;        // rows whose shapes run IntersectionTest here (default [0, H))
     // ---- results
     rsv_hit* hits;
-    uint32_t* kind_queue;            // [8][cap_pairs]: record indices binned by pair kind / staging class
+    uint32_t* kind_queue;            // [cap_pairs]: record indices grouped by narrowphase bin
     rsv_contact* contacts;
     Counters* ctr;
     // ---- geometry of the grid

@@ -242,11 +242,23 @@ __device__ __forceinline__ PolyT<STAGED> make_poly(const DevView& d, uint32_t sl
 
 // Pair kinds: bit 1 = tester is a ConvexPolygon, bit 0 = other is a ConvexPolygon (circle.go:69-82, convexPolygon.go:288-300).
 enum { kCircleCircle = 0, kCircleConvex = 1, kConvexCircle = 2, kConvexConvex = 3 };
-constexpr int kNarrowBins = 8;  // pair kind, + 4 when a polygon exceeds kStageVerts
+// Narrowphase bins: pair kind x vertex-count class of the polygon(s). Within a bin all lanes of a warp run the same
+// pair test with (nearly) the same loop trip counts.
+//   0            circle-circle
+//   1..3         circle-convex, class of the polygon            4..6   convex-circle, class of the polygon
+//   7..15        convex-convex, 7 + 3 * class(A) + class(B)
+//   16 + kind    some polygon has more than kStageVerts vertices (read through L1 instead of the shared-memory stage)
+constexpr int kNarrowBins = 20;
+constexpr uint32_t kNoBin = 0xffffffffu;
+__device__ __forceinline__ int size_class(uint32_t nv) { return nv <= 4 ? 0 : (nv <= 6 ? 1 : 2); }
 
-// Bins the gated records by pair kind so that every warp of k_narrow runs ONE of the four pair tests (a mixed
-// world otherwise diverges four ways, times the spread of polygon sizes: 3 active lanes per warp were measured).
-// Records that failed the Bounds gate (RSV_FRAME_ALL_CANDIDATES dumps) are finalised here as empty sets.
+// Per-record pass in front of the narrowphase, one thread per record:
+//  * the exact float64 Bounds gate (utils.go:146-173) — k_pairs only applied the conservative float32 one; records
+//    that fail it (and, in RSV_FRAME_ALL_CANDIDATES dumps, records that failed the float gate) are finalised here as
+//    empty sets;
+//  * computes the record's narrowphase bin (parked in the still unused first_contact field) and counts the bins.
+// A mixed world otherwise diverges four ways per warp, times the spread of polygon sizes: 3 active lanes per warp
+// were measured before binning.
 __global__ void __launch_bounds__(256) k_bin(DevView d) {
     if (d.ctr->overflow & RSV_OVF_PAIRS) return;  // records past the capacity were never written: frame is retried
     const uint32_t n_rec = min(d.ctr->pair_cursor, d.cap_pairs);
@@ -254,12 +266,11 @@ __global__ void __launch_bounds__(256) k_bin(DevView d) {
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t base = blockIdx.x * blockDim.x; base < n_rec; base += stride) {
         const uint32_t p = base + threadIdx.x;
-        int kind = -1;
+        uint32_t bin = kNoBin;
         if (p < n_rec) {
             const uint4 rec = *reinterpret_cast<const uint4*>(d.hits + p);
             bool gated = !(rec.w & RSV_HIT_NOT_GATED);
             if (gated) {
-                // exact float64 Bounds gate (utils.go:146-173): k_pairs only applied the conservative float32 one
                 const Box a = load_box_nc(d.aabb + rec.x), o = load_box_nc(d.aabb + rec.y);
                 gated = bounds_gate(a.minx, a.miny, a.maxx, a.maxy, o.minx, o.miny, o.maxx, o.maxy);
                 if (!gated) d.hits[p].count_rank = rec.w | RSV_HIT_NOT_GATED;
@@ -268,36 +279,58 @@ __global__ void __launch_bounds__(256) k_bin(DevView d) {
                 reinterpret_cast<double2*>(d.hits + p)[1] = make_double2(0.0, 0.0);
             } else {
                 const uint32_t ma = __ldg(d.meta + rec.x), mb = __ldg(d.meta + rec.y);
-                kind = ((ma & RSV_META_POLYGON) ? 2 : 0) | ((mb & RSV_META_POLYGON) ? 1 : 0);
-                // bins 4..7: some polygon has too many vertices for the shared-memory stage
-                if (((ma & RSV_META_POLYGON) && (ma >> RSV_META_NV_SHIFT) > kStageVerts) ||
-                    ((mb & RSV_META_POLYGON) && (mb >> RSV_META_NV_SHIFT) > kStageVerts)) kind += 4;
+                const bool polyA = ma & RSV_META_POLYGON, polyB = mb & RSV_META_POLYGON;
+                const uint32_t na = ma >> RSV_META_NV_SHIFT, nb = mb >> RSV_META_NV_SHIFT;
+                const int kind = (polyA ? 2 : 0) | (polyB ? 1 : 0);
+                if ((polyA && na > kStageVerts) || (polyB && nb > kStageVerts)) bin = 16 + kind;
+                else if (kind == kConvexConvex) bin = 7 + 3 * size_class(na) + size_class(nb);
+                else if (kind == kConvexCircle) bin = 4 + size_class(na);
+                else if (kind == kCircleConvex) bin = 1 + size_class(nb);
+                else bin = 0;
             }
+            d.hits[p].first_contact = bin;
         }
-#pragma unroll
-        for (int k = 0; k < kNarrowBins; k++) {
-            const uint32_t m = __ballot_sync(0xffffffffu, kind == k);
-            if (m == 0) continue;
-            uint32_t at = 0;
-            if (lane == __ffs(m) - 1) at = atomicAdd(&d.ctr->kind_count[k], __popc(m));
-            at = __shfl_sync(0xffffffffu, at, __ffs(m) - 1);
-            if (kind == k) d.kind_queue[(size_t)k * d.cap_pairs + at + __popc(m & ((1u << lane) - 1u))] = p;
-        }
+        const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+        if (bin != kNoBin && lane == __ffs(peers) - 1) atomicAdd(&d.ctr->kind_count[bin], __popc(peers));
+    }
+}
+
+// Second pass: scatters the record indices into one queue, bin after bin (offsets = prefix sums of the bin counts).
+__global__ void __launch_bounds__(256) k_bin_scatter(DevView d) {
+    if (d.ctr->overflow & RSV_OVF_PAIRS) return;
+    __shared__ uint32_t s_off[kNarrowBins];
+    __shared__ int s_nonempty;
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        int ne = 0;
+        for (int k = 0; k < kNarrowBins; k++) { s_off[k] = run; run += d.ctr->kind_count[k]; ne += d.ctr->kind_count[k] != 0; }
+        s_nonempty = ne;
+    }
+    __syncthreads();
+    if (s_nonempty <= 1) return;  // one bin only (e.g. a world of rectangles): k_narrow walks the records directly
+    const uint32_t n_rec = min(d.ctr->pair_cursor, d.cap_pairs);
+    const int lane = threadIdx.x & 31;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n_rec; base += stride) {
+        const uint32_t p = base + threadIdx.x;
+        const uint32_t bin = p < n_rec ? d.hits[p].first_contact : kNoBin;
+        const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+        const int leader = __ffs(peers) - 1;
+        uint32_t at = 0;
+        if (bin != kNoBin && lane == leader) at = atomicAdd(&d.ctr->kind_cursor[bin], __popc(peers));
+        at = __shfl_sync(0xffffffffu, at, leader);
+        if (bin != kNoBin) d.kind_queue[s_off[bin] + at + __popc(peers & ((1u << lane) - 1u))] = p;
+        else if (p < n_rec) d.hits[p].first_contact = 0u;  // an empty set owns no contacts
     }
 }
 
 // One ordered pair of kind KIND, owned by one lane. Two passes around the warp-aggregated contact allocation.
 template <int KIND, bool STAGED>
-__device__ __forceinline__ void narrow_kind(const DevView& d, double2* sva, double2* svb, uint32_t n_q,
-                                            const uint32_t* queue) {
+__device__ __forceinline__ void narrow_one(const DevView& d, double2* sva, double2* svb, bool live, uint32_t p) {
     const int lane = threadIdx.x & 31;
-    const uint32_t stride = gridDim.x * kNarrowBlock;
-    for (uint32_t base = blockIdx.x * kNarrowBlock; base < n_q; base += stride) {
-        const uint32_t qi = base + threadIdx.x;
-        const bool live = qi < n_q;
-        uint32_t p = 0, A = 0, B = 0, cr = 0;
+    {
+        uint32_t A = 0, B = 0, cr = 0;
         if (live) {
-            p = queue[qi];
             const uint4 rec = *reinterpret_cast<const uint4*>(d.hits + p);
             A = rec.x; B = rec.y; cr = rec.w;
         }
@@ -348,7 +381,7 @@ __device__ __forceinline__ void narrow_kind(const DevView& d, double2* sva, doub
             if (first + total > d.cap_contacts || first + total < first) atomicOr(&d.ctr->overflow, RSV_OVF_CONTACTS);
         }
         first = __shfl_sync(0xffffffffu, first, 0) + (inc - n);
-        if (!live) continue;
+        if (!live) return;
         V2 mtv{0, 0};
         if (n > 127) { atomicOr(&d.ctr->overflow, RSV_OVF_CONTACTS); n = 127; }
         if (n && (unsigned long long)first + n <= d.cap_contacts) {
@@ -419,23 +452,75 @@ __device__ __forceinline__ void narrow_kind(const DevView& d, double2* sva, doub
     }
 }
 
+// GROUP 0: the convex-convex bins with staged vertices (the heavy ones; compiled on their own so that the other pair
+// tests do not inflate this kernel's registers and code). GROUP 1: every other bin.
+template <int GROUP>
 __global__ void __launch_bounds__(kNarrowBlock, RSV_NARROW_MIN_BLOCKS) k_narrow(DevView d) {
     __shared__ double2 s_va[kStageVerts][kNarrowBlock];
     __shared__ double2 s_vb[kStageVerts][kNarrowBlock];
     if (d.ctr->overflow & RSV_OVF_PAIRS) return;
     double2* sva = &s_va[0][threadIdx.x];
     double2* svb = &s_vb[0][threadIdx.x];
-    const uint32_t* q = d.kind_queue;
-    const uint32_t* kc = d.ctr->kind_count;
-    const size_t cap = d.cap_pairs;
-    // heaviest kind first so that the light ones fill the tail
-    narrow_kind<kConvexConvex, true>(d, sva, svb, min(kc[3], d.cap_pairs), q + 3 * cap);
-    narrow_kind<kConvexCircle, true>(d, sva, svb, min(kc[2], d.cap_pairs), q + 2 * cap);
-    narrow_kind<kCircleConvex, true>(d, sva, svb, min(kc[1], d.cap_pairs), q + 1 * cap);
-    narrow_kind<kCircleCircle, true>(d, sva, svb, min(kc[0], d.cap_pairs), q);
-    narrow_kind<kConvexConvex, false>(d, sva, svb, min(kc[7], d.cap_pairs), q + 7 * cap);
-    narrow_kind<kConvexCircle, false>(d, sva, svb, min(kc[6], d.cap_pairs), q + 6 * cap);
-    narrow_kind<kCircleConvex, false>(d, sva, svb, min(kc[5], d.cap_pairs), q + 5 * cap);
+    // The bins of this group form one chunk space of 32 records per chunk (a chunk never straddles two bins); warps
+    // take chunks round-robin, so every warp runs one pair test with similar trip counts and the load is spread.
+    constexpr int kMaxOrder = 11;
+    __shared__ uint32_t s_off[kMaxOrder], s_cnt[kMaxOrder], s_chunk0[kMaxOrder + 1];
+    __shared__ int s_n, s_single;
+    if (threadIdx.x == 0) {
+        uint32_t boff[kNarrowBins], off = 0;
+        int ne = 0, only = 0;
+        for (int k = 0; k < kNarrowBins; k++) {
+            boff[k] = off; off += d.ctr->kind_count[k];
+            if (d.ctr->kind_count[k]) { ne++; only = k; }
+        }
+        // a single non-empty bin was not scattered: its "queue" is the record buffer itself (other records: kNoBin)
+        s_single = ne == 1 ? only : -1;
+        // processing order: heaviest bins first
+        const int order0[9] = {15, 14, 13, 12, 11, 10, 9, 8, 7};
+        const int order1[11] = {6, 5, 4, 3, 2, 1, 0, 19, 18, 17, 16};
+        const int n = GROUP == 0 ? 9 : 11;
+        uint32_t run = 0;
+        for (int i = 0; i < n; i++) {
+            const int b = GROUP == 0 ? order0[i] : order1[i];
+            s_off[i] = boff[b] | ((uint32_t)b << 27);   // bin id rides in the top bits (queues are < 2^27 records)
+            s_cnt[i] = d.ctr->kind_count[b];
+            if (s_single == b) s_cnt[i] = min(d.ctr->pair_cursor, d.cap_pairs);  // walk every record, skip the others
+            s_chunk0[i] = run;
+            run += (s_cnt[i] + 31) / 32;
+        }
+        s_chunk0[n] = run;
+        s_n = n;
+    }
+    __syncthreads();
+    const uint32_t n_chunks = s_chunk0[s_n];
+    const uint32_t warp_id = blockIdx.x * (kNarrowBlock / 32) + (threadIdx.x >> 5), n_warps = gridDim.x * (kNarrowBlock / 32);
+    const int lane = threadIdx.x & 31;
+    for (uint32_t c = warp_id; c < n_chunks; c += n_warps) {
+        int i = 0;
+        while (c >= s_chunk0[i + 1]) i++;
+        const uint32_t idx = (c - s_chunk0[i]) * 32 + lane;
+        bool live = idx < s_cnt[i];
+        const uint32_t boff = s_off[i] & 0x7ffffffu;
+        uint32_t p = 0;
+        if (s_single >= 0) {
+            p = idx;
+            live = live && d.hits[p].first_contact == (uint32_t)s_single;
+        } else if (live) {
+            p = d.kind_queue[boff + idx];
+        }
+        if (GROUP == 0) {
+            narrow_one<kConvexConvex, true>(d, sva, svb, live, p);
+        } else {
+            const int bin = (int)(s_off[i] >> 27);
+            if (bin >= 16) {
+                if (bin == 19) narrow_one<kConvexConvex, false>(d, sva, svb, live, p);
+                else if (bin == 18) narrow_one<kConvexCircle, false>(d, sva, svb, live, p);
+                else if (bin == 17) narrow_one<kCircleConvex, false>(d, sva, svb, live, p);
+            } else if (bin >= 4) narrow_one<kConvexCircle, true>(d, sva, svb, live, p);
+            else if (bin >= 1) narrow_one<kCircleConvex, true>(d, sva, svb, live, p);
+            else narrow_one<kCircleCircle, true>(d, sva, svb, live, p);
+        }
+    }
 }
 
 }  // namespace rsv
