@@ -31,6 +31,7 @@ namespace rsv {
 
 constexpr int kLinesBlock = 128;
 constexpr double kDdaSlack = 1.0;
+constexpr int kRayCache = 4;  // hit shapes per ray remembered between the count pass and the write pass
 
 struct LineState {
     // pinned host staging
@@ -229,6 +230,7 @@ __device__ __forceinline__ void ray_candidates(const DevView& d, const Ray& ray,
 // One thread per ray, two passes around one warp-aggregated allocation, so that all hit records of a ray are
 // contiguous (ray_first / ray_count) and in candidate generation order.
 __global__ void __launch_bounds__(kLinesBlock) k_linetest(DevView d, LinesView L, uint32_t flags) {
+    __shared__ uint32_t s_hitB[kRayCache][kLinesBlock], s_hitRank[kRayCache][kLinesBlock];
     const int lane = threadIdx.x & 31;
     const bool dda = (flags & RSV_LINE_DDA) != 0;
     unsigned long long my_cands = 0, my_hits = 0;
@@ -251,11 +253,17 @@ __global__ void __launch_bounds__(kLinesBlock) k_linetest(DevView d, LinesView L
             ray.useAny = (w & 1ull) != 0;
             space = (uint32_t)(w >> 32);
             if (space >= d.n_spaces) space = 0;
+            uint32_t rank = 0;
             ray_candidates(d, ray, dda, space, [&](uint32_t B) {
                 if (!ray_filter(d, ray, B)) return;
                 my_cands++;
                 const uint32_t n = ray_vs_shape<0>(d, ray, B, nullptr, nullptr);
-                if (n) { nh++; nc += n; }
+                if (n) {
+                    // remember the first few hit shapes: pass 2 then re-tests only these instead of re-walking the grid
+                    if (nh < kRayCache) { s_hitB[nh][threadIdx.x] = B; s_hitRank[nh][threadIdx.x] = rank; }
+                    nh++; nc += n;
+                }
+                rank++;
             });
         }
         // warp-aggregated allocation of hit records and contacts
@@ -280,20 +288,25 @@ __global__ void __launch_bounds__(kLinesBlock) k_linetest(DevView d, LinesView L
         L.ray_count[i] = nh;
         my_hits += nh;
         if (nh && (unsigned long long)bh + nh <= L.cap_hits && (unsigned long long)bc + nc <= L.cap_contacts) {
-            uint32_t wh = 0, wc = 0, rank = 0;
-            ray_candidates(d, ray, dda, space, [&](uint32_t B) {
-                if (!ray_filter(d, ray, B)) return;
-                const uint32_t n = ray_vs_shape<0>(d, ray, B, nullptr, nullptr);
-                if (n) {
-                    rsv_ray_hit rec;
-                    rec.ray = i; rec.b = B; rec.first_contact = bc + wc; rec.count_rank = (n & 0xffu) | (rank << 8);
-                    rec.pad = 0.0;
-                    ray_vs_shape<1>(d, ray, B, L.contacts + bc + wc, &rec);
-                    L.hits[bh + wh] = rec;
-                    wh++; wc += n;
-                }
-                rank++;
-            });
+            uint32_t wh = 0, wc = 0;
+            auto emit = [&](uint32_t B, uint32_t rank) {
+                rsv_ray_hit rec;
+                rec.ray = i; rec.b = B; rec.first_contact = bc + wc; rec.pad = 0.0;
+                const uint32_t n = ray_vs_shape<1>(d, ray, B, L.contacts + bc + wc, &rec);
+                rec.count_rank = (n & 0xffu) | (rank << 8);
+                L.hits[bh + wh] = rec;
+                wh++; wc += n;
+            };
+            if (nh <= kRayCache) {
+                for (uint32_t k = 0; k < nh; k++) emit(s_hitB[k][threadIdx.x], s_hitRank[k][threadIdx.x]);
+            } else {
+                uint32_t rank = 0;
+                ray_candidates(d, ray, dda, space, [&](uint32_t B) {
+                    if (!ray_filter(d, ray, B)) return;
+                    if (ray_vs_shape<0>(d, ray, B, nullptr, nullptr)) emit(B, rank);
+                    rank++;
+                });
+            }
         }
     }
     for (int o = 16; o > 0; o >>= 1) {
