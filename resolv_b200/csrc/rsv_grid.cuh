@@ -45,6 +45,26 @@ __device__ __forceinline__ uint32_t cell_base(const DevView& d, uint32_t i) {
     return d.n_spaces > 1 ? __ldg(d.space_idx + i) * d.cells_per_space : 0u;
 }
 
+// Shapes covering more than kBigCells cells (walls, floors) are not walked by their own thread: the warp takes them
+// one at a time and strides its 32 lanes over the cells (a 640x16 wall on 16 px cells is 80 dependent atomics
+// otherwise — 75 us of a 300-shape frame were measured in k_scatter alone).
+constexpr int kBigCells = 16;
+
+// Calls f(x, y) for every cell of the rect [x0,x1]x[y0,y1] of every lane that has `big` set, cooperatively.
+template <class F>
+__device__ __forceinline__ void warp_big_rects(bool big, int x0, int y0, int x1, int y1, uint32_t payload, uint32_t base, F f) {
+    const int lane = threadIdx.x & 31;
+    for (uint32_t m = __ballot_sync(0xffffffffu, big); m; m &= m - 1) {
+        const int src = __ffs(m) - 1;
+        const int bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
+        const int bx1 = __shfl_sync(0xffffffffu, x1, src), by1 = __shfl_sync(0xffffffffu, y1, src);
+        const uint32_t pl = __shfl_sync(0xffffffffu, payload, src), bb = __shfl_sync(0xffffffffu, base, src);
+        const int w = bx1 - bx0 + 1;
+        const long long n = (long long)w * (long long)(by1 - by0 + 1);
+        for (long long c = lane; c < n; c += 32) f(bx0 + (int)(c % w), by0 + (int)(c / w), bx0, by0, bx1, by1, pl, bb);
+    }
+}
+
 // Bounds() -> toCellSpace() per shape, and the per-cell registration counts.
 //   Circle.Bounds                circle.go:33-39      (pos +- r  ==  pos + (-r, +r), exact in IEEE)
 //   ConvexPolygon.Bounds         convexPolygon.go:158-161 (cached local bounds + position)
@@ -55,7 +75,13 @@ __global__ void __launch_bounds__(kGridBlock) k_bounds(DevView d, int margin) {
     const uint32_t n = n_items(d);
     if (blockIdx.x == 0 && threadIdx.x == 0 && d.n_ghosts && *d.n_ghosts > d.cap_ghosts)
         atomicOr(&d.ctr->overflow, RSV_OVF_GHOSTS);
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t j0 = blockIdx.x * blockDim.x; j0 < n; j0 += stride) {  // (warp-uniform trip count)
+        const uint32_t j = j0 + threadIdx.x;
+        bool big = false;
+        int x0 = 0, y0 = 0, x1 = -1, y1 = -1;
+        uint32_t base = 0;
+        if (j < n) {
         const uint32_t i = item_slot(d, j);
         uint32_t meta = __ldg(d.meta + i);
         double2 p = __ldg(d.pos + i);
@@ -72,7 +98,6 @@ __global__ void __launch_bounds__(kGridBlock) k_bounds(DevView d, int margin) {
         d.tester_count[i] = 0;
         const bool tester = (meta & RSV_META_TESTER) && !(meta & RSV_META_ABSENT) && is_home(d, r);
         if (tester) my_testers++;
-        int x0, y0, x1, y1;
         const bool in_grid = clamp_rect(d, r, x0, y0, x1, y1);
         if (tester && !in_grid) {
             // SelectTouchingCells(margin) can still reach stored cells (shape.go:220-237): k_pairs finds testers
@@ -82,13 +107,20 @@ __global__ void __launch_bounds__(kGridBlock) k_bounds(DevView d, int margin) {
             if (qx0 <= qx1 && qy0 <= qy1) d.orphans[atomicAdd(&d.ctr->n_orphans, 1u)] = i;
         }
         if (in_grid) {
-            uint32_t base = cell_base(d, i);
-            for (int y = y0; y <= y1; y++) {
-                uint32_t row = base + (uint32_t)(y - d.row_lo) * (uint32_t)d.W;
-                for (int x = x0; x <= x1; x++) atomicAdd(d.cell + row + x + 1, 1u);
-            }
-            my_entries += (unsigned long long)(x1 - x0 + 1) * (unsigned long long)(y1 - y0 + 1);
+            base = cell_base(d, i);
+            const long long ncell = (long long)(x1 - x0 + 1) * (long long)(y1 - y0 + 1);
+            my_entries += (unsigned long long)ncell;
+            big = ncell > kBigCells;
+            if (!big)
+                for (int y = y0; y <= y1; y++) {
+                    uint32_t row = base + (uint32_t)(y - d.row_lo) * (uint32_t)d.W;
+                    for (int x = x0; x <= x1; x++) atomicAdd(d.cell + row + x + 1, 1u);
+                }
         }
+        }
+        warp_big_rects(big, x0, y0, x1, y1, 0u, base, [&](int x, int y, int, int, int, int, uint32_t, uint32_t bb) {
+            atomicAdd(d.cell + bb + (uint32_t)(y - d.row_lo) * (uint32_t)d.W + x + 1, 1u);
+        });
     }
     // block reduction of the two statistics -> one atomic each per block
     for (int o = 16; o > 0; o >>= 1) {
@@ -261,24 +293,33 @@ constexpr int kEntShift = 6;
 
 __global__ void __launch_bounds__(kGridBlock) k_scatter(DevView d) {
     const uint32_t n = n_items(d);
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-        const uint32_t i = item_slot(d, j);
-        int4 r = d.crect[i];
-        int x0, y0, x1, y1;
-        if (!clamp_rect(d, r, x0, y0, x1, y1)) continue;
-        uint32_t meta = __ldg(d.meta + i);
-        uint32_t base = cell_base(d, i);
-        uint32_t tag = (i << kEntShift) | (((meta & RSV_META_TESTER) && is_home(d, r)) ? kEntTester : 0u) |
-                       ((meta & RSV_META_USE_ANY) ? kEntUseAny : 0u);
-        for (int y = y0; y <= y1; y++) {
-            uint32_t row = base + (uint32_t)(y - d.row_lo) * (uint32_t)d.W;
-            for (int x = x0; x <= x1; x++) {
-                uint32_t slot = atomicAdd(d.cell + row + x + 1, 1u);
-                if (slot < d.cap_entries)
-                    d.entries[slot] = tag | (x == x0 ? kEntFirstCol : 0u) | (y == y0 ? kEntFirstRow : 0u) |
-                                      (x == x1 ? kEntLastCol : 0u) | (y == y1 ? kEntLastRow : 0u);
+    const uint32_t stride = gridDim.x * blockDim.x;
+    auto place = [&](int x, int y, int x0, int y0, int x1, int y1, uint32_t tag, uint32_t base) {
+        const uint32_t slot = atomicAdd(d.cell + base + (uint32_t)(y - d.row_lo) * (uint32_t)d.W + x + 1, 1u);
+        if (slot < d.cap_entries)
+            d.entries[slot] = tag | (x == x0 ? kEntFirstCol : 0u) | (y == y0 ? kEntFirstRow : 0u) |
+                              (x == x1 ? kEntLastCol : 0u) | (y == y1 ? kEntLastRow : 0u);
+    };
+    for (uint32_t j0 = blockIdx.x * blockDim.x; j0 < n; j0 += stride) {  // (warp-uniform trip count)
+        const uint32_t j = j0 + threadIdx.x;
+        bool big = false;
+        int x0 = 0, y0 = 0, x1 = -1, y1 = -1;
+        uint32_t base = 0, tag = 0;
+        if (j < n) {
+            const uint32_t i = item_slot(d, j);
+            const int4 r = d.crect[i];
+            if (clamp_rect(d, r, x0, y0, x1, y1)) {
+                const uint32_t meta = __ldg(d.meta + i);
+                base = cell_base(d, i);
+                tag = (i << kEntShift) | (((meta & RSV_META_TESTER) && is_home(d, r)) ? kEntTester : 0u) |
+                      ((meta & RSV_META_USE_ANY) ? kEntUseAny : 0u);
+                big = (long long)(x1 - x0 + 1) * (long long)(y1 - y0 + 1) > kBigCells;
+                if (!big)
+                    for (int y = y0; y <= y1; y++)
+                        for (int x = x0; x <= x1; x++) place(x, y, x0, y0, x1, y1, tag, base);
             }
         }
+        warp_big_rects(big, x0, y0, x1, y1, tag, base, place);
     }
 }
 

@@ -389,14 +389,17 @@ __global__ void __launch_bounds__(kPairsBlock) k_pairs(DevView d, int margin, ui
     uint32_t* q = sm.queue;
     unsigned long long my_cands = 0;
     const uint32_t R = (uint32_t)min((unsigned long long)d.cap_entries, d.ctr->n_entries);
-    const uint32_t n_chunks = (R + kPairsChunk - 1) / kPairsChunk;
+    // chunk size: kPairsChunk entries for large frames; small frames are cut finer so that every warp gets work
+    const uint32_t n_warps = gridDim.x * kPairsWarps;
+    const uint32_t chunk_sz = min((uint32_t)kPairsChunk, max(32u, ((R + n_warps - 1) / n_warps + 31u) & ~31u));
+    const uint32_t n_chunks = (R + chunk_sz - 1) / chunk_sz;
     uint32_t qn = 0;
     for (;;) {
         uint32_t c = 0;
         if (lane == 0) c = atomicAdd(&d.ctr->chunk_cursor, 1u);
         c = __shfl_sync(0xffffffffu, c, 0);
         if (c >= n_chunks) break;
-        const uint32_t lo = c * kPairsChunk, hi = min(lo + kPairsChunk, R);
+        const uint32_t lo = c * chunk_sz, hi = min(lo + chunk_sz, R);
         for (uint32_t base = lo; base < hi; base += 32) {
             uint32_t k = base + lane;
             uint32_t ent = k < hi ? d.entries[k] : 0u;
