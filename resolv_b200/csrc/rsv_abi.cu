@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -54,6 +55,16 @@ struct rsv_space {
         bool pending = false;
     } slot[2];
     int launch_slot = 0, finish_slot = 0, last_slot = 0;
+    // captured launch sequence of a frame, one per result slot (frame_via_graph)
+    struct FrameGraph {
+        struct Key {
+            int32_t margin; uint32_t flags; cudaStream_t stream; uint32_t n_tiles; int blocks[3];
+        } key{};
+        DevView view{};
+        cudaGraphExec_t exec = nullptr;
+        int seen = 0;
+    } graph[2];
+    bool graphs = true;  // RSV_NO_GRAPH=1 in the environment turns graph replay off
     cudaStream_t copy_stream = nullptr;
     cudaStream_t side_stream = nullptr;  // second narrowphase kernel
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -91,6 +102,12 @@ static int32_t fail(rsv_space* s, int32_t code, const char* fmt, ...) {
             return fail((s), e__ == cudaErrorMemoryAllocation ? RSV_ERR_OOM : RSV_ERR_CUDA, "%s: %s", #call, \
                         cudaGetErrorString(e__));                                                     \
     } while (0)
+
+static void drop_graph(rsv_space::FrameGraph& g) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    g.exec = nullptr;
+    g.seen = 0;
+}
 
 static size_t buf_elem_bytes(int which) {
     switch (which) {
@@ -262,6 +279,7 @@ int32_t rsv_create(const rsv_config* cfg, rsv_space** out) {
     CUC(cudaHostAlloc(&s->h_ctr, sizeof(Counters), cudaHostAllocDefault));
     CUC(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&s->side_stream, cudaStreamNonBlocking));
+    if (const char* e = getenv("RSV_NO_GRAPH")) s->graphs = !(e[0] && e[0] != '0');
     CUC(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
     CUC(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
     for (auto& sl : s->slot) {
@@ -308,6 +326,7 @@ int32_t rsv_destroy(rsv_space* s) {
         if (sl.h_contacts) cudaFreeHost(sl.h_contacts);
         if (sl.ev_done) cudaEventDestroy(sl.ev_done);
     }
+    for (auto& g : s->graph) drop_graph(g);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->side_stream) cudaStreamDestroy(s->side_stream);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
@@ -418,19 +437,9 @@ static inline int blocks_for(uint32_t n, int block, int cap) {
     return (int)b;
 }
 
-int32_t rsv_frame_launch(rsv_space* s, int32_t margin, uint32_t flags) {
-    if (!s) return RSV_ERR_BAD_ARG;
-    if (margin < 0 || margin > (1 << 20)) return fail(s, RSV_ERR_BAD_ARG, "rsv_frame: margin %d out of range", margin);
-    CU(s, cudaSetDevice(s->device));
-    DevView& d = s->d;
-    cudaStream_t st = s->stream;
-    rsv_space::FrameSlot& sl = s->slot[s->launch_slot];
-    if (sl.pending) {  // both slots busy: the oldest frame was never finished -> its results are dropped
-        sl.pending = false;
-        if (s->finish_slot == s->launch_slot) s->finish_slot ^= 1;
-    }
-    d.hits = sl.hits; d.contacts = sl.contacts; d.kind_queue = sl.kind_queue;
-    const bool timing = (flags & RSV_FRAME_TIMING) != 0;
+// The kernels of one frame plus the counter read-back, enqueued on `st` (directly, or into a stream capture).
+static int32_t enqueue_frame(rsv_space* s, const DevView& d, int32_t margin, uint32_t flags, rsv_space::FrameSlot& sl,
+                             cudaStream_t st, bool timing) {
     auto mark = [&](int k) { if (timing) cudaEventRecord(s->ev[k], st); };
     mark(RSV_K_CLEAR);
     {
@@ -470,6 +479,71 @@ int32_t rsv_frame_launch(rsv_space* s, int32_t margin, uint32_t flags) {
     mark(RSV_K_COUNT);
     CU(s, cudaGetLastError());
     CU(s, cudaMemcpyAsync(sl.h_ctr, d.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    return RSV_OK;
+}
+
+// A frame is a fixed chain of a dozen dependent launches whose arguments only change when capacities, counts or the
+// strip layout change, so steady-state frames replay one captured CUDA graph per result slot: small worlds (the
+// reference's own examples are a few hundred shapes) are bound by launch overhead, not by the kernels.
+// Returns 1 if the frame was submitted as a graph, 0 if the caller has to launch directly, < 0 on error.
+static int32_t frame_via_graph(rsv_space* s, const DevView& d, int32_t margin, uint32_t flags, rsv_space::FrameSlot& sl,
+                               rsv_space::FrameGraph& g, cudaStream_t st) {
+    rsv_space::FrameGraph::Key key{};
+    key.margin = margin; key.flags = flags; key.stream = st; key.n_tiles = s->n_tiles;
+    key.blocks[0] = s->pairs_blocks; key.blocks[1] = s->narrow_blocks; key.blocks[2] = s->narrow_blocks1;
+    const bool same = g.seen && memcmp(&key, &g.key, sizeof key) == 0 && memcmp(&d, &g.view, sizeof d) == 0;
+    if (!same) {
+        drop_graph(g);
+        g.key = key;
+        memcpy(&g.view, &d, sizeof d);
+        g.seen = 1;
+        return 0;  // first frame with these parameters: launch directly, capture if they come again
+    }
+    if (!g.exec) {
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+            cudaGetLastError();
+            s->graphs = false;
+            return 0;
+        }
+        const int32_t rc = enqueue_frame(s, d, margin, flags, sl, st, false);
+        const cudaError_t e = cudaStreamEndCapture(st, &graph);
+        if (rc != RSV_OK || e != cudaSuccess || !graph || cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) {
+            cudaGetLastError();
+            if (graph) cudaGraphDestroy(graph);
+            g.exec = nullptr;
+            s->graphs = false;  // capture is not possible on this stream: stay with direct launches
+            return 0;
+        }
+        cudaGraphDestroy(graph);
+    }
+    CU(s, cudaGraphLaunch(g.exec, st));
+    return 1;
+}
+
+int32_t rsv_frame_launch(rsv_space* s, int32_t margin, uint32_t flags) {
+    if (!s) return RSV_ERR_BAD_ARG;
+    if (margin < 0 || margin > (1 << 20)) return fail(s, RSV_ERR_BAD_ARG, "rsv_frame: margin %d out of range", margin);
+    CU(s, cudaSetDevice(s->device));
+    DevView& d = s->d;
+    cudaStream_t st = s->stream;
+    rsv_space::FrameSlot& sl = s->slot[s->launch_slot];
+    if (sl.pending) {  // both slots busy: the oldest frame was never finished -> its results are dropped
+        sl.pending = false;
+        if (s->finish_slot == s->launch_slot) s->finish_slot ^= 1;
+    }
+    d.hits = sl.hits; d.contacts = sl.contacts; d.kind_queue = sl.kind_queue;
+    const bool timing = (flags & RSV_FRAME_TIMING) != 0;
+    int32_t submitted = 0;
+    // (strip frames change their ghost count every frame, timed frames record events between the kernels)
+    if (s->graphs && !timing && !s->strip_mode) {
+        submitted = frame_via_graph(s, d, margin, flags, sl, s->graph[s->launch_slot], st);
+        if (submitted < 0) return submitted;
+    }
+    if (!submitted) {
+        const int32_t rc = enqueue_frame(s, d, margin, flags, sl, st, timing);
+        if (rc != RSV_OK) return rc;
+    }
     CU(s, cudaEventRecord(sl.ev_done, st));
     sl.flags = flags;
     sl.pending = true;

@@ -231,3 +231,49 @@ def test_two_frames_in_flight_give_the_same_results_as_sequential_frames():
         assert seq[0][0] != seq[1][0]
     finally:
         ds.close()
+
+
+def test_replayed_frame_graph_matches_direct_launches(monkeypatch):
+    """Steady-state frames replay a captured CUDA graph (from the third identical rsv_frame_launch on); the frames it
+    produces must be the ones direct launches produce, frame after frame, while the shapes move."""
+    w = worlds.make_mixed(6000, space=4000, cell=32, filtered=True)
+    traj = [w.pos.copy()]
+    for f in range(1, 7):
+        worlds.advance(w, f)
+        traj.append(w.pos.copy())
+
+    def run(no_graph):
+        monkeypatch.setenv("RSV_NO_GRAPH", "1" if no_graph else "0")
+        ds = space_for_world(w)
+        out = []
+        try:
+            ds.set_positions(traj[0])
+            ds.frame(w.margin, _abi.FRAME_DOWNLOAD, grow=True)   # settle capacities first
+            for p in traj:
+                ds.set_positions(p)
+                c = ds.frame(w.margin, _abi.FRAME_DOWNLOAD)
+                h, k = ds.results()
+                o = np.lexsort((h["b"], h["a"]))
+                n = h["count_rank"][o] & 0x7f
+                pts = [k["p"][f:f + m] for f, m in zip(h["first_contact"][o], n)]
+                out.append((c.as_dict(), h["a"][o].copy(), h["b"][o].copy(), h["count_rank"][o].copy(),
+                            h["mtv"][o].view(np.uint64).copy(),
+                            np.concatenate(pts).view(np.uint64).copy() if pts else np.zeros(0, np.uint64)))
+        finally:
+            ds.close()
+        return out
+
+    direct, replay = run(True), run(False)
+    assert len({tuple(sorted(f[0].items())) for f in direct}) > 1, "the world did not change between frames"
+    for fd, fr in zip(direct, replay):
+        assert fd[0] == fr[0]
+        for x, y in zip(fd[1:], fr[1:]):
+            assert np.array_equal(x, y)
+    # and the replayed frames are the oracle's
+    ob = OracleBatch(w)
+    ds = space_for_world(w)
+    try:
+        for _ in range(4):
+            compare_frame(ds, ob, w.margin, check_rank=True)
+    finally:
+        ds.close()
