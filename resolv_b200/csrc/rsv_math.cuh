@@ -45,23 +45,37 @@ __device__ __forceinline__ double vmag2(V2 a) { return dadd(dmul(a.x, a.x), dmul
 // Exact shortcut for axis-aligned vectors (rectangles, tiles, walls — most of a 2D game): when one component is
 // +-0, x*x + 0 rounds to fl(x*x) and sqrt(fl(x*x)) == |x| exactly for every double whose square neither
 // overflows nor falls into the subnormal range, so the IEEE sqrt (a ~20-instruction sequence on the fp64 pipe)
-// can be skipped with bit-identical results. The range test keeps the generic path for everything else.
-__device__ __forceinline__ bool axis_safe(double m) { return m == 0.0 || (m > 1e-150 && m < 1e150); }
+// can be skipped with bit-identical results. The tests run on the bit patterns (integer pipe): `axis_mag` returns
+// true and |v| when v is axis-aligned with 2^-498 <= |v| < 2^498; everything else takes the generic path.
+__device__ __forceinline__ bool axis_mag(V2 a, double& m, bool& along_x) {
+    const uint32_t hx = (uint32_t)__double2hiint(a.x) & 0x7fffffffu, hy = (uint32_t)__double2hiint(a.y) & 0x7fffffffu;
+    const bool yz = (hy | (uint32_t)__double2loint(a.y)) == 0u;   // a.y == +-0
+    const bool xz = (hx | (uint32_t)__double2loint(a.x)) == 0u;
+    along_x = yz;
+    const uint32_t h = yz ? hx : hy;
+    m = fabs(yz ? a.x : a.y);
+    return (yz | xz) & (h - 0x20d00000u < 0x5f100000u - 0x20d00000u);
+}
 
 __device__ __forceinline__ double vmag(V2 a) {                                                      // vector.go:112-114
-    if (a.y == 0.0) { double m = fabs(a.x); if (axis_safe(m)) return m; }
-    else if (a.x == 0.0) { double m = fabs(a.y); if (axis_safe(m)) return m; }
+    double m;
+    bool ax;
+    if (axis_mag(a, m, ax)) return m;
     return sqrt(vmag2(a));
 }
 __device__ __forceinline__ double vdist2(V2 a, V2 b) { return vmag2(vsub(a, b)); }                  // vector.go:152-156
 __device__ __forceinline__ V2 vunit(V2 a) {                                                         // vector.go:167-175
-    double l = vmag(a);
-    if (l < 1e-8 || l == 1.0) return a;
-    // x / |x| == +-1 and +-0 / l == +-0 exactly: skip the two IEEE divisions for axis-aligned vectors
-    if (l < 1e150) {  // (finite: inf / inf must stay NaN)
-        if (a.y == 0.0 && l == fabs(a.x)) return V2{copysign(1.0, a.x), a.y};
-        if (a.x == 0.0 && l == fabs(a.y)) return V2{a.x, copysign(1.0, a.y)};
+    double l;
+    bool ax;
+    if (axis_mag(a, l, ax)) {
+        // l = |a| exactly; `l < 1e-8 || l == 1.0` on the bit pattern (l > 0 here, so the order of doubles is the order of bits)
+        const unsigned long long lb = (unsigned long long)__double_as_longlong(l);
+        if (lb < 0x3e45798ee2308c3aull || lb == 0x3ff0000000000000ull) return a;
+        // x / |x| == +-1 and +-0 / l == +-0 exactly: no IEEE division needed
+        return ax ? V2{copysign(1.0, a.x), a.y} : V2{a.x, copysign(1.0, a.y)};
     }
+    l = sqrt(vmag2(a));
+    if (l < 1e-8 || l == 1.0) return a;
     return V2{a.x / l, a.y / l};
 }
 

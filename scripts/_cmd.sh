@@ -1,2 +1,4 @@
-RSV_NO_GRAPH=1 python scripts/profile_frame.py --frames 3 2>&1 | tail -4
-RSV_NO_GRAPH=1 python scripts/profile_frame.py --frames 3 --workload cfg3 2>&1 | tail -4
+set -x
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+bash scripts/quick_bench.sh 2>&1 | tail -3
+bash scripts/quick_bench.sh --workload cfg3 2>&1 | tail -3
