@@ -31,7 +31,6 @@ namespace rsv {
 
 constexpr int kLinesBlock = 128;
 constexpr double kDdaSlack = 1.0;
-constexpr int kRayCache = 4;  // hit shapes per ray remembered between the count pass and the write pass
 
 struct LineState {
     // pinned host staging
@@ -155,7 +154,25 @@ __device__ __forceinline__ bool ray_filter(const DevView& d, const Ray& ray, uin
     return (t & ray.none) == 0;                           // NotByTags
 }
 
-// Visits every candidate of the ray in generation order and calls f(B).
+// DDA iterator only: conservative cast-line-versus-AABB test on the entry's float box grown by kDdaGate world units
+// (separating axes: the segment's bounds, then the box against the segment's supporting line). A shape whose grown
+// box the cast line misses cannot touch it geometrically; what is skipped are only contacts the "+1" fudge of
+// IntersectionPointsLine invents for lines that pass a shape by (the DDA deviation). Saves the random
+// gathers and the per-edge tests for ~80 % of the entries a traversal visits.
+constexpr double kDdaGate = 1.0;
+__device__ __forceinline__ bool ray_box_gate(const Ray& ray, float4 fb) {
+    const double minx = (double)fb.x - kDdaGate, miny = (double)fb.y - kDdaGate;
+    const double maxx = (double)fb.z + kDdaGate, maxy = (double)fb.w + kDdaGate;
+    const double ax = ray.start.x, ay = ray.start.y, bx = ray.E.x, by = ray.E.y;
+    if (fmax(ax, bx) < minx || fmin(ax, bx) > maxx || fmax(ay, by) < miny || fmin(ay, by) > maxy) return false;
+    const double dx = bx - ax, dy = by - ay;
+    const double cx = 0.5 * (minx + maxx), cy = 0.5 * (miny + maxy), hx = 0.5 * (maxx - minx), hy = 0.5 * (maxy - miny);
+    const double s = dx * (cy - ay) - dy * (cx - ax);
+    const double r = fabs(dx) * hy + fabs(dy) * hx;
+    return !(fabs(s) > r);   // (NaN anywhere: keep the candidate)
+}
+
+// Visits every candidate of the ray in generation order and calls f(B, k) (k = index of the grid entry).
 template <class F>
 __device__ __forceinline__ void ray_candidates(const DevView& d, const Ray& ray, bool dda, uint32_t space, F f) {
     const uint32_t base = space * d.cells_per_space;
@@ -173,7 +190,7 @@ __device__ __forceinline__ void ray_candidates(const DevView& d, const Ray& ray,
                 const uint32_t ent = d.entries[k];
                 if (!((ent & kEntFirstCol) || k < s1)) continue;      // first occurrence in the row-major walk
                 if (!((ent & kEntFirstRow) || y == qy0)) continue;
-                f(ent >> kEntShift);
+                f(ent >> kEntShift, k);
             }
         }
         return;
@@ -218,7 +235,7 @@ __device__ __forceinline__ void ray_candidates(const DevView& d, const Ray& ray,
             for (uint32_t k = s; k < e; k++) {
                 const uint32_t ent = d.entries[k];
                 if ((ent & need) != need) continue;
-                f(ent >> kEntShift);
+                f(ent >> kEntShift, k);
             }
         }
         if (nx == 0 && ny == 0) break;
@@ -227,86 +244,209 @@ __device__ __forceinline__ void ray_candidates(const DevView& d, const Ray& ray,
     }
 }
 
-// One thread per ray, two passes around one warp-aggregated allocation, so that all hit records of a ray are
-// contiguous (ray_first / ray_count) and in candidate generation order.
-__global__ void __launch_bounds__(kLinesBlock) k_linetest(DevView d, LinesView L, uint32_t flags) {
-    __shared__ uint32_t s_hitB[kRayCache][kLinesBlock], s_hitRank[kRayCache][kLinesBlock];
-    const int lane = threadIdx.x & 31;
-    const bool dda = (flags & RSV_LINE_DDA) != 0;
-    unsigned long long my_cands = 0, my_hits = 0;
-    const uint32_t stride = gridDim.x * kLinesBlock;
-    for (uint32_t base = blockIdx.x * kLinesBlock; base < L.n_rays; base += stride) {
-        const uint32_t i = base + threadIdx.x;
-        const bool live = i < L.n_rays;
-        Ray ray{};
-        uint32_t space = 0;
-        uint32_t nh = 0, nc = 0;
-        if (live) {
-            const double2* sp = reinterpret_cast<const double2*>(L.seg + 4 * (size_t)i);
-            const double2 s = __ldg(sp), e = __ldg(sp + 1);
-            ray.S = V2{s.x, s.y}; ray.E = V2{e.x, e.y};
-            ray.vu = vunit(vsub(ray.E, ray.S));
-            ray.start = vsub(ray.S, vscale(ray.vu, 0.01));
-            ray.any = __ldg(L.mask + 3 * (size_t)i);
-            ray.none = __ldg(L.mask + 3 * (size_t)i + 1);
-            const unsigned long long w = __ldg(L.mask + 3 * (size_t)i + 2);
-            ray.useAny = (w & 1ull) != 0;
-            space = (uint32_t)(w >> 32);
-            if (space >= d.n_spaces) space = 0;
-            uint32_t rank = 0;
-            ray_candidates(d, ray, dda, space, [&](uint32_t B) {
-                if (!ray_filter(d, ray, B)) return;
-                my_cands++;
-                const uint32_t n = ray_vs_shape<0>(d, ray, B, nullptr, nullptr);
-                if (n) {
-                    // remember the first few hit shapes: pass 2 then re-tests only these instead of re-walking the grid
-                    if (nh < kRayCache) { s_hitB[nh][threadIdx.x] = B; s_hitRank[nh][threadIdx.x] = rank; }
-                    nh++; nc += n;
-                }
-                rank++;
-            });
-        }
-        // warp-aggregated allocation of hit records and contacts
-        uint32_t ih = nh, ic = nc;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t th = __shfl_up_sync(0xffffffffu, ih, o), tc = __shfl_up_sync(0xffffffffu, ic, o);
-            if (lane >= o) { ih += th; ic += tc; }
-        }
-        const uint32_t toth = __shfl_sync(0xffffffffu, ih, 31), totc = __shfl_sync(0xffffffffu, ic, 31);
-        uint32_t bh = 0, bc = 0;
-        if (lane == 0 && toth) {
-            bh = atomicAdd(&d.ctr->ray_hit_cursor, toth);
-            bc = atomicAdd(&d.ctr->ray_contact_cursor, totc);
-            if (bh + toth > L.cap_hits || bh + toth < bh) atomicOr(&d.ctr->overflow, RSV_OVF_RAY_HITS);
-            if (bc + totc > L.cap_contacts || bc + totc < bc) atomicOr(&d.ctr->overflow, RSV_OVF_RAY_CONTACTS);
-        }
-        bh = __shfl_sync(0xffffffffu, bh, 0) + (ih - nh);
-        bc = __shfl_sync(0xffffffffu, bc, 0) + (ic - nc);
-        if (!live) continue;
-        L.ray_first[i] = bh;
-        L.ray_count[i] = nh;
-        my_hits += nh;
-        if (nh && (unsigned long long)bh + nh <= L.cap_hits && (unsigned long long)bc + nc <= L.cap_contacts) {
-            uint32_t wh = 0, wc = 0;
-            auto emit = [&](uint32_t B, uint32_t rank) {
+// ---- the kernel -----------------------------------------------------------------------------------------------
+// A warp takes 32 rays. The cell walks are per lane (they are short and light once no exact test sits inside
+// them), but everything heavy is done one QUEUE ITEM per lane: the walk only appends (shape, owner ray, rank) items
+// to a per-warp queue in shared memory — per ray contiguous and in generation order — and the exact tests
+// (ray_vs_shape) then run over the queue with all 32 lanes busy, no matter how candidates are distributed over rays.
+// The first version tested inside the walk and ran at 2.7-3.9 active threads per warp instruction (ncu, profiles/).
+//   W1  walk: count this ray's items (DDA: after the box gate)            -> prefix sums, rounds of <= kRayQueue items
+//   W2  walk again, write the items of the round's rays
+//   T1  per item: count contacts                                           (balanced)
+//       per ray: number of hits / contacts, positions of its items; one warp-aggregated allocation per round
+//   T2  per hit item: contacts + hit record at its final position          (balanced)
+// A single ray with more than kRayQueue items is handled by its lane alone (ray_serial), like the first version.
+constexpr int kRayQueue = 512;   // (qPos packs the hit index in 10 bits)
+static_assert(kRayQueue <= 1024, "qPos packing");
+constexpr int kLinesWarps = kLinesBlock / 32;
+
+struct RayWarpSmem {
+    double rs[8][32];            // per ray: S.x S.y E.x E.y vu.x vu.y start.x start.y
+    uint32_t qB[kRayQueue];      // item: shape slot
+    uint32_t qMeta[kRayQueue];   // item: owner lane | generation rank << 5
+    uint32_t qN[kRayQueue];      // item: contacts (T1)
+    uint32_t qPos[kRayQueue];    // item: index of its hit record within the ray's records | first contact within the ray's << 10
+    uint32_t hbase[32], cbase[32];  // per ray: first hit record / first contact of the ray
+};
+
+__device__ __forceinline__ Ray ray_from_smem(const RayWarpSmem& sm, int o) {
+    Ray r{};
+    r.S = V2{sm.rs[0][o], sm.rs[1][o]}; r.E = V2{sm.rs[2][o], sm.rs[3][o]};
+    r.vu = V2{sm.rs[4][o], sm.rs[5][o]}; r.start = V2{sm.rs[6][o], sm.rs[7][o]};
+    return r;
+}
+
+__device__ __forceinline__ void load_ray(const DevView& d, const LinesView& L, uint32_t i, Ray& ray, uint32_t& space) {
+    const double2* sp = reinterpret_cast<const double2*>(L.seg + 4 * (size_t)i);
+    const double2 s = __ldg(sp), e = __ldg(sp + 1);
+    ray.S = V2{s.x, s.y}; ray.E = V2{e.x, e.y};
+    ray.vu = vunit(vsub(ray.E, ray.S));
+    ray.start = vsub(ray.S, vscale(ray.vu, 0.01));
+    ray.any = __ldg(L.mask + 3 * (size_t)i);
+    ray.none = __ldg(L.mask + 3 * (size_t)i + 1);
+    const unsigned long long w = __ldg(L.mask + 3 * (size_t)i + 2);
+    ray.useAny = (w & 1ull) != 0;
+    space = (uint32_t)(w >> 32);
+    if (space >= d.n_spaces) space = 0;
+}
+
+// The whole LineTest of one ray by one thread (count pass, allocation, write pass). Returns the number of hits.
+__device__ __noinline__ uint32_t ray_serial(const DevView d, const LinesView L, bool dda, uint32_t i) {  // (by value: a reference would make the kernel keep an addressable copy of its parameters)
+    Ray ray{};
+    uint32_t space = 0;
+    load_ray(d, L, i, ray, space);
+    uint32_t nh = 0, nc = 0;
+    ray_candidates(d, ray, dda, space, [&](uint32_t B, uint32_t k) {
+        if (!ray_filter(d, ray, B)) return;
+        if (dda && !ray_box_gate(ray, d.ent_box[k])) return;
+        const uint32_t n = ray_vs_shape<0>(d, ray, B, nullptr, nullptr);
+        if (n) { nh++; nc += n; }
+    });
+    uint32_t bh = 0, bc = 0;
+    if (nh) {
+        bh = atomicAdd(&d.ctr->ray_hit_cursor, nh);
+        bc = atomicAdd(&d.ctr->ray_contact_cursor, nc);
+        if (bh + nh > L.cap_hits || bh + nh < bh) atomicOr(&d.ctr->overflow, RSV_OVF_RAY_HITS);
+        if (bc + nc > L.cap_contacts || bc + nc < bc) atomicOr(&d.ctr->overflow, RSV_OVF_RAY_CONTACTS);
+    }
+    L.ray_first[i] = bh;
+    L.ray_count[i] = nh;
+    if (nh && (unsigned long long)bh + nh <= L.cap_hits && (unsigned long long)bc + nc <= L.cap_contacts) {
+        uint32_t wh = 0, wc = 0, rank = 0;
+        ray_candidates(d, ray, dda, space, [&](uint32_t B, uint32_t k) {
+            if (!ray_filter(d, ray, B)) return;
+            if (!(dda && !ray_box_gate(ray, d.ent_box[k])) && ray_vs_shape<0>(d, ray, B, nullptr, nullptr)) {
                 rsv_ray_hit rec;
                 rec.ray = i; rec.b = B; rec.first_contact = bc + wc; rec.pad = 0.0;
                 const uint32_t n = ray_vs_shape<1>(d, ray, B, L.contacts + bc + wc, &rec);
                 rec.count_rank = (n & 0xffu) | (rank << 8);
                 L.hits[bh + wh] = rec;
                 wh++; wc += n;
-            };
-            if (nh <= kRayCache) {
-                for (uint32_t k = 0; k < nh; k++) emit(s_hitB[k][threadIdx.x], s_hitRank[k][threadIdx.x]);
-            } else {
-                uint32_t rank = 0;
-                ray_candidates(d, ray, dda, space, [&](uint32_t B) {
+            }
+            rank++;
+        });
+    }
+    return nh;
+}
+
+__global__ void __launch_bounds__(kLinesBlock, 3) k_linetest(DevView d, LinesView L, uint32_t flags) {
+    __shared__ RayWarpSmem s_warp[kLinesWarps];
+    const int lane = threadIdx.x & 31;
+    RayWarpSmem& sm = s_warp[threadIdx.x >> 5];
+    const bool dda = (flags & RSV_LINE_DDA) != 0;
+    unsigned long long my_cands = 0, my_hits = 0;
+    const uint32_t stride = gridDim.x * kLinesBlock;
+    for (uint32_t base = blockIdx.x * kLinesBlock + (threadIdx.x & ~31u); base < L.n_rays; base += stride) {
+        const uint32_t i = base + lane;
+        const bool live = i < L.n_rays;
+        Ray ray{};
+        uint32_t space = 0, cnt = 0;
+        if (live) {
+            load_ray(d, L, i, ray, space);
+            // ---- W1: count the items of this ray
+            ray_candidates(d, ray, dda, space, [&](uint32_t B, uint32_t k) {
+                if (!ray_filter(d, ray, B)) return;
+                my_cands++;
+                if (!dda || ray_box_gate(ray, d.ent_box[k])) cnt++;
+            });
+        }
+        sm.rs[0][lane] = ray.S.x; sm.rs[1][lane] = ray.S.y; sm.rs[2][lane] = ray.E.x; sm.rs[3][lane] = ray.E.y;
+        sm.rs[4][lane] = ray.vu.x; sm.rs[5][lane] = ray.vu.y; sm.rs[6][lane] = ray.start.x; sm.rs[7][lane] = ray.start.y;
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        __syncwarp();
+        // ---- rounds over ranges of rays [r0, r1) whose items fit the queue
+        int r0 = 0;
+        while (r0 < 32) {
+            const uint32_t before = r0 ? __shfl_sync(0xffffffffu, incl, r0 - 1) : 0u;
+            const uint32_t fits = __ballot_sync(0xffffffffu, lane >= r0 && incl - before <= (uint32_t)kRayQueue);
+            // rays r0.. fit as long as the mask is contiguous from r0 (incl is monotone, so it is)
+            const int r1 = fits ? 32 - __clz(fits) : r0;
+            if (r1 == r0) {  // this ray alone overflows the queue
+                if (lane == r0 && live) my_hits += ray_serial(d, L, dda, i);
+                __syncwarp();
+                r0++;
+                continue;
+            }
+            const bool mine = lane >= r0 && lane < r1;
+            const uint32_t off = incl - cnt - before;  // first queue slot of this ray
+            const uint32_t n_items = __shfl_sync(0xffffffffu, incl, r1 - 1) - before;
+            // ---- W2: write the items
+            if (mine && cnt) {
+                uint32_t pos = off, rank = 0;
+                ray_candidates(d, ray, dda, space, [&](uint32_t B, uint32_t k) {
                     if (!ray_filter(d, ray, B)) return;
-                    if (ray_vs_shape<0>(d, ray, B, nullptr, nullptr)) emit(B, rank);
+                    if (!dda || ray_box_gate(ray, d.ent_box[k])) {
+                        sm.qB[pos] = B;
+                        sm.qMeta[pos] = (uint32_t)lane | (rank << 5);
+                        pos++;
+                    }
                     rank++;
                 });
             }
+            __syncwarp();
+            // ---- T1: contacts per item
+            for (uint32_t j = lane; j < n_items; j += 32) {
+                const Ray r = ray_from_smem(sm, (int)(sm.qMeta[j] & 31u));
+                sm.qN[j] = ray_vs_shape<0>(d, r, sm.qB[j], nullptr, nullptr);
+            }
+            __syncwarp();
+            // ---- per ray: hits, contacts, positions of its items
+            uint32_t nh = 0, nc = 0;
+            if (mine) {
+                for (uint32_t j = off; j < off + cnt; j++) {
+                    const uint32_t n = sm.qN[j];
+                    sm.qPos[j] = nh | (nc << 10);   // nh < kRayQueue <= 1024, nc <= 255 * kRayQueue < 2^22
+                    nh += n ? 1u : 0u; nc += n;
+                }
+            }
+            uint32_t ih = nh, ic = nc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t th = __shfl_up_sync(0xffffffffu, ih, o), tc = __shfl_up_sync(0xffffffffu, ic, o);
+                if (lane >= o) { ih += th; ic += tc; }
+            }
+            const uint32_t toth = __shfl_sync(0xffffffffu, ih, 31), totc = __shfl_sync(0xffffffffu, ic, 31);
+            uint32_t bh = 0, bc = 0;
+            if (lane == 0 && toth) {
+                bh = atomicAdd(&d.ctr->ray_hit_cursor, toth);
+                bc = atomicAdd(&d.ctr->ray_contact_cursor, totc);
+                if (bh + toth > L.cap_hits || bh + toth < bh) atomicOr(&d.ctr->overflow, RSV_OVF_RAY_HITS);
+                if (bc + totc > L.cap_contacts || bc + totc < bc) atomicOr(&d.ctr->overflow, RSV_OVF_RAY_CONTACTS);
+            }
+            bh = __shfl_sync(0xffffffffu, bh, 0);
+            bc = __shfl_sync(0xffffffffu, bc, 0);
+            const bool room = (unsigned long long)bh + toth <= L.cap_hits && (unsigned long long)bc + totc <= L.cap_contacts;
+            sm.hbase[lane] = bh + (ih - nh);
+            sm.cbase[lane] = bc + (ic - nc);
+            if (mine && live) {
+                L.ray_first[i] = bh + (ih - nh);
+                L.ray_count[i] = nh;
+                my_hits += nh;
+            }
+            __syncwarp();
+            // ---- T2: contacts and hit records
+            if (room) {
+                for (uint32_t j = lane; j < n_items; j += 32) {
+                    if (!sm.qN[j]) continue;
+                    const uint32_t m = sm.qMeta[j];
+                    const int o = (int)(m & 31u);
+                    const Ray r = ray_from_smem(sm, o);
+                    const uint32_t qp = sm.qPos[j];
+                    const uint32_t c0 = sm.cbase[o] + (qp >> 10);
+                    rsv_ray_hit rec;
+                    rec.ray = base + (uint32_t)o; rec.b = sm.qB[j]; rec.first_contact = c0; rec.pad = 0.0;
+                    const uint32_t n = ray_vs_shape<1>(d, r, rec.b, L.contacts + c0, &rec);
+                    rec.count_rank = (n & 0xffu) | ((m >> 5) << 8);
+                    L.hits[sm.hbase[o] + (qp & 1023u)] = rec;
+                }
+            }
+            __syncwarp();
+            r0 = r1;
         }
     }
     for (int o = 16; o > 0; o >>= 1) {

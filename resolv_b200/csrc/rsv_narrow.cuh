@@ -129,12 +129,16 @@ __device__ __forceinline__ V2 box_center(const Box& b) {
 }
 
 // One SAT axis step of calculateMTV (convexPolygon.go:430-441 and twins). axis is a line normal.
+// smag caches smallest.Magnitude(), which the reference recomputes on every axis: it only changes with `smallest`.
 template <class Poly, class ProjOther>
-__device__ __forceinline__ bool sat_axis(const Poly& cp, V2 axis, ProjOther projOther, V2& smallest) {
+__device__ __forceinline__ bool sat_axis(const Poly& cp, V2 axis, ProjOther projOther, V2& smallest, double& smag) {
     V2 u = vunit(axis);  // Project() re-normalises its argument
     double ov = overlap(project_poly(cp, u), projOther(u));
     if (ov <= 0) return false;
-    if (vmag(smallest) > ov) smallest = vscale(axis, ov);
+    if (smag > ov) {
+        smallest = vscale(axis, ov);
+        smag = vmag(smallest);
+    }
     return true;
 }
 
@@ -142,11 +146,12 @@ __device__ __forceinline__ bool sat_axis(const Poly& cp, V2 axis, ProjOther proj
 template <class Poly>
 __device__ __forceinline__ bool mtv_poly_poly(const Poly& cp, const Poly& other, V2 centerCp, V2 centerOther, V2& out) {
     V2 smallest{DBL_MAX, 0.0};
+    double smag = vmag(smallest);
     auto projOther = [&](V2 u) { return project_poly(other, u); };
     for (int i = 0; i < cp.nl; i++)
-        if (!sat_axis(cp, edge_normal(cp.get(i), cp.line_end(i)), projOther, smallest)) return false;
+        if (!sat_axis(cp, edge_normal(cp.get(i), cp.line_end(i)), projOther, smallest, smag)) return false;
     for (int i = 0; i < other.nl; i++)
-        if (!sat_axis(cp, edge_normal(other.get(i), other.line_end(i)), projOther, smallest)) return false;
+        if (!sat_axis(cp, edge_normal(other.get(i), other.line_end(i)), projOther, smallest, smag)) return false;
     if (vdot(vsub(centerCp, centerOther), smallest) < 0) smallest = vinv(smallest);
     V2 delta = smallest;
     if (vdot(vsub(other.pos, cp.pos), delta) > 0) delta = vinv(delta);
@@ -172,8 +177,9 @@ __device__ __forceinline__ bool mtv_poly_circle(const Poly& cp, V2 centerCp, V2 
     double ov = overlap(project_poly(cp, u), projOther(u));
     if (ov <= 0) return false;
     V2 smallest = vscale(u, ov);  // axis.Unit().Scale(overlap)
+    double smag = vmag(smallest);
     for (int i = 0; i < cp.nl; i++)
-        if (!sat_axis(cp, edge_normal(cp.get(i), cp.line_end(i)), projOther, smallest)) return false;
+        if (!sat_axis(cp, edge_normal(cp.get(i), cp.line_end(i)), projOther, smallest, smag)) return false;
     if (vdot(vsub(centerCp, cpos), smallest) < 0) smallest = vinv(smallest);
     V2 delta = smallest;
     if (vdot(vsub(cpos, cp.pos), delta) > 0) delta = vinv(delta);

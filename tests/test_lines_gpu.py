@@ -101,6 +101,24 @@ def _supercover_touches(rays_i, cell_rect, cw, ch):
     return t0 <= t1
 
 
+def _segment_touches_box(seg, box, grow):
+    """Exact: does the closed segment touch the box (minx, miny, maxx, maxy) grown by `grow` on every side?"""
+    (x0, y0, x1, y1) = [Fraction(float(v)) for v in seg]
+    g = Fraction(grow)
+    bx0, by0, bx1, by1 = Fraction(float(box[0])) - g, Fraction(float(box[1])) - g, Fraction(float(box[2])) + g, Fraction(float(box[3])) + g
+    t0, t1 = Fraction(0), Fraction(1)
+    for p, d, lo, hi in ((x0, x1 - x0, bx0, bx1), (y0, y1 - y0, by0, by1)):
+        if d == 0:
+            if p < lo or p > hi:
+                return False
+        else:
+            u0, u1 = (lo - p) / d, (hi - p) / d
+            if u0 > u1:
+                u0, u1 = u1, u0
+            t0, t1 = max(t0, u0), min(t1, u1)
+    return t0 <= t1
+
+
 def test_dda_iterator_bit_identical_sets_and_only_phantoms_missing():
     w, ds, sp, rays, kw = _setup(n_rays=30000)
     try:
@@ -121,16 +139,19 @@ def test_dda_iterator_bit_identical_sets_and_only_phantoms_missing():
         assert np.array_equal(bits(dc), bits(ocs))
         assert np.array_equal(bits(h["mtv"]), bits(oh.mtv[osel])) and np.array_equal(bits(h["center"]), bits(oh.center[osel]))
         assert np.array_equal(bits(h["key"]), bits(oh.dist[osel]))
-        # anything missing must be a phantom: its shape is in no cell the exact supercover of the cast line touches
+        # anything missing must be a phantom of the "+1" fudge: the cast line does not come within 0.9 world units of
+        # the shape's Bounds (the device gate is 1.0), or the shape is in no cell the exact supercover of the line touches
         missing = o[~sel]
-        assert len(missing) <= 0.002 * len(o), (len(missing), len(o))
+        assert len(missing) <= 0.01 * len(o), (len(missing), len(o))
         for m in missing:
             r, b = int(oh.a[m]), int(oh.b[m])
             s, e = rays[r, :2], rays[r, 2:]
             vu = (e - s) / np.hypot(*(e - s))
             st = s - 0.01 * vu
-            assert not _supercover_touches((st[0], st[1], e[0], e[1]), sp.cell_rect(b), w.cell_w, w.cell_h), \
-                f"ray {r} misses shape {b} although its cells touch the cast line"
+            seg = (st[0], st[1], e[0], e[1])
+            assert (not _segment_touches_box(seg, sp.bounds(b), 0.9)
+                    or not _supercover_touches(seg, sp.cell_rect(b), w.cell_w, w.cell_h)), \
+                f"ray {r} misses shape {b} although the cast line touches its bounds"
         assert c.n_candidates < fc.candidates
     finally:
         ds.close()
