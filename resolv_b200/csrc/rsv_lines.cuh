@@ -251,14 +251,16 @@ __device__ __forceinline__ void ray_candidates(const DevView& d, const Ray& ray,
 // (ray_vs_shape) then run over the queue with all 32 lanes busy, no matter how candidates are distributed over rays.
 // The first version tested inside the walk and ran at 2.7-3.9 active threads per warp instruction (ncu, profiles/).
 //   W1  walk: count this ray's items (DDA: after the box gate)            -> prefix sums, rounds of <= kRayQueue items
-//   W2  walk again, write the items of the round's rays
+//   W2  write the items of the round's rays: from the first walk's per-lane cache if the ray has <= kRaySeg items
+//       (almost always with the DDA iterator), otherwise by walking again
 //   T1  per item: count contacts                                           (balanced)
 //       per ray: number of hits / contacts, positions of its items; one warp-aggregated allocation per round
 //   T2  per hit item: contacts + hit record at its final position          (balanced)
 // A single ray with more than kRayQueue items is handled by its lane alone (ray_serial), like the first version.
-constexpr int kRayQueue = 512;   // (qPos packs the hit index in 10 bits)
+constexpr int kRayQueue = 448;   // (qPos packs the hit index in 10 bits)
 static_assert(kRayQueue <= 1024, "qPos packing");
 constexpr int kLinesWarps = kLinesBlock / 32;
+constexpr int kRaySeg = 8;
 
 struct RayWarpSmem {
     double rs[8][32];            // per ray: S.x S.y E.x E.y vu.x vu.y start.x start.y
@@ -267,6 +269,8 @@ struct RayWarpSmem {
     uint32_t qN[kRayQueue];      // item: contacts (T1)
     uint32_t qPos[kRayQueue];    // item: index of its hit record within the ray's records | first contact within the ray's << 10
     uint32_t hbase[32], cbase[32];  // per ray: first hit record / first contact of the ray
+    uint32_t segB[kRaySeg][32];  // the first items of each ray, kept from the count walk (saves the second walk)
+    uint32_t segRank[kRaySeg][32];
 };
 
 __device__ __forceinline__ Ray ray_from_smem(const RayWarpSmem& sm, int o) {
@@ -343,12 +347,17 @@ __global__ void __launch_bounds__(kLinesBlock, 3) k_linetest(DevView d, LinesVie
         uint32_t space = 0, cnt = 0;
         if (live) {
             load_ray(d, L, i, ray, space);
-            // ---- W1: count the items of this ray
+            // ---- W1: count the items of this ray (and keep the first few)
+            uint32_t rank = 0;
             ray_candidates(d, ray, dda, space, [&](uint32_t B, uint32_t k) {
                 if (!ray_filter(d, ray, B)) return;
-                my_cands++;
-                if (!dda || ray_box_gate(ray, d.ent_box[k])) cnt++;
+                if (!dda || ray_box_gate(ray, d.ent_box[k])) {
+                    if (cnt < (uint32_t)kRaySeg) { sm.segB[cnt][lane] = B; sm.segRank[cnt][lane] = rank; }
+                    cnt++;
+                }
+                rank++;
             });
+            my_cands += rank;
         }
         sm.rs[0][lane] = ray.S.x; sm.rs[1][lane] = ray.S.y; sm.rs[2][lane] = ray.E.x; sm.rs[3][lane] = ray.E.y;
         sm.rs[4][lane] = ray.vu.x; sm.rs[5][lane] = ray.vu.y; sm.rs[6][lane] = ray.start.x; sm.rs[7][lane] = ray.start.y;
@@ -376,7 +385,12 @@ __global__ void __launch_bounds__(kLinesBlock, 3) k_linetest(DevView d, LinesVie
             const uint32_t off = incl - cnt - before;  // first queue slot of this ray
             const uint32_t n_items = __shfl_sync(0xffffffffu, incl, r1 - 1) - before;
             // ---- W2: write the items
-            if (mine && cnt) {
+            if (mine && cnt && cnt <= (uint32_t)kRaySeg) {
+                for (uint32_t q = 0; q < cnt; q++) {
+                    sm.qB[off + q] = sm.segB[q][lane];
+                    sm.qMeta[off + q] = (uint32_t)lane | (sm.segRank[q][lane] << 5);
+                }
+            } else if (mine && cnt) {
                 uint32_t pos = off, rank = 0;
                 ray_candidates(d, ray, dda, space, [&](uint32_t B, uint32_t k) {
                     if (!ray_filter(d, ray, B)) return;

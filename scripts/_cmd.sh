@@ -1,3 +1,3 @@
 set -x
-python -m pytest tests/test_lines_gpu.py tests/test_host_gpu.py tests/test_fuzz_gpu.py -m gpu -x -q 2>&1 | tail -5
+python -m pytest tests/test_lines_gpu.py tests/test_host_gpu.py -m gpu -x -q 2>&1 | tail -5
 python scripts/measure_rays.py 2>&1 | tail -3
