@@ -288,6 +288,31 @@ int32_t rsv_halo_pack(rsv_space* s, int32_t up_row_max, int32_t dn_row_min, void
 int32_t rsv_halo_apply(rsv_space* s, const void* dev_recv_up, int32_t slot_off_up, const void* dev_recv_dn, int32_t slot_off_dn,
                        uint32_t cap_records);
 
+/* Peer-memory halo transport (NVLink / NVSwitch P2P): no collective library on the data path. Every device owns a
+ * mailbox (receive buffers for both neighbours, double-buffered by epoch parity, plus flag words); a device pushes
+ * its packed records straight into its neighbours' mailboxes with peer stores, raises their `ready` flag and waits
+ * for its own with stream-ordered memory waits. Set-up, once:
+ *   rsv_halo_mailbox (allocate, get the device pointer) -> rsv_ipc_export (64-byte CUDA IPC handle; ship it to the
+ *   neighbour processes by any host channel) -> rsv_ipc_open on the neighbours' handles -> rsv_halo_connect.
+ * Then rsv_halo_exchange once per frame on every device (same number of calls everywhere, like a collective),
+ * followed by rsv_frame*. Spaces living in ONE process connect with each other's mailbox pointers directly. */
+#define RSV_IPC_HANDLE_BYTES 64
+int32_t rsv_halo_mailbox(rsv_space* s, uint32_t cap_records, void** dev_mailbox, size_t* bytes);
+int32_t rsv_ipc_export(void* dev_ptr, unsigned char handle[RSV_IPC_HANDLE_BYTES]);
+int32_t rsv_ipc_open(const unsigned char handle[RSV_IPC_HANDLE_BYTES], int32_t device, void** dev_ptr);
+int32_t rsv_ipc_close(void* dev_ptr);
+/* up_mailbox / dn_mailbox: the neighbours' mailboxes as mapped in this process (NULL: no neighbour on that side). */
+int32_t rsv_halo_connect(rsv_space* s, void* up_mailbox, void* dn_mailbox);
+/* rsv_halo_pack straight into the neighbours' mailboxes + publish + wait + rsv_halo_apply, all enqueued on the
+ * space's stream (arguments as for those calls). phases: RSV_HALO_SEND | RSV_HALO_RECV for the whole exchange in one
+ * call (one process per GPU). A process driving SEVERAL spaces on one device must enqueue the SEND halves of all of
+ * them before any RECV half: streams of one process can share a hardware queue, and a memory wait queued ahead of
+ * the store it waits for would never be satisfied. */
+#define RSV_HALO_SEND 1u
+#define RSV_HALO_RECV 2u
+int32_t rsv_halo_exchange(rsv_space* s, int32_t up_row_max, int32_t dn_row_min, int32_t slot_off_up, int32_t slot_off_dn,
+                          uint32_t phases);
+
 /* ---- parity / debug dumps --------------------------------------------------------------------------------- */
 /* Cell membership after the last frame: cell_end[c] (exclusive end offset of cell c in `entries`, cells row-major,
  * spaces concatenated; start = cell_end[c-1] or 0) and the shape slots per cell in ascending slot order. Either

@@ -31,6 +31,7 @@ ABI_SYMBOLS = [
     "rsv_timer_stop", "rsv_debug_cells", "rsv_debug_cell_rects", "rsv_linetest", "rsv_linetest_launch",
     "rsv_linetest_finish", "rsv_ray_staging", "rsv_ray_reserve", "rsv_ray_results_view", "rsv_tester_table",
     "rsv_set_stream", "rsv_strip_setup", "rsv_halo_pack", "rsv_halo_apply", "rsv_staging_page", "rsv_commit_pos_page",
+    "rsv_halo_mailbox", "rsv_ipc_export", "rsv_ipc_open", "rsv_ipc_close", "rsv_halo_connect", "rsv_halo_exchange",
 ]
 
 

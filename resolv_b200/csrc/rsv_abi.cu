@@ -4,6 +4,8 @@
 // Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false
 //             -Xcompiler -fPIC -shared rsv_abi.cu -o libresolv_b200.so
 // -fmad=false is part of the numerical contract (Go/amd64 does not fuse multiply-add), see rsv_math.cuh.
+#include <cuda.h>
+
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -79,6 +81,11 @@ struct rsv_space {
     int narrow_blocks = 148 * 4;
     int narrow_blocks1 = 148 * 4;
     int pairs_blocks = 148 * 8;
+    // peer-memory halo transport (rsv_halo_abi.inl)
+    void* mailbox = nullptr;            // this device's mailbox
+    uint32_t mailbox_cap = 0;
+    void* peer_mailbox[2] = {};         // neighbours' mailboxes as mapped in this process: 0 upper, 1 lower
+    uint32_t halo_epoch = 0;
     // line tests
     LineState lines{};
     std::string error;
@@ -327,6 +334,7 @@ int32_t rsv_destroy(rsv_space* s) {
         if (sl.ev_done) cudaEventDestroy(sl.ev_done);
     }
     for (auto& g : s->graph) drop_graph(g);
+    if (s->mailbox) cudaFree(s->mailbox);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->side_stream) cudaStreamDestroy(s->side_stream);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
@@ -535,8 +543,8 @@ int32_t rsv_frame_launch(rsv_space* s, int32_t margin, uint32_t flags) {
     d.hits = sl.hits; d.contacts = sl.contacts; d.kind_queue = sl.kind_queue;
     const bool timing = (flags & RSV_FRAME_TIMING) != 0;
     int32_t submitted = 0;
-    // (strip frames change their ghost count every frame, timed frames record events between the kernels)
-    if (s->graphs && !timing && !s->strip_mode) {
+    // (timed frames record events between the kernels; the ghost count of strip frames is read on the device)
+    if (s->graphs && !timing) {
         submitted = frame_via_graph(s, d, margin, flags, sl, s->graph[s->launch_slot], st);
         if (submitted < 0) return submitted;
     }

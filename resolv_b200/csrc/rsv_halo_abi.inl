@@ -46,7 +46,9 @@ int32_t rsv_halo_pack(rsv_space* s, int32_t up_row_max, int32_t dn_row_min, void
     const uint32_t n = s->d.own_hi - s->d.own_lo;
     if (n && (dev_send_up || dev_send_dn))
         k_halo_pack<<<blocks_for(n, kGridBlock, s->sm_count * 8), kGridBlock, 0, st>>>(s->d, up_row_max, dn_row_min, (HaloRec*)dev_send_up,
-                                                                                      (HaloRec*)dev_send_dn, cap_records);
+                                                                                      (HaloRec*)dev_send_dn, cap_records,
+                                                                                      dev_send_up ? &((HaloRec*)dev_send_up)->slot : nullptr,
+                                                                                      dev_send_dn ? &((HaloRec*)dev_send_dn)->slot : nullptr);
     CU(s, cudaGetLastError());
     return RSV_OK;
 }
@@ -61,6 +63,140 @@ int32_t rsv_halo_apply(rsv_space* s, const void* dev_recv_up, int32_t slot_off_u
     const int blocks = blocks_for(cap_records, kGridBlock, s->sm_count * 2);
     if (dev_recv_up) k_halo_apply<<<blocks, kGridBlock, 0, st>>>(s->d, (const HaloRec*)dev_recv_up, slot_off_up, cap_records);
     if (dev_recv_dn) k_halo_apply<<<blocks, kGridBlock, 0, st>>>(s->d, (const HaloRec*)dev_recv_dn, slot_off_dn, cap_records);
+    CU(s, cudaGetLastError());
+    return RSV_OK;
+}
+
+// ---- peer-memory transport: mailbox + IPC plumbing + one stream-ordered exchange call
+typedef CUresult (*rsv_stream_wait32_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static rsv_stream_wait32_fn stream_wait32() {
+    static rsv_stream_wait32_fn fn = []() -> rsv_stream_wait32_fn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return (rsv_stream_wait32_fn)p;
+    }();
+    return fn;
+}
+
+int32_t rsv_halo_mailbox(rsv_space* s, uint32_t cap_records, void** dev_mailbox, size_t* bytes) {
+    if (!s || !cap_records) return RSV_ERR_BAD_ARG;
+    if (!s->strip_mode) return fail(s, RSV_ERR_BAD_ARG, "rsv_halo_mailbox: call rsv_strip_setup first");
+    CU(s, cudaSetDevice(s->device));
+    if (!stream_wait32()) return fail(s, RSV_ERR_CUDA, "rsv_halo_mailbox: the driver has no cuStreamWaitValue32");
+    if (s->mailbox && s->mailbox_cap != cap_records) return fail(s, RSV_ERR_BAD_ARG, "rsv_halo_mailbox: capacity is fixed once the mailbox exists");
+    if (!s->mailbox) {
+        const size_t b = halo_mailbox_bytes(cap_records);
+        CU(s, cudaMalloc(&s->mailbox, b));   // (a plain allocation: pool memory cannot be exported through CUDA IPC)
+        CU(s, cudaMemset(s->mailbox, 0, b));
+        HaloMailboxHeader h{};
+        h.cap = cap_records;
+        CU(s, cudaMemcpy(s->mailbox, &h, sizeof h, cudaMemcpyHostToDevice));
+        s->mailbox_cap = cap_records;
+        s->halo_epoch = 0;
+        CU(s, cudaDeviceSynchronize());
+    }
+    if (dev_mailbox) *dev_mailbox = s->mailbox;
+    if (bytes) *bytes = halo_mailbox_bytes(cap_records);
+    return RSV_OK;
+}
+
+int32_t rsv_ipc_export(void* dev_ptr, unsigned char handle[RSV_IPC_HANDLE_BYTES]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == RSV_IPC_HANDLE_BYTES, "IPC handle size");
+    if (!dev_ptr || !handle) return RSV_ERR_BAD_ARG;
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, dev_ptr) != cudaSuccess) {
+        g_create_error = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(cudaGetLastError());
+        return RSV_ERR_CUDA;
+    }
+    memcpy(handle, &h, sizeof h);
+    return RSV_OK;
+}
+
+int32_t rsv_ipc_open(const unsigned char handle[RSV_IPC_HANDLE_BYTES], int32_t device, void** dev_ptr) {
+    if (!handle || !dev_ptr) return RSV_ERR_BAD_ARG;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    if (cudaSetDevice(device) != cudaSuccess || cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        g_create_error = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(cudaGetLastError());
+        return RSV_ERR_CUDA;
+    }
+    return RSV_OK;
+}
+
+int32_t rsv_ipc_close(void* dev_ptr) {
+    if (!dev_ptr) return RSV_OK;
+    return cudaIpcCloseMemHandle(dev_ptr) == cudaSuccess ? RSV_OK : RSV_ERR_CUDA;
+}
+
+int32_t rsv_halo_connect(rsv_space* s, void* up_mailbox, void* dn_mailbox) {
+    if (!s) return RSV_ERR_BAD_ARG;
+    if (!s->mailbox) return fail(s, RSV_ERR_BAD_ARG, "rsv_halo_connect: call rsv_halo_mailbox first");
+    CU(s, cudaSetDevice(s->device));
+    CU(s, cudaStreamSynchronize(s->stream));
+    void* peers[2] = {up_mailbox, dn_mailbox};
+    for (int i = 0; i < 2; i++) {
+        if (peers[i]) {
+            HaloMailboxHeader h{};
+            CU(s, cudaMemcpy(&h, peers[i], sizeof h, cudaMemcpyDefault));
+            if (h.cap != s->mailbox_cap) return fail(s, RSV_ERR_BAD_ARG, "rsv_halo_connect: neighbour mailbox holds %u records, ours %u", h.cap, s->mailbox_cap);
+        }
+        s->peer_mailbox[i] = peers[i];
+    }
+    // epochs restart at 1: clear our flag words (callers synchronise all devices between connect and the first exchange)
+    CU(s, cudaMemset(s->mailbox, 0, offsetof(HaloMailboxHeader, cap)));
+    CU(s, cudaMemset((char*)s->mailbox + offsetof(HaloMailboxHeader, cnt), 0, sizeof(uint32_t) * 2));
+    s->halo_epoch = 0;
+    return RSV_OK;
+}
+
+// pack straight into both neighbours' mailboxes -> publish counts + `ready` -> wait for both neighbours' records ->
+// apply -> tell them their buffers are free. Four small kernels and a few stream memory waits, all enqueued on the
+// space's stream; the host never blocks. Every device of the strip chain has to call this the same number of times
+// (epochs), like a collective.
+int32_t rsv_halo_exchange(rsv_space* s, int32_t up_row_max, int32_t dn_row_min, int32_t slot_off_up, int32_t slot_off_dn,
+                          uint32_t phases) {
+    if (!s) return RSV_ERR_BAD_ARG;
+    if (!s->mailbox) return fail(s, RSV_ERR_BAD_ARG, "rsv_halo_exchange: call rsv_halo_mailbox / rsv_halo_connect first");
+    if (!(phases & (RSV_HALO_SEND | RSV_HALO_RECV))) return fail(s, RSV_ERR_BAD_ARG, "rsv_halo_exchange: no phase selected");
+    CU(s, cudaSetDevice(s->device));
+    cudaStream_t st = s->stream;
+    rsv_stream_wait32_fn wait32 = stream_wait32();
+    if (phases & RSV_HALO_SEND) ++s->halo_epoch;
+    const uint32_t cap = s->mailbox_cap, e = s->halo_epoch;
+    const int par = (int)(e & 1u);
+    HaloMailboxHeader* mine = (HaloMailboxHeader*)s->mailbox;
+    HaloMailboxHeader* peer[2] = {(HaloMailboxHeader*)s->peer_mailbox[0], (HaloMailboxHeader*)s->peer_mailbox[1]};
+    HaloRec* dst[2] = {nullptr, nullptr};   // where our records go: the neighbour's buffer for data from ITS other side
+    if (phases & RSV_HALO_SEND) {
+    for (int side = 0; side < 2; side++) {  // side: where the neighbour sits (0 upper, 1 lower)
+        if (!peer[side]) continue;
+        dst[side] = halo_mailbox_recv(peer[side], cap, 1 - side, par);
+        // the neighbour must have applied what we stored into this parity two epochs ago
+        if (e > 2 && wait32(st, (CUdeviceptr)&mine->done[side][par], e - 2, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+            return fail(s, RSV_ERR_CUDA, "cuStreamWaitValue32 failed");
+    }
+    const uint32_t n = s->d.own_hi - s->d.own_lo;
+    if (n && (dst[0] || dst[1]))
+        k_halo_pack<<<blocks_for(n, kGridBlock, s->sm_count * 8), kGridBlock, 0, st>>>(s->d, up_row_max, dn_row_min, dst[0], dst[1], cap,
+                                                                                      &mine->cnt[0], &mine->cnt[1]);
+    k_halo_publish<<<1, 1, 0, st>>>(mine->cnt, dst[0], dst[1], peer[0] ? &peer[0]->ready[1][par] : nullptr,
+                                    peer[1] ? &peer[1]->ready[0][par] : nullptr, e, s->d.n_ghosts);
+    }
+    if (!(phases & RSV_HALO_RECV)) {
+        CU(s, cudaGetLastError());
+        return RSV_OK;
+    }
+    for (int side = 0; side < 2; side++)
+        if (peer[side] && wait32(st, (CUdeviceptr)&mine->ready[side][par], e, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+            return fail(s, RSV_ERR_CUDA, "cuStreamWaitValue32 failed");
+    k_halo_apply2<<<dim3(blocks_for(cap, kGridBlock, s->sm_count), 2), kGridBlock, 0, st>>>(
+        s->d, peer[0] ? halo_mailbox_recv(mine, cap, 0, par) : nullptr, slot_off_up,
+        peer[1] ? halo_mailbox_recv(mine, cap, 1, par) : nullptr, slot_off_dn, cap);
+    k_halo_signal<<<1, 1, 0, st>>>(peer[0] ? &peer[0]->done[1][par] : nullptr, peer[1] ? &peer[1]->done[0][par] : nullptr, e);
     CU(s, cudaGetLastError());
     return RSV_OK;
 }

@@ -13,6 +13,7 @@ span is the largest number of extra rows a shape covers.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import time
 from dataclasses import dataclass
 
@@ -149,6 +150,21 @@ class StripRank:
         L.rsv_halo_pack.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint32]
         L.rsv_halo_apply.restype = C.c_int32
         L.rsv_halo_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_uint32]
+        L.rsv_halo_mailbox.restype = C.c_int32
+        L.rsv_halo_mailbox.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        L.rsv_ipc_export.restype = C.c_int32
+        L.rsv_ipc_export.argtypes = [C.c_void_p, C.c_char_p]
+        L.rsv_ipc_open.restype = C.c_int32
+        L.rsv_ipc_open.argtypes = [C.c_char_p, C.c_int32, C.POINTER(C.c_void_p)]
+        L.rsv_ipc_close.restype = C.c_int32
+        L.rsv_ipc_close.argtypes = [C.c_void_p]
+        L.rsv_halo_connect.restype = C.c_int32
+        L.rsv_halo_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.rsv_halo_exchange.restype = C.c_int32
+        L.rsv_halo_exchange.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint32]
+        self.peer_mode = False
+        self._opened = []
+        self.device = device
         self.ds._check(L.rsv_strip_setup(self.ds.h, n, 2 * n, self.plan.home_lo, self.plan.home_hi, 2 * cap_halo))
         self.cap = cap_halo
         dev = torch.device("cuda", device)
@@ -176,16 +192,72 @@ class StripRank:
         with self.torch.cuda.stream(self.stream):
             exchange(self.send_up, self.send_dn, self.recv_up, self.recv_dn, self.rank, self.world)
 
+    # --- peer-memory transport (NVLink P2P through CUDA IPC mailboxes): no NCCL call per frame
+    def mailbox(self):
+        """Allocates this rank's mailbox; returns (device pointer, 64-byte CUDA IPC handle)."""
+        ptr, nbytes = C.c_void_p(), C.c_size_t()
+        self.ds._check(self.ds.L.rsv_halo_mailbox(self.ds.h, self.cap, C.byref(ptr), C.byref(nbytes)))
+        handle = C.create_string_buffer(64)
+        rc = self.ds.L.rsv_ipc_export(ptr, handle)
+        return ptr.value, (bytes(handle.raw) if rc == 0 else None)
+
+    def connect(self, up_ptr, dn_ptr):
+        """Neighbour mailboxes as device pointers valid in this process (None: no neighbour on that side)."""
+        self.ds._check(self.ds.L.rsv_halo_connect(self.ds.h, C.c_void_p(up_ptr), C.c_void_p(dn_ptr)))
+        self.peer_mode = True
+
+    def connect_ipc(self, dist):
+        """All ranks: exchange IPC handles over torch.distributed (host plumbing, once) and map both neighbours'
+        mailboxes. Returns False (and stays on the NCCL transport) if CUDA IPC is not available."""
+        _, handle = self.mailbox()
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle)
+        if any(h is None for h in handles):
+            return False
+        ptrs = {}
+        ok = True
+        for r in (self.rank - 1, self.rank + 1):
+            if 0 <= r < self.world:
+                p = C.c_void_p()
+                if self.ds.L.rsv_ipc_open(handles[r], self.device, C.byref(p)) != 0:
+                    ok = False
+                    break
+                ptrs[r] = p.value
+                self._opened.append(p.value)
+        flags = [None] * self.world
+        dist.all_gather_object(flags, ok)
+        if not all(flags):
+            return False
+        self.connect(ptrs.get(self.rank - 1), ptrs.get(self.rank + 1))
+        dist.barrier()
+        return True
+
+    def exchange_peer(self, phases=3):
+        """phases: 1 = send half, 2 = receive half, 3 = both (see rsv_halo_exchange)."""
+        p = self.plan
+        self.ds._check(self.ds.L.rsv_halo_exchange(self.ds.h, p.up_row_max, p.dn_row_min, -self.n, self.n, phases))
+
+    def halo_step(self):
+        """pack -> neighbour exchange -> apply, on the rank's stream, by whichever transport is connected."""
+        if self.peer_mode:
+            self.exchange_peer()
+        else:
+            self.pack()
+            self.exchange()
+            self.apply()
+
     def step_launch(self, extra_flags=0):
-        self.pack()
-        self.exchange()
-        self.apply()
+        self.halo_step()
         self.ds.frame_launch(self.margin, self.flags | extra_flags)
 
     def global_slot(self, local):
         return np.asarray(local, dtype=np.int64) + (self.rank - 1) * self.n
 
     def close(self):
+        self.ds.sync()
+        for p in self._opened:
+            self.ds.L.rsv_ipc_close(C.c_void_p(p))
+        self._opened = []
         self.ds.close()
 
 
@@ -201,11 +273,12 @@ def run_bench(args, rank, world, local_rank):
     sr = StripRank(args.workload, n, rank, world, local_rank, margin=1, span_rows=1)
     ds = sr.ds
     dev = torch.device("cuda", local_rank)
+    transport = "NCCL send/recv"
+    if os.environ.get("RSV_HALO_TRANSPORT", "peer") == "peer" and sr.connect_ipc(dist):
+        transport = "peer-memory mailboxes over NVLink (CUDA IPC, stream-ordered waits; no NCCL call per step)"
     # warm-up (also sizes the output buffers: grow on capacity errors)
     for i in range(W):
-        sr.pack()
-        sr.exchange()
-        sr.apply()
+        sr.halo_step()
         c = ds.frame(sr.margin, sr.flags | _abi.FRAME_DOWNLOAD, grow=True)
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -232,15 +305,13 @@ def run_bench(args, rank, world, local_rank):
     # one sequential warm pass sizes the buffers for both position sets
     for pg in (0, 1):
         ds.commit_pos_page(pg, n, 2 * n)
-        sr.pack(); sr.exchange(); sr.apply()
+        sr.halo_step()
         ds.frame(sr.margin, sr.flags | _abi.FRAME_DOWNLOAD, grow=True)
     h2d = d2h = 0
 
     def launch(i):
         ds.commit_pos_page(i % 2, n, 2 * n)
-        sr.pack()
-        sr.exchange()
-        sr.apply()
+        sr.halo_step()
         ds.frame_launch(sr.margin, sr.flags | _abi.FRAME_DOWNLOAD)
 
     torch.cuda.synchronize()
@@ -261,7 +332,8 @@ def run_bench(args, rank, world, local_rank):
     tot = torch.tensor([int(c.n_candidates), int(c.n_hits), int(c.n_contacts), int(c.n_entries), h2d // K, d2h // K], device=dev, dtype=torch.int64)
     dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     clocks = sampler.stop()
-    ds.close()
+    dist.barrier()      # (a rank must not unmap a neighbour's mailbox while that neighbour is still running)
+    sr.close()
     if rank != 0:
         return None
     ms_per_step = float(ms.item()) / K
@@ -272,7 +344,7 @@ def run_bench(args, rank, world, local_rank):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": workload_name(args, world) + f"; Space grown to 65536 x {65536 * world}, strip-partitioned by cell rows, "
-                   "halo exchange of (slot, position) records with both neighbours every step (NCCL send/recv)",
+                   "halo exchange of (slot, position) records with both neighbours every step: " + transport,
                    "l2": "inputs + per-frame intermediates (~0.3 GB per GPU) exceed the 126 MB L2", "margin": 1},
         "pair_tests_per_sec": int(tot[0].item()) / (ms_per_step * 1e-3),
         "counts": {"n_shapes": N, "n_candidates": int(tot[0].item()), "n_hits": int(tot[1].item()), "n_contacts": int(tot[2].item()),

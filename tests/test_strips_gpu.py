@@ -20,11 +20,17 @@ def _hits_table(hits, con, to_global):
     return a, b, n, rank, h["mtv"].copy(), cons
 
 
-@pytest.mark.parametrize("kind", ["cfg2", "cfg3"])
-def test_two_strips_equal_one_space(kind):
+@pytest.mark.parametrize("kind,transport", [("cfg2", "copy"), ("cfg3", "copy"), ("cfg3", "peer")])
+def test_two_strips_equal_one_space(kind, transport):
     import torch
     n, size, world = 20000, 9280, 2
     ranks = [strips.StripRank(kind, n, r, world, 0, size=size, cap_halo=8192) for r in range(world)]
+    if transport == "peer":
+        # the peer-memory transport with both "devices" in one process: mailboxes are connected by pointer (processes
+        # on different GPUs map them through CUDA IPC instead); pushes, flag waits and applies are all stream-ordered
+        boxes = [sr.mailbox()[0] for sr in ranks]
+        ranks[0].connect(None, boxes[1])
+        ranks[1].connect(boxes[0], None)
     ref_world = strips.concat_worlds([strips.tile_world(kind, n, t, size=size) for t in range(world)], size * world)
     ref = space_for_world(ref_world)
     try:
@@ -35,15 +41,22 @@ def test_two_strips_equal_one_space(kind):
                 for r, sr in enumerate(ranks):
                     sr.ds.buf[_abi.BUF_POS][2 * n:4 * n] = ref_world.pos[r * n:(r + 1) * n].reshape(-1)
                     sr.ds.commit(1 << _abi.BUF_POS, n, 2 * n)
-            for sr in ranks:
-                sr.pack()
-            torch.cuda.synchronize()
-            ranks[1].recv_up.copy_(ranks[0].send_dn)
-            ranks[0].recv_dn.copy_(ranks[1].send_up)
-            torch.cuda.synchronize()
+            if transport == "peer":
+                for sr in ranks:            # all send halves first: both ranks' streams may share a hardware queue
+                    sr.exchange_peer(1)
+                for sr in ranks:
+                    sr.exchange_peer(2)
+            else:
+                for sr in ranks:
+                    sr.pack()
+                torch.cuda.synchronize()
+                ranks[1].recv_up.copy_(ranks[0].send_dn)
+                ranks[0].recv_dn.copy_(ranks[1].send_up)
+                torch.cuda.synchronize()
             tables, P = [], 0
             for sr in ranks:
-                sr.apply()
+                if transport != "peer":
+                    sr.apply()
                 c = sr.ds.frame(1, sr.flags | _abi.FRAME_DOWNLOAD, grow=True)
                 P += c.n_candidates
                 hits, con = sr.ds.results()
