@@ -332,6 +332,7 @@ def run_bench(args, rank, world, local_rank):
     tot = torch.tensor([int(c.n_candidates), int(c.n_hits), int(c.n_contacts), int(c.n_entries), h2d // K, d2h // K], device=dev, dtype=torch.int64)
     dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     clocks = sampler.stop()
+    sr_peer = sr.peer_mode
     dist.barrier()      # (a rank must not unmap a neighbour's mailbox while that neighbour is still running)
     sr.close()
     if rank != 0:
@@ -352,7 +353,8 @@ def run_bench(args, rank, world, local_rank):
         "clocks": clocks,
         "e2e": {"value": N * K / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int(tot[4].item()),
                 "d2h_bytes_per_step": int(tot[5].item()), "ms_per_step": 1e3 * float(te.item()) / K},
-        "gpu_launches": K * (7 + 3) * world,
+        # per rank and step: 11 frame kernels + the halo exchange (4 kernels on the peer transport; pack + 2 applies on NCCL)
+        "gpu_launches": K * (11 + (4 if sr_peer else 3)) * world,
         "roofline": {"bound": "hbm", "kernel": "frame", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
                      "traffic": None, "peak_source": peak_src, "note": "per-kernel roofline is reported by the N=1 run"},
     }

@@ -1,3 +1,5 @@
 set -x
-timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 scripts/measure_strips.py 2>&1 | grep -E "us/step|rror|IPC|n_shapes" 
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 20 --warmup 5 2>gpurun_out/bench_n2.err | tee gpurun_out/bench_n2.json | cut -c1-600
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python bench.py --steps 20 --warmup 5 2>gpurun_out/bench_r1_final.err > gpurun_out/bench_r1_final.json; tail -c 3000 gpurun_out/bench_r1_final.json
+python bench.py --steps 20 --warmup 5 --workload cfg3 --no-cpu-baseline 2>/dev/null > gpurun_out/bench_r1_final_cfg3.json
+python scripts/measure_small.py 2>&1 | tail -6 > gpurun_out/small_final.txt; cat gpurun_out/small_final.txt
