@@ -474,7 +474,7 @@ static int32_t enqueue_frame(rsv_space* s, const DevView& d, int32_t margin, uin
     if (d.n_shapes && !grid_only) k_pairs<<<s->pairs_blocks, kPairsBlock, 0, st>>>(d, margin, flags);
     mark(RSV_K_NARROW);
     if (!grid_only) {
-        k_bin<<<s->sm_count * 4, 256, 0, st>>>(d);
+        k_bin<<<s->sm_count * 8, 256, 0, st>>>(d);
         k_bin_scatter<<<s->sm_count * 4, 256, 0, st>>>(d);
         // the two narrowphase kernels touch disjoint records: run them side by side (their tails overlap)
         CU(s, cudaEventRecord(s->ev_fork, st));

@@ -270,6 +270,11 @@ __global__ void __launch_bounds__(256) k_bin(DevView d) {
     const uint32_t n_rec = min(d.ctr->pair_cursor, d.cap_pairs);
     const int lane = threadIdx.x & 31;
     const uint32_t stride = gridDim.x * blockDim.x;
+    // bin counts are collected per block first: a uniform world puts every record into ONE bin, and one global word
+    // cannot take an atomic per warp
+    __shared__ uint32_t s_cnt[kNarrowBins];
+    if (threadIdx.x < kNarrowBins) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
     for (uint32_t base = blockIdx.x * blockDim.x; base < n_rec; base += stride) {
         const uint32_t p = base + threadIdx.x;
         uint32_t bin = kNoBin;
@@ -297,8 +302,10 @@ __global__ void __launch_bounds__(256) k_bin(DevView d) {
             d.hits[p].first_contact = bin;
         }
         const uint32_t peers = __match_any_sync(0xffffffffu, bin);
-        if (bin != kNoBin && lane == __ffs(peers) - 1) atomicAdd(&d.ctr->kind_count[bin], __popc(peers));
+        if (bin != kNoBin && lane == __ffs(peers) - 1) atomicAdd(&s_cnt[bin], __popc(peers));
     }
+    __syncthreads();
+    if (threadIdx.x < kNarrowBins && s_cnt[threadIdx.x]) atomicAdd(&d.ctr->kind_count[threadIdx.x], s_cnt[threadIdx.x]);
 }
 
 // Second pass: scatters the record indices into one queue, bin after bin (offsets = prefix sums of the bin counts).
