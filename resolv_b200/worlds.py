@@ -275,6 +275,26 @@ def make_platformer_batch(n_spaces: int, seed: int = 20264, n_tiles: int = 500, 
     return w.finalize()
 
 
+def make_platformer_probes(w: World, reach: float = 16.0):
+    """Config 4's LineTest probes (examples/worldPlatformer.go:221-246,291-296 in spirit): per dynamic body two rays
+    straight down from its two bottom vertices and two rays along its facing from the leading edge's two vertices,
+    each `reach` long, against ByTags(Platform). Returns (rays f64[4B,4], use_any u8, any_mask u64, space_idx u32)."""
+    body = np.nonzero(w.tester != 0)[0]
+    p = w.pos[body]
+    hw, hh = 8.0, 6.0
+    face = np.where((w.vel[body, 0] if w.vel is not None else np.ones(len(body))) < 0, -1.0, 1.0)
+    rays = np.zeros((len(body), 4, 4))
+    for k, sx in enumerate((-hw, hw)):                      # down from the bottom vertices
+        rays[:, k, 0] = p[:, 0] + sx; rays[:, k, 1] = p[:, 1] + hh
+        rays[:, k, 2] = p[:, 0] + sx; rays[:, k, 3] = p[:, 1] + hh + reach
+    for k, sy in enumerate((-hh, hh)):                      # along the facing from the leading edge
+        rays[:, 2 + k, 0] = p[:, 0] + face * hw; rays[:, 2 + k, 1] = p[:, 1] + sy
+        rays[:, 2 + k, 2] = p[:, 0] + face * (hw + reach); rays[:, 2 + k, 3] = p[:, 1] + sy
+    n = 4 * len(body)
+    return (rays.reshape(n, 4), np.ones(n, np.uint8), np.full(n, TAG_PLATFORM, np.uint64),
+            np.repeat(w.space_idx[body], 4).astype(np.uint32))
+
+
 def advance(w: World, frame: int) -> None:
     """Per-frame motion of SURVEY.md §8d: pos += vel, reflected at the Space borders (in place)."""
     if w.vel is None:

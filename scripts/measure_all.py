@@ -40,11 +40,26 @@ for name, fl in (("rect", 0), ("dda", _abi.LINE_DDA)):
     rc = ds.linetest(rays, flags=fl | _abi.LINE_RESIDENT)
     out[f"rays_{name}_4M"] = dict(kernel_us=rc.kernel_us, rays_per_s=nr / rc.kernel_us * 1e6, counts=rc.as_dict())
 ds.close()
-# config 4: 512 platformer Spaces on one GPU (4096 / 8)
+# config 5's ray sweep on one GPU: 10 M segments over the 1 M-shape mixed world
+nr = 10_000_000
+ds = _abi.DeviceSpace(w.space_w, w.space_h, w.cell_w, w.cell_h, max_shapes=w.n, max_verts=len(w.verts), max_rays=nr)
+ds.upload_world(w)
+ds.frame(1, _abi.FRAME_GRID_ONLY)
+rays = worlds.make_rays(nr, 6, w.space_w, w.space_h)
+rc = ds.linetest(rays, flags=_abi.LINE_DDA)
+rc = ds.linetest(rays, flags=_abi.LINE_DDA | _abi.LINE_RESIDENT)
+out["rays_dda_10M"] = dict(kernel_us=rc.kernel_us, rays_per_s=nr / rc.kernel_us * 1e6, counts=rc.as_dict())
+ds.close()
+# config 4: 512 platformer Spaces on one GPU (4096 / 8): the frame, then four LineTest probes per dynamic body
 w = worlds.make_platformer_batch(512)
-ds = space_for_world(w)
+rays, use_any, any_mask, sidx = worlds.make_platformer_probes(w)
+ds = space_for_world(w, max_rays=len(rays))
 ms, c, t = frame_time(ds, w.margin, 0)
 out["cfg4_512_spaces"] = dict(ms=ms, shapes=w.n, shapes_per_s=w.n / ms * 1e3, testers=int(c.n_testers), pair_tests_per_s=c.n_candidates / ms * 1e3,
                               counts=c.as_dict(), kernels_us=t)
+for name, fl in (("rect", 0), ("dda", _abi.LINE_DDA)):
+    rc = ds.linetest(rays, use_any=use_any, any_mask=any_mask, flags=fl, space_idx=sidx)
+    rc = ds.linetest(rays, use_any=use_any, any_mask=any_mask, flags=fl | _abi.LINE_RESIDENT, space_idx=sidx)
+    out[f"cfg4_512_spaces_probes_{name}"] = dict(rays=len(rays), kernel_us=rc.kernel_us, counts=rc.as_dict())
 ds.close()
 print(json.dumps(out, indent=1))
