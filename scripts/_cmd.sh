@@ -1,1 +1,1 @@
-timeout 300 python -m pytest tests/test_lines_gpu.py -m gpu -x -q -k platformer 2>&1 | tail -40
+timeout 900 python scripts/fuzz_long.py 320 5000 2>&1 | tail -6
