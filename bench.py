@@ -186,6 +186,11 @@ def run_b200(args):
         ds.set_positions(frames[i % len(frames)])
         c = ds.frame(margin, _abi.FRAME_DOWNLOAD | base_flags, grow=True)
     n_cells = ds.grid_w * ds.rows * ds.n_spaces
+    # warm the exact call pattern of the timed loop too (same flags: the launch sequence is captured into a CUDA graph
+    # per result slot on the second identical call and replayed from the third)
+    for i in range(max(W, 6)):
+        ds.frame_launch(margin, base_flags)
+    ds.frame_finish()
 
     sampler = ClockSampler(local_rank)
     sampler.start()

@@ -280,6 +280,9 @@ def run_bench(args, rank, world, local_rank):
     for i in range(W):
         sr.halo_step()
         c = ds.frame(sr.margin, sr.flags | _abi.FRAME_DOWNLOAD, grow=True)
+    for i in range(max(W, 6)):      # the timed loop's exact call pattern (its flags select its own CUDA graphs)
+        sr.step_launch()
+    ds.frame_finish()
     sampler = ClockSampler(local_rank)
     sampler.start()
     dist.barrier()
