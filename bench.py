@@ -154,6 +154,24 @@ def survey_frame_bytes(c, w, n_cells):
     return s_bp + 16 * R + 8 * (n_cells + 1) + 16 * P + s_np + 32 * H + 32 * K
 
 
+def bind_to_gpu_cpus(index):
+    """Runs this process on the CPU cores NVML reports as local to GPU `index`, so that the pinned staging buffers
+    allocated afterwards sit on the GPU's NUMA node (the e2e leg is PCIe-bound; with several ranks per box, staging
+    memory on the far socket halves it). Returns the previous affinity (restore it before the CPU baseline)."""
+    try:
+        import pynvml
+        old = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index), words)
+        cpus = {64 * i + b for i, wd in enumerate(mask) for b in range(64) if (int(wd) >> b) & 1} & old
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return old
+    except Exception:
+        return None
+
+
 def run_b200(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -162,6 +180,7 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: there is no CPU fallback for the product path")
     torch.cuda.set_device(local_rank)
+    old_affinity = bind_to_gpu_cpus(local_rank)
     if world_size > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -277,6 +296,8 @@ def run_b200(args):
                      "survey_frame_bytes": int(survey_frame_bytes(c, w, n_cells)),
                      "survey_frame_frac": survey_frame_bytes(c, w, n_cells) / (ms_per_step * 1e-3) / 1e9 / peak},
     }
+    if old_affinity:
+        os.sched_setaffinity(0, old_affinity)   # the CPU baseline may use every core of the box
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, budget_s=20.0)
     ds.close()

@@ -225,22 +225,37 @@ __device__ __forceinline__ void ray_candidates(const DevView& d, const Ray& ray,
     double tmx = ddx != 0.0 ? (((double)(ix + (stepx > 0 ? 1 : 0)) * d.cell_w - ax) / ddx) : 0.0;
     double tmy = ddy != 0.0 ? (((double)(iy + (stepy > 0 ? 1 : 0)) * d.cell_h - ay) / ddy) : 0.0;
     int came = 0;  // how the current cell was entered: 0 start, 1 step in x, 2 step in y
-    for (;;) {
-        if (ix >= 0 && ix < d.W && iy >= d.row_lo && iy < d.row_hi) {
-            const uint32_t c = base + (uint32_t)(iy - d.row_lo) * (uint32_t)d.W + (uint32_t)ix;
-            const uint32_t s = d.cell[c], e = min(d.cell[c + 1], d.cap_entries);
-            // a shape is new here iff the cell we came from is outside its (in-grid) cell rect
-            const uint32_t need = came == 0 ? 0u : (came == 1 ? (stepx > 0 ? kEntFirstCol : kEntLastCol)
-                                                              : (stepy > 0 ? kEntFirstRow : kEntLastRow));
-            for (uint32_t k = s; k < e; k++) {
-                const uint32_t ent = d.entries[k];
-                if ((ent & need) != need) continue;
-                f(ent >> kEntShift, k);
-            }
+    // The walk is a chain of dependent loads (cell offsets -> entry -> box); the next cell's offsets do not depend on
+    // the current cell's entries, so they are requested before those are processed.
+    auto cell_range = [&](int x, int y, uint32_t& s0, uint32_t& e0) {
+        s0 = e0 = 0;
+        if (x >= 0 && x < d.W && y >= d.row_lo && y < d.row_hi) {
+            const uint32_t c = base + (uint32_t)(y - d.row_lo) * (uint32_t)d.W + (uint32_t)x;
+            s0 = d.cell[c];
+            e0 = min(d.cell[c + 1], d.cap_entries);
         }
-        if (nx == 0 && ny == 0) break;
-        if (ny == 0 || (nx != 0 && tmx < tmy)) { ix += stepx; tmx += tdx; nx--; came = 1; }
-        else { iy += stepy; tmy += tdy; ny--; came = 2; }
+    };
+    uint32_t s, e;
+    cell_range(ix, iy, s, e);
+    for (;;) {
+        const bool last = nx == 0 && ny == 0;
+        const int came_now = came;
+        uint32_t s2 = 0, e2 = 0;
+        if (!last) {
+            if (ny == 0 || (nx != 0 && tmx < tmy)) { ix += stepx; tmx += tdx; nx--; came = 1; }
+            else { iy += stepy; tmy += tdy; ny--; came = 2; }
+            cell_range(ix, iy, s2, e2);
+        }
+        // a shape is new here iff the cell we came from is outside its (in-grid) cell rect
+        const uint32_t need = came_now == 0 ? 0u : (came_now == 1 ? (stepx > 0 ? kEntFirstCol : kEntLastCol)
+                                                                  : (stepy > 0 ? kEntFirstRow : kEntLastRow));
+        for (uint32_t k = s; k < e; k++) {
+            const uint32_t ent = d.entries[k];
+            if ((ent & need) != need) continue;
+            f(ent >> kEntShift, k);
+        }
+        if (last) break;
+        s = s2; e = e2;
     }
 }
 
