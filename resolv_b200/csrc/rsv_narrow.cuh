@@ -468,7 +468,8 @@ __device__ __forceinline__ void narrow_one(const DevView& d, double2* sva, doubl
 // GROUP 0: the convex-convex bins with staged vertices (the heavy ones; compiled on their own so that the other pair
 // tests do not inflate this kernel's registers and code). GROUP 1: every other bin.
 template <int GROUP>
-__global__ void __launch_bounds__(kNarrowBlock, RSV_NARROW_MIN_BLOCKS) k_narrow(DevView d) {
+// (the convex-convex instantiation fits 96 registers without spilling: five blocks per SM; the mixed one does not)
+__global__ void __launch_bounds__(kNarrowBlock, GROUP == 0 ? RSV_NARROW_MIN_BLOCKS + 1 : RSV_NARROW_MIN_BLOCKS) k_narrow(DevView d) {
     __shared__ double2 s_va[kStageVerts][kNarrowBlock];
     __shared__ double2 s_vb[kStageVerts][kNarrowBlock];
     if (d.ctr->overflow & RSV_OVF_PAIRS) return;
