@@ -80,7 +80,7 @@ struct rsv_space {
     rsv_timing_info timing{};
     int narrow_blocks = 148 * 4;
     int narrow_blocks1 = 148 * 4;
-    int pairs_blocks = 148 * 8;
+    int pairs_blocks[2] = {148 * 8, 148 * 8};  // k_pairs<false> (no tag filters), k_pairs<true>
     // peer-memory halo transport (rsv_halo_abi.inl)
     void* mailbox = nullptr;            // this device's mailbox
     uint32_t mailbox_cap = 0;
@@ -304,8 +304,10 @@ int32_t rsv_create(const rsv_config* cfg, rsv_space** out) {
         s->narrow_blocks = s->sm_count * occ;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_narrow<1>, kNarrowBlock, 0) == cudaSuccess && occ > 0)
         s->narrow_blocks1 = s->sm_count * occ;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pairs, kPairsBlock, 0) == cudaSuccess && occ > 0)
-        s->pairs_blocks = s->sm_count * occ;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pairs<false>, kPairsBlock, 0) == cudaSuccess && occ > 0)
+        s->pairs_blocks[0] = s->sm_count * occ;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pairs<true>, kPairsBlock, 0) == cudaSuccess && occ > 0)
+        s->pairs_blocks[1] = s->sm_count * occ;
     CUC(cudaStreamSynchronize(s->stream));
 #undef CUC
     *out = s;
@@ -471,7 +473,10 @@ static int32_t enqueue_frame(rsv_space* s, const DevView& d, int32_t margin, uin
     k_entboxes<<<gcap, kGridBlock, 0, st>>>(d, flags);
     mark(RSV_K_PAIRS);
     const bool grid_only = (flags & RSV_FRAME_GRID_ONLY) != 0;
-    if (d.n_shapes && !grid_only) k_pairs<<<s->pairs_blocks, kPairsBlock, 0, st>>>(d, margin, flags);
+    if (d.n_shapes && !grid_only) {
+        if (flags & RSV_FRAME_NO_TAG_FILTERS) k_pairs<false><<<s->pairs_blocks[0], kPairsBlock, 0, st>>>(d, margin, flags);
+        else k_pairs<true><<<s->pairs_blocks[1], kPairsBlock, 0, st>>>(d, margin, flags);
+    }
     mark(RSV_K_NARROW);
     if (!grid_only) {
         k_bin<<<s->sm_count * 8, 256, 0, st>>>(d);
@@ -498,7 +503,7 @@ static int32_t frame_via_graph(rsv_space* s, const DevView& d, int32_t margin, u
                                rsv_space::FrameGraph& g, cudaStream_t st) {
     rsv_space::FrameGraph::Key key{};
     key.margin = margin; key.flags = flags; key.stream = st; key.n_tiles = s->n_tiles;
-    key.blocks[0] = s->pairs_blocks; key.blocks[1] = s->narrow_blocks; key.blocks[2] = s->narrow_blocks1;
+    key.blocks[0] = s->pairs_blocks[0] ^ (s->pairs_blocks[1] << 16); key.blocks[1] = s->narrow_blocks; key.blocks[2] = s->narrow_blocks1;
     const bool same = g.seen && memcmp(&key, &g.key, sizeof key) == 0 && memcmp(&d, &g.view, sizeof d) == 0;
     if (!same) {
         drop_graph(g);

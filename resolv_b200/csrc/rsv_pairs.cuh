@@ -40,12 +40,18 @@
 
 namespace rsv {
 
-constexpr int kPairsBlock = 128;
+#ifndef RSV_PAIRS_BLOCK
+#define RSV_PAIRS_BLOCK 128
+#endif
+#ifndef RSV_ITEM_ROUND
+#define RSV_ITEM_ROUND 160
+#endif
+constexpr int kPairsBlock = RSV_PAIRS_BLOCK;
 constexpr int kPairsWarps = kPairsBlock / 32;
 constexpr int kPairsChunk = 256;  // entries per grabbed chunk
 constexpr int kPairStage = 96;    // staged records per warp batch
 constexpr int kRowGroup = 4;      // query-rect rows flattened together
-constexpr int kItemRound = 160;   // items staged through shared memory per round
+constexpr int kItemRound = RSV_ITEM_ROUND;   // items staged through shared memory per round
 constexpr int kCandWords = 60;    // super-round = kCandWords * 32 items = 12 rounds
 constexpr uint32_t kSuper = kCandWords * 32;
 static_assert(kSuper % kItemRound == 0, "super-rounds are whole rounds");
@@ -65,12 +71,13 @@ __device__ __forceinline__ uint32_t popc_range(const uint32_t* cw, uint32_t lo, 
     return n;
 }
 
+template <bool FILTERS>
 struct PairsWarpSmem {
     float4 itBox[kItemRound];   // cp.async landing zone: entry float boxes
     float4 fbox[32];            // outward-rounded float AABB of each tester of the batch
     uint4 cum[32];              // per tester: cumulative run lengths of the current row group
     uint2 run[kRowGroup][32];   // per (row, tester): (start of run, end of the run's first cell)
-    unsigned long long itTags[kItemRound];  // cp.async landing zone: entry tags (frames with tag filters only)
+    unsigned long long itTags[FILTERS ? kItemRound : 1];  // cp.async landing zone: entry tags (frames with tag filters only)
     uint32_t itEnt[kItemRound]; // cp.async landing zone: entry words
     uint16_t itMeta[kItemRound];  // tester lane | first-column-cell << 5 | first-row << 6
     uint32_t queue[64];         // home entries waiting for a full batch
@@ -97,10 +104,11 @@ __device__ __forceinline__ bool exact_gate(const DevView& d, uint32_t A, uint32_
 //  kStage: count candidates; stage every candidate that survives the float gate (or every candidate in `all` mode).
 //  kCount: count candidates and records with the exact gate inline.   kWrite: same walk, records written in place.
 // Returns the number of staged (kStage) or produced (kCount/kWrite) records; uniform across the warp.
-template <int MODE>
-__device__ __forceinline__ uint32_t pairs_pass(const DevView& d, bool all, bool filters, unsigned long long myAny,
-                                               unsigned long long myNone, PairsWarpSmem& sm, bool have, int rows,
+template <int MODE, bool FILTERS>
+__device__ __forceinline__ uint32_t pairs_pass(const DevView& d, bool all, unsigned long long myAny,
+                                               unsigned long long myNone, PairsWarpSmem<FILTERS>& sm, bool have, int rows,
                                                const uint32_t* row0, int ncols, uint32_t chunk) {
+    constexpr bool filters = FILTERS;
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
     uint32_t produced = 0;
@@ -264,7 +272,8 @@ __device__ __forceinline__ uint32_t pairs_pass(const DevView& d, bool all, bool 
 
 // Assigns every staged record its index within its tester's records (stage order is generation order within a
 // tester), one record per lane.
-__device__ __forceinline__ uint32_t pairs_assign(PairsWarpSmem& sm, uint32_t staged) {
+template <bool FILTERS>
+__device__ __forceinline__ uint32_t pairs_assign(PairsWarpSmem<FILTERS>& sm, uint32_t staged) {
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
     for (uint32_t base = 0; base < staged; base += 32) {
@@ -284,17 +293,17 @@ __device__ __forceinline__ uint32_t pairs_assign(PairsWarpSmem& sm, uint32_t sta
 }
 
 // One batch: lane `lane` owns a tester, given by its home entry index `hk` (or, for orphans, directly by slot A).
+template <bool FILTERS>
 __device__ __forceinline__ void pairs_batch(const DevView& d, int margin, uint32_t flags, bool have, uint32_t hk,
-                                            uint32_t A, PairsWarpSmem& sm, unsigned long long& my_cands) {
+                                            uint32_t A, PairsWarpSmem<FILTERS>& sm, unsigned long long& my_cands) {
     const int lane = threadIdx.x & 31;
     const bool all = (flags & RSV_FRAME_ALL_CANDIDATES) != 0;
     int rows = 0, ncols = 0;
     bool useAnyBit = false;
     unsigned long long myAny = 0, myNone = 0;
-    const bool filtersOn = !(flags & RSV_FRAME_NO_TAG_FILTERS);
     const uint32_t* row0 = d.cell;
     if (have) {
-        const bool filters0 = !(flags & RSV_FRAME_NO_TAG_FILTERS);
+        constexpr bool filters0 = FILTERS;
         int qx0, qx1, qy0, qy1;
         uint32_t base_cell;
         if (hk != kNoEntry) {
@@ -323,7 +332,7 @@ __device__ __forceinline__ void pairs_batch(const DevView& d, int margin, uint32
             ncols = qx1 - qx0 + 1;
             row0 = d.cell + base_cell + (size_t)(qy0 - d.row_lo) * (size_t)d.W + qx0;
         }
-        const bool filters = !(flags & RSV_FRAME_NO_TAG_FILTERS);
+        constexpr bool filters = FILTERS;
         const bool useAny = filters && useAnyBit;
         ulonglong2 qm = make_ulonglong2(0ull, 0ull);
         if (filters) qm = __ldg(d.qmask + A);
@@ -334,7 +343,7 @@ __device__ __forceinline__ void pairs_batch(const DevView& d, int margin, uint32
     sm.cand[lane] = 0;
     sm.gated[lane] = 0;
     __syncwarp();
-    const uint32_t staged = pairs_pass<kStage>(d, all, filtersOn, myAny, myNone, sm, have, rows, row0, ncols, 0u);
+    const uint32_t staged = pairs_pass<kStage, FILTERS>(d, all, myAny, myNone, sm, have, rows, row0, ncols, 0u);
     const bool fits = staged <= kPairStage;
     uint32_t total;
     if (fits) {
@@ -342,7 +351,7 @@ __device__ __forceinline__ void pairs_batch(const DevView& d, int margin, uint32
     } else {
         sm.cand[lane] = 0;
         __syncwarp();
-        total = pairs_pass<kCount>(d, all, filtersOn, myAny, myNone, sm, have, rows, row0, ncols, 0u);
+        total = pairs_pass<kCount, FILTERS>(d, all, myAny, myNone, sm, have, rows, row0, ncols, 0u);
     }
     const uint32_t cnt = sm.gated[lane];
     my_cands += sm.cand[lane];
@@ -377,15 +386,18 @@ __device__ __forceinline__ void pairs_batch(const DevView& d, int margin, uint32
         sm.cand[lane] = 0;
         sm.gated[lane] = 0;
         __syncwarp();
-        pairs_pass<kWrite>(d, all, filtersOn, myAny, myNone, sm, have, rows, row0, ncols, chunk);
+        pairs_pass<kWrite, FILTERS>(d, all, myAny, myNone, sm, have, rows, row0, ncols, chunk);
     }
     __syncwarp();
 }
 
+// FILTERS = false: frames launched with RSV_FRAME_NO_TAG_FILTERS (no tags staged: less shared memory per warp, so
+// more warps per SM for this latency-bound kernel).
+template <bool FILTERS>
 __global__ void __launch_bounds__(kPairsBlock) k_pairs(DevView d, int margin, uint32_t flags) {
-    __shared__ PairsWarpSmem s_warp[kPairsWarps];
+    __shared__ PairsWarpSmem<FILTERS> s_warp[kPairsWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    PairsWarpSmem& sm = s_warp[warp];
+    PairsWarpSmem<FILTERS>& sm = s_warp[warp];
     uint32_t* q = sm.queue;
     unsigned long long my_cands = 0;
     const uint32_t R = (uint32_t)min((unsigned long long)d.cap_entries, d.ctr->n_entries);
@@ -412,7 +424,7 @@ __global__ void __launch_bounds__(kPairsBlock) k_pairs(DevView d, int margin, ui
             if (qn >= 32) {
                 uint32_t hk = q[lane];
                 __syncwarp();
-                pairs_batch(d, margin, flags, true, hk, 0u, sm, my_cands);
+                pairs_batch<FILTERS>(d, margin, flags, true, hk, 0u, sm, my_cands);
                 if (lane + 32 < qn) { uint32_t t = q[lane + 32]; q[lane] = t; }
                 qn -= 32;
                 __syncwarp();
@@ -421,7 +433,7 @@ __global__ void __launch_bounds__(kPairsBlock) k_pairs(DevView d, int margin, ui
     }
     if (qn) {
         uint32_t hk = lane < qn ? q[lane] : kNoEntry;
-        pairs_batch(d, margin, flags, lane < qn, hk, 0u, sm, my_cands);
+        pairs_batch<FILTERS>(d, margin, flags, lane < qn, hk, 0u, sm, my_cands);
     }
     // testers with no stored cell whose margin still reaches the grid
     const uint32_t n_orph = min(d.ctr->n_orphans, d.n_shapes);
@@ -432,7 +444,7 @@ __global__ void __launch_bounds__(kPairsBlock) k_pairs(DevView d, int margin, ui
         if (o >= n_orph) break;
         bool have = o + lane < n_orph;
         uint32_t A = have ? d.orphans[o + lane] : 0u;
-        pairs_batch(d, margin, flags, have, kNoEntry, A, sm, my_cands);
+        pairs_batch<FILTERS>(d, margin, flags, have, kNoEntry, A, sm, my_cands);
     }
     for (int o = 16; o > 0; o >>= 1) my_cands += __shfl_down_sync(0xffffffffu, my_cands, o);
     if (lane == 0 && my_cands) atomicAdd(&d.ctr->n_candidates, my_cands);
