@@ -358,7 +358,8 @@ def run_reference(args):
     n_gpus = args.gpus
     return {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
             "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": workload_name(args, 1), "margin": 1},
+            "data": "synthetic", "config": {"workload": workload_name(args, max(n_gpus, 1)), "margin": 1,
+                                            "note": "throughput per frame is measured on the bounded sample described in cpu_baseline.sample"},
             "pair_tests_per_sec": cb["pair_tests_per_sec"], "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
