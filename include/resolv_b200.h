@@ -215,6 +215,8 @@ int32_t rsv_timer_stop(rsv_space* s, float* ms);
  * ShapeLineTest (convexPolygon.go:322-415) is built on this by the host layer: one ray per selected vertex. */
 #define RSV_LINE_DDA 0x100u
 #define RSV_LINE_RESIDENT 0x200u /* rays of the previous call are still on the device: skip their upload */
+#define RSV_LINE_HOME_ONLY 0x400u /* strip partitioning: report a shape only on the device whose home rows hold its first cell row,
+                                     so that the union of all devices' sets for a ray is the ray's result on the whole Space */
 #define RSV_FRAME_GRID_ONLY 0x20u /* rsv_frame: rebuild the grid only (no candidate pairs, no narrowphase) */
 #define RSV_OVF_RAY_HITS 0x8u
 #define RSV_OVF_RAY_CONTACTS 0x10u
@@ -258,7 +260,7 @@ typedef struct rsv_ray_results {
  * which = 1: u64[3*max_rays] (ByTags mask, OR of NotByTags masks, bit0 = chain has ByTags | space index << 32). */
 void* rsv_ray_staging(rsv_space* s, int32_t which, size_t* bytes);
 int32_t rsv_ray_reserve(rsv_space* s, uint32_t max_hits, uint32_t max_contacts);
-/* flags: RSV_FRAME_DOWNLOAD | RSV_LINE_DDA | RSV_LINE_RESIDENT */
+/* flags: RSV_FRAME_DOWNLOAD | RSV_LINE_DDA | RSV_LINE_RESIDENT | RSV_LINE_HOME_ONLY */
 int32_t rsv_linetest(rsv_space* s, uint32_t n_rays, uint32_t flags, rsv_ray_counts* out);
 int32_t rsv_linetest_launch(rsv_space* s, uint32_t n_rays, uint32_t flags);
 int32_t rsv_linetest_finish(rsv_space* s, rsv_ray_counts* out);

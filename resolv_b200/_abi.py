@@ -74,7 +74,7 @@ class RayResults(C.Structure):
                 ("ray_first", C.c_void_p), ("ray_count", C.c_void_p), ("n_rays", C.c_uint64)]
 
 
-LINE_DDA, LINE_RESIDENT, FRAME_GRID_ONLY = 0x100, 0x200, 0x20
+LINE_DDA, LINE_RESIDENT, LINE_HOME_ONLY, FRAME_GRID_ONLY = 0x100, 0x200, 0x400, 0x20
 HIT_DTYPE = np.dtype([("a", np.uint32), ("b", np.uint32), ("first_contact", np.uint32), ("count_rank", np.uint32),
                       ("mtv", np.float64, (2,))])
 CONTACT_DTYPE = np.dtype([("p", np.float64, (2,)), ("n", np.float64, (2,))])

@@ -85,6 +85,7 @@ struct Ray {
     V2 start;      // cast line start (pulled back by castMargin)
     unsigned long long any, none;
     bool useAny;
+    bool homeOnly;  // RSV_LINE_HOME_ONLY
 };
 
 // Tests one shape against the cast line. PASS 0 counts contacts; PASS 1 writes them to out[0..n), sorts them and
@@ -148,6 +149,7 @@ __device__ __forceinline__ uint32_t ray_vs_shape(const DevView& d, const Ray& ra
 }
 
 __device__ __forceinline__ bool ray_filter(const DevView& d, const Ray& ray, uint32_t B) {
+    if (ray.homeOnly && !is_home(d, d.crect[B])) return false;   // strips: another device reports this shape
     if (!ray.useAny && ray.none == 0) return true;
     const unsigned long long t = __ldg(d.tags + B);
     if (ray.useAny && (t & ray.any) == 0) return false;   // ByTags (tags.go:29-31)
@@ -295,7 +297,9 @@ __device__ __forceinline__ Ray ray_from_smem(const RayWarpSmem& sm, int o) {
     return r;
 }
 
-__device__ __forceinline__ void load_ray(const DevView& d, const LinesView& L, uint32_t i, Ray& ray, uint32_t& space) {
+__device__ __forceinline__ void load_ray(const DevView& d, const LinesView& L, uint32_t i, Ray& ray, uint32_t& space,
+                                         bool home_only) {
+    ray.homeOnly = home_only;
     const double2* sp = reinterpret_cast<const double2*>(L.seg + 4 * (size_t)i);
     const double2 s = __ldg(sp), e = __ldg(sp + 1);
     ray.S = V2{s.x, s.y}; ray.E = V2{e.x, e.y};
@@ -310,10 +314,10 @@ __device__ __forceinline__ void load_ray(const DevView& d, const LinesView& L, u
 }
 
 // The whole LineTest of one ray by one thread (count pass, allocation, write pass). Returns the number of hits.
-__device__ __noinline__ uint32_t ray_serial(const DevView d, const LinesView L, bool dda, uint32_t i) {  // (by value: a reference would make the kernel keep an addressable copy of its parameters)
+__device__ __noinline__ uint32_t ray_serial(const DevView d, const LinesView L, bool dda, uint32_t i, bool home_only) {  // (by value: a reference would make the kernel keep an addressable copy of its parameters)
     Ray ray{};
     uint32_t space = 0;
-    load_ray(d, L, i, ray, space);
+    load_ray(d, L, i, ray, space, home_only);
     uint32_t nh = 0, nc = 0;
     ray_candidates(d, ray, dda, space, [&](uint32_t B, uint32_t k) {
         if (!ray_filter(d, ray, B)) return;
@@ -352,7 +356,7 @@ __global__ void __launch_bounds__(kLinesBlock, 3) k_linetest(DevView d, LinesVie
     __shared__ RayWarpSmem s_warp[kLinesWarps];
     const int lane = threadIdx.x & 31;
     RayWarpSmem& sm = s_warp[threadIdx.x >> 5];
-    const bool dda = (flags & RSV_LINE_DDA) != 0;
+    const bool dda = (flags & RSV_LINE_DDA) != 0, home_only = (flags & RSV_LINE_HOME_ONLY) != 0;
     unsigned long long my_cands = 0, my_hits = 0;
     const uint32_t stride = gridDim.x * kLinesBlock;
     for (uint32_t base = blockIdx.x * kLinesBlock + (threadIdx.x & ~31u); base < L.n_rays; base += stride) {
@@ -361,7 +365,7 @@ __global__ void __launch_bounds__(kLinesBlock, 3) k_linetest(DevView d, LinesVie
         Ray ray{};
         uint32_t space = 0, cnt = 0;
         if (live) {
-            load_ray(d, L, i, ray, space);
+            load_ray(d, L, i, ray, space, home_only);
             // ---- W1: count the items of this ray (and keep the first few)
             uint32_t rank = 0;
             ray_candidates(d, ray, dda, space, [&](uint32_t B, uint32_t k) {
@@ -391,7 +395,7 @@ __global__ void __launch_bounds__(kLinesBlock, 3) k_linetest(DevView d, LinesVie
             // rays r0.. fit as long as the mask is contiguous from r0 (incl is monotone, so it is)
             const int r1 = fits ? 32 - __clz(fits) : r0;
             if (r1 == r0) {  // this ray alone overflows the queue
-                if (lane == r0 && live) my_hits += ray_serial(d, L, dda, i);
+                if (lane == r0 && live) my_hits += ray_serial(d, L, dda, i, home_only);
                 __syncwarp();
                 r0++;
                 continue;

@@ -113,7 +113,7 @@ class StripRank:
     """One rank of a strip-partitioned Space: the local DeviceSpace holds tiles rank-1, rank, rank+1 (3n slots; the
     owned range is [n, 2n)), stores rows [row_lo,row_hi) and runs frames on torch's current CUDA stream."""
 
-    def __init__(self, kind, n, rank, world, device, margin=1, span_rows=1, cap_halo=65536, seed=20265, size=65536):
+    def __init__(self, kind, n, rank, world, device, margin=1, span_rows=1, cap_halo=65536, seed=20265, size=65536, max_rays=0):
         import torch
         from . import _abi, worlds
         self.n, self.rank, self.world = n, rank, world
@@ -135,7 +135,7 @@ class StripRank:
         self.plan = make_plan(rank, world, H, margin, span_rows)
         self.ds = _abi.DeviceSpace(self.w.space_w, space_h, self.w.cell_w, cell_h, max_shapes=3 * n,
                                    max_verts=max(len(self.w.verts), 1), device=device, row_lo=self.plan.row_lo,
-                                   row_hi=self.plan.row_hi)
+                                   row_hi=self.plan.row_hi, max_rays=max_rays)
         self.ds.upload_world(self.w)
         meta = self.ds.buf[_abi.BUF_META][:3 * n]
         meta[self.absent] |= _abi.META_ABSENT
@@ -249,6 +249,18 @@ class StripRank:
     def step_launch(self, extra_flags=0):
         self.halo_step()
         self.ds.frame_launch(self.margin, self.flags | extra_flags)
+
+    def linetest(self, rays, flags=0, **kw):
+        """LineTest of a batch of rays against the shapes HOMED on this rank (RSV_LINE_HOME_ONLY): every rank is given
+        the same rays, each (ray, shape) set is produced by exactly one rank, and the union over ranks is the result on
+        the whole Space. Returns (hits with GLOBAL shape slots, contacts, ray_first, ray_count) of this rank; callers
+        gather them at the ray's owner (e.g. dist.all_gather_object) and order each ray's sets by `key`."""
+        from . import _abi
+        self.ds.linetest(rays, flags=flags | _abi.FRAME_DOWNLOAD | _abi.LINE_HOME_ONLY, **kw)
+        hits, con, first, count = self.ds.ray_results()
+        hits = hits.copy()
+        hits["b"] = self.global_slot(hits["b"]).astype(np.uint32)
+        return hits, con.copy(), first.copy(), count.copy()
 
     def global_slot(self, local):
         return np.asarray(local, dtype=np.int64) + (self.rank - 1) * self.n

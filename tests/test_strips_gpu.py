@@ -81,3 +81,53 @@ def test_two_strips_equal_one_space(kind, transport):
         for sr in ranks:
             sr.close()
         ref.close()
+
+
+@pytest.mark.parametrize("dda", [False, True])
+def test_rays_across_two_strips(dda):
+    """Every rank tests all rays against the shapes homed on it (RSV_LINE_HOME_ONLY); the union over ranks must be the
+    single-Space LineTest: same (ray, shape) sets, bit-identical MTV / Center / key / contacts."""
+    import torch
+    from resolv_b200 import worlds
+    n, size, world = 20000, 9280, 2
+    ranks = [strips.StripRank("cfg3", n, r, world, 0, size=size, cap_halo=8192, max_rays=2000) for r in range(world)]
+    ref_world = strips.concat_worlds([strips.tile_world("cfg3", n, t, size=size) for t in range(world)], size * world)
+    rays = worlds.make_rays(6000, 77, ref_world.space_w, ref_world.space_h, 16, 1200)
+    rays[:2000, 1] = size - 40 + (rays[:2000, 1] % 80)       # a third of the rays start right at the strip boundary
+    ref = space_for_world(ref_world, max_rays=len(rays))
+    fl = _abi.LINE_DDA if dda else 0
+    try:
+        for sr in ranks:
+            sr.pack()
+        torch.cuda.synchronize()
+        ranks[1].recv_up.copy_(ranks[0].send_dn)
+        ranks[0].recv_dn.copy_(ranks[1].send_up)
+        torch.cuda.synchronize()
+        got = {}
+        for sr in ranks:
+            sr.apply()
+            sr.ds.frame(1, sr.flags | _abi.FRAME_GRID_ONLY)
+            # (the ray capacity of a StripRank's space is whatever its default is: feed the rays in slices)
+            step = 2000
+            for lo in range(0, len(rays), step):
+                hits, con, first, count = sr.linetest(rays[lo:lo + step], flags=fl)
+                for h in hits:
+                    k, c0 = int(h["count_rank"] & 0xff), int(h["first_contact"])
+                    key = (lo + int(h["ray"]), int(h["b"]))
+                    assert key not in got, "a (ray, shape) set was produced by both ranks"
+                    got[key] = (bits(h["mtv"]).tolist(), bits(h["center"]).tolist(), int(bits(np.array([h["key"]]))[0]),
+                                bits(np.concatenate([con["p"][c0:c0 + k], con["n"][c0:c0 + k]], -1)).tolist())
+        ref.frame(1, _abi.FRAME_GRID_ONLY)
+        ref.linetest(rays, flags=_abi.FRAME_DOWNLOAD | fl)
+        rh, rc, _, _ = ref.ray_results()
+        want = {}
+        for h in rh:
+            k, c0 = int(h["count_rank"] & 0xff), int(h["first_contact"])
+            want[(int(h["ray"]), int(h["b"]))] = (bits(h["mtv"]).tolist(), bits(h["center"]).tolist(), int(bits(np.array([h["key"]]))[0]),
+                                                   bits(np.concatenate([rc["p"][c0:c0 + k], rc["n"][c0:c0 + k]], -1)).tolist())
+        assert len(want) > 3000
+        assert got == want
+    finally:
+        for sr in ranks:
+            sr.close()
+        ref.close()
