@@ -80,6 +80,10 @@ enum {
 #define RSV_META_TESTER 0x4u   /* this shape runs IntersectionTest in rsv_frame */
 #define RSV_META_USE_ANY 0x8u  /* tester's filter chain contains ByTags(qmask[2i]) */
 #define RSV_META_ABSENT 0x10u  /* slot is free / shape was Space.Remove()d (space.go:50-66): in no cell, never a tester */
+#define RSV_META_STATIC 0x20u  /* the host promises that this shape has not moved (position, local bounds, tags, Space)
+                                  since the flag was committed: RSV_FRAME_INCREMENTAL keeps its cell registrations. The
+                                  counterpart of the reference only touching the cells of the shape whose update()
+                                  ran (shape.go:239-242); tiles and walls of a platformer never re-register. */
 #define RSV_META_NV_SHIFT 8
 #define RSV_MAX_POLY_VERTS 255
 
@@ -218,6 +222,19 @@ int32_t rsv_timer_stop(rsv_space* s, float* ms);
 #define RSV_LINE_HOME_ONLY 0x400u /* strip partitioning: report a shape only on the device whose home rows hold its first cell row,
                                      so that the union of all devices' sets for a ray is the ray's result on the whole Space */
 #define RSV_FRAME_GRID_ONLY 0x20u /* rsv_frame: rebuild the grid only (no candidate pairs, no narrowphase) */
+/* Incremental grid. Replaces re-registering every shape every frame — which the reference never
+ * does: only ShapeBase.update of a moved shape touches cells (shape.go:183-214,239-242, cell.go:19-38) — for worlds
+ * that are mostly static. The registrations of all RSV_META_STATIC shapes are built once and cached on the device;
+ * a frame re-registers only the other shapes and merges both into a grid that is bit-identical to a full rebuild
+ * (so every result of the frame is, too). The cache is dropped by rsv_commit of META / LOCAL_AABB / TAGS /
+ * SPACE_IDX, by rsv_set_counts with a new shape count, and by rsv_static_invalidate (call it after moving a static
+ * shape); the next incremental frame rebuilds it (synchronously). Ignored (full rebuild) for strip-partitioned
+ * spaces and when more than half of the shapes are dynamic. */
+#define RSV_FRAME_INCREMENTAL 0x40u
+int32_t rsv_static_invalidate(rsv_space* s);
+/* Registrations held by the cached static grid and number of shapes re-registered per frame (0 / n_shapes while no
+ * cache exists). */
+int32_t rsv_static_info(rsv_space* s, uint32_t* static_entries, uint32_t* n_dynamic);
 #define RSV_OVF_RAY_HITS 0x8u
 #define RSV_OVF_RAY_CONTACTS 0x10u
 

@@ -19,7 +19,9 @@ BUF_DTYPES = {BUF_POS: np.float64, BUF_LOCAL_AABB: np.float64, BUF_RADIUS: np.fl
               BUF_META: np.uint32, BUF_VERT_OFF: np.uint32, BUF_VERTS: np.float64, BUF_QMASK: np.uint64,
               BUF_SPACE_IDX: np.uint32}
 META_POLYGON, META_CLOSED, META_TESTER, META_USE_ANY, META_ABSENT, META_NV_SHIFT = 1, 2, 4, 8, 16, 8
+META_STATIC = 0x20
 FRAME_DOWNLOAD, FRAME_ALL_CANDIDATES, FRAME_TIMING, FRAME_NO_TAG_FILTERS, FRAME_TESTER_TABLE = 1, 2, 4, 8, 16
+FRAME_INCREMENTAL = 0x40
 HIT_NOT_GATED = 0x80
 KERNEL_NAMES = ["clear", "bounds", "scan", "scatter", "cellsort", "pairs", "narrow"]
 
@@ -32,6 +34,7 @@ ABI_SYMBOLS = [
     "rsv_linetest_finish", "rsv_ray_staging", "rsv_ray_reserve", "rsv_ray_results_view", "rsv_tester_table",
     "rsv_set_stream", "rsv_strip_setup", "rsv_halo_pack", "rsv_halo_apply", "rsv_staging_page", "rsv_commit_pos_page",
     "rsv_halo_mailbox", "rsv_ipc_export", "rsv_ipc_open", "rsv_ipc_close", "rsv_halo_connect", "rsv_halo_exchange",
+    "rsv_static_invalidate", "rsv_static_info",
 ]
 
 
@@ -147,6 +150,10 @@ def load():
     L.rsv_debug_cells.argtypes = [vp, vp, u64, vp, u64]
     L.rsv_debug_cell_rects.restype = i32
     L.rsv_debug_cell_rects.argtypes = [vp, vp, u64]
+    L.rsv_static_invalidate.restype = i32
+    L.rsv_static_invalidate.argtypes = [vp]
+    L.rsv_static_info.restype = i32
+    L.rsv_static_info.argtypes = [vp, C.POINTER(u32), C.POINTER(u32)]
     if hasattr(L, "rsv_linetest"):
         L.rsv_ray_staging.restype = vp
         L.rsv_ray_staging.argtypes = [vp, i32, C.POINTER(C.c_size_t)]
@@ -250,6 +257,22 @@ class DeviceSpace:
 
     def sync(self):
         self._check(self.L.rsv_sync(self.h))
+
+    # ---- incremental grid (RSV_META_STATIC + FRAME_INCREMENTAL)
+    def set_static(self, mask):
+        """Marks the shapes of the boolean `mask` RSV_META_STATIC (and clears the flag on the others)."""
+        meta = self.buf[BUF_META][:self.n_shapes]
+        meta[:] = np.where(np.asarray(mask, dtype=bool), meta | np.uint32(META_STATIC), meta & np.uint32(~META_STATIC & 0xffffffff))
+        self.commit(1 << BUF_META)
+
+    def static_invalidate(self):
+        self._check(self.L.rsv_static_invalidate(self.h))
+
+    def static_info(self):
+        """(registrations held by the cached static grid, shapes re-registered per frame)."""
+        a, b = C.c_uint32(), C.c_uint32()
+        self._check(self.L.rsv_static_info(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def reserve(self, entries=0, pairs=0, contacts=0):
         self._check(self.L.rsv_reserve(self.h, entries, pairs, contacts))

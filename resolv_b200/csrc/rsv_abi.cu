@@ -86,6 +86,9 @@ struct rsv_space {
     uint32_t mailbox_cap = 0;
     void* peer_mailbox[2] = {};         // neighbours' mailboxes as mapped in this process: 0 upper, 1 lower
     uint32_t halo_epoch = 0;
+    // incremental grid (RSV_FRAME_INCREMENTAL): cached registrations of the RSV_META_STATIC shapes
+    StaticGrid sg{};
+    bool static_valid = false;
     // line tests
     LineState lines{};
     std::string error;
@@ -167,7 +170,7 @@ static int32_t alloc_outputs(rsv_space* s, uint32_t cap_entries, uint32_t cap_pa
         CU(s, cudaMalloc(&d.ent_tags, (size_t)cap_entries * 8));
         if (d.multi) cudaFree(d.multi);
         d.multi = nullptr;
-        d.cap_multi = cap_entries / 2 + 1;  // a cell with >= 2 entries uses up at least two registrations
+        d.cap_multi = cap_entries + 1;  // (incremental frames list every cell that received a dynamic registration)
         CU(s, cudaMalloc(&d.multi, (size_t)d.cap_multi * 4));
         CU(s, cudaMalloc(&d.entries, (size_t)cap_entries * 4));
         CU(s, cudaMalloc(&d.ent_box, (size_t)cap_entries * sizeof(float4)));
@@ -336,6 +339,10 @@ int32_t rsv_destroy(rsv_space* s) {
         if (sl.ev_done) cudaEventDestroy(sl.ev_done);
     }
     for (auto& g : s->graph) drop_graph(g);
+    {
+        void* sv[] = {s->sg.cell, s->sg.entries, s->sg.ent_box, s->sg.ent_home, s->sg.ent_tags, s->sg.cell_of, d.dyn_list, d.n_dyn_dev};
+        for (void* p : sv) if (p) cudaFree(p);
+    }
     if (s->mailbox) cudaFree(s->mailbox);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->side_stream) cudaStreamDestroy(s->side_stream);
@@ -408,6 +415,7 @@ int32_t rsv_set_counts(rsv_space* s, uint32_t n_shapes, uint32_t n_verts) {
     if (!s) return RSV_ERR_BAD_ARG;
     if (n_shapes > s->cfg.max_shapes) return fail(s, RSV_ERR_BAD_ARG, "rsv_set_counts: %u shapes > capacity %u", n_shapes, s->cfg.max_shapes);
     if (n_verts > (s->cfg.max_verts ? s->cfg.max_verts : 1)) return fail(s, RSV_ERR_BAD_ARG, "rsv_set_counts: %u vertices > capacity %u", n_verts, s->cfg.max_verts);
+    if (n_shapes != s->n_shapes) s->static_valid = false;
     s->n_shapes = n_shapes;
     s->n_verts = n_verts;
     s->d.n_shapes = n_shapes;
@@ -419,6 +427,10 @@ int32_t rsv_commit(rsv_space* s, uint32_t which_mask, uint32_t lo, uint32_t hi) 
     if (!s) return RSV_ERR_BAD_ARG;
     if (hi > s->n_shapes) hi = s->n_shapes;
     CU(s, cudaSetDevice(s->device));
+    // anything that can change a static shape's registrations drops the cached static grid (positions are the
+    // host's promise: RSV_META_STATIC means "not moved since the flag was committed")
+    if (which_mask & ((1u << RSV_BUF_META) | (1u << RSV_BUF_LOCAL_AABB) | (1u << RSV_BUF_TAGS) | (1u << RSV_BUF_SPACE_IDX)))
+        s->static_valid = false;
     for (int b = 0; b < RSV_BUF_COUNT; b++) {
         if (!(which_mask & (1u << b))) continue;
         size_t off, len;
@@ -461,16 +473,26 @@ static int32_t enqueue_frame(rsv_space* s, const DevView& d, int32_t margin, uin
     }
     mark(RSV_K_BOUNDS);
     const int gcap = s->sm_count * 8;
-    const uint32_t max_items = (d.own_hi - d.own_lo) + (d.n_ghosts ? d.cap_ghosts : 0u);
+    const bool inc = d.subset == kSubsetDynamic;   // incremental frame: only dyn_list is re-registered
+    const uint32_t max_items = inc ? d.n_dyn : (d.own_hi - d.own_lo) + (d.n_ghosts ? d.cap_ghosts : 0u);
+    // (an incremental frame launches k_bounds even without dynamic shapes: it carries the static counts over)
     if (d.n_shapes) k_bounds<<<blocks_for(max_items, kGridBlock, gcap), kGridBlock, 0, st>>>(d, margin);
     mark(RSV_K_SCAN);
-    k_scan<<<(d.n_cells + 1 + kScanTile - 1) / kScanTile, kScanBlock, 0, st>>>(d.cell, d.n_cells + 1, d.tile_state, &d.ctr->scan_ticket,
-                                                                              d.multi, &d.ctr->n_multi, d.cap_multi);
+    const int scan_blocks = (d.n_cells + 1 + kScanTile - 1) / kScanTile;
+    if (inc) k_scan<true><<<scan_blocks, kScanBlock, 0, st>>>(d.cell, d.n_cells + 1, d.tile_state, &d.ctr->scan_ticket, d.multi,
+                                                              &d.ctr->n_multi, d.cap_multi, s->sg.cell);
+    else k_scan<false><<<scan_blocks, kScanBlock, 0, st>>>(d.cell, d.n_cells + 1, d.tile_state, &d.ctr->scan_ticket, d.multi,
+                                                           &d.ctr->n_multi, d.cap_multi, nullptr);
     mark(RSV_K_SCATTER);
-    if (d.n_shapes) k_scatter<<<blocks_for(max_items, kGridBlock, gcap), kGridBlock, 0, st>>>(d);
+    if (inc && d.static_entries) k_static_place<<<blocks_for(d.static_entries, kGridBlock, gcap), kGridBlock, 0, st>>>(d, s->sg, flags);
+    if (d.n_shapes && max_items) k_scatter<<<blocks_for(max_items, kGridBlock, gcap), kGridBlock, 0, st>>>(d);
     mark(RSV_K_CELLSORT);
-    k_cellsort<<<blocks_for(std::min<uint32_t>(d.n_cells, d.cap_multi), kGridBlock, gcap), kGridBlock, 0, st>>>(d);
-    k_entboxes<<<gcap, kGridBlock, 0, st>>>(d, flags);
+    if (inc) {
+        k_cellfix<<<blocks_for(std::min<uint32_t>(d.n_cells, 4u * std::max<uint32_t>(d.n_dyn, 1u)), kGridBlock, gcap), kGridBlock, 0, st>>>(d, flags);
+    } else {
+        k_cellsort<<<blocks_for(std::min<uint32_t>(d.n_cells, d.cap_multi), kGridBlock, gcap), kGridBlock, 0, st>>>(d);
+        k_entboxes<<<gcap, kGridBlock, 0, st>>>(d, flags);
+    }
     mark(RSV_K_PAIRS);
     const bool grid_only = (flags & RSV_FRAME_GRID_ONLY) != 0;
     if (d.n_shapes && !grid_only) {
@@ -534,10 +556,90 @@ static int32_t frame_via_graph(rsv_space* s, const DevView& d, int32_t margin, u
     return 1;
 }
 
+// One-off build of the cached static grid: the regular grid kernels over the RSV_META_STATIC shapes that hold
+// cells, written into s->sg; every other live shape is appended to dyn_list. Synchronous (two small read-backs).
+static int32_t build_static(rsv_space* s) {
+    DevView& d = s->d;
+    cudaStream_t st = s->stream;
+    StaticGrid& sg = s->sg;
+    const size_t cell_bytes = (size_t)s->n_tiles * kScanTile * 4;
+    if (!sg.cell) CU(s, cudaMalloc(&sg.cell, cell_bytes));
+    if (!d.dyn_list) CU(s, cudaMalloc(&d.dyn_list, (size_t)s->cfg.max_shapes * 4));
+    if (!d.n_dyn_dev) CU(s, cudaMalloc(&d.n_dyn_dev, 4));
+    for (auto& g : s->graph) drop_graph(g);
+    DevView v = d;
+    v.subset = kSubsetStaticBuild;
+    v.cell = sg.cell;
+    const int gcap = s->sm_count * 8;
+    const uint32_t n4 = (uint32_t)(((size_t)d.n_cells + 1 + 3) / 4);
+    k_clear<<<blocks_for(n4, kGridBlock, gcap), kGridBlock, 0, st>>>(reinterpret_cast<uint4*>(sg.cell), n4, d.tile_state, s->n_tiles,
+                                                                     reinterpret_cast<uint32_t*>(d.ctr),
+                                                                     (uint32_t)(offsetof(Counters, ray_hit_cursor) / 4));
+    CU(s, cudaMemsetAsync(d.n_dyn_dev, 0, 4, st));
+    const uint32_t items = d.own_hi - d.own_lo;
+    if (items) k_bounds<<<blocks_for(items, kGridBlock, gcap), kGridBlock, 0, st>>>(v, 0);
+    Counters hc_local{};   // (pageable on purpose: the pinned mirrors may belong to a frame / ray batch in flight)
+    Counters* hc = &hc_local;
+    uint32_t n_dyn = 0;
+    CU(s, cudaMemcpyAsync(hc, d.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CU(s, cudaMemcpyAsync(&n_dyn, d.n_dyn_dev, 4, cudaMemcpyDeviceToHost, st));
+    CU(s, cudaStreamSynchronize(st));
+    if (hc->n_entries >= 0xfffffff0ull) return fail(s, RSV_ERR_CAPACITY, "static grid: %llu registrations", (unsigned long long)hc->n_entries);
+    const uint32_t Rs = (uint32_t)hc->n_entries;
+    if (Rs > sg.cap) {
+        void* old[] = {sg.entries, sg.ent_box, sg.ent_home, sg.ent_tags, sg.cell_of};
+        for (void* p : old) if (p) cudaFree(p);
+        sg.entries = nullptr; sg.ent_box = nullptr; sg.ent_home = nullptr; sg.ent_tags = nullptr; sg.cell_of = nullptr; sg.cap = 0;
+        const uint32_t cap = (uint32_t)std::min<unsigned long long>((unsigned long long)Rs + Rs / 8 + 1024, 0xfffffff0ull);
+        CU(s, cudaMalloc(&sg.entries, (size_t)cap * 4));
+        CU(s, cudaMalloc(&sg.ent_box, (size_t)cap * sizeof(float4)));
+        CU(s, cudaMalloc(&sg.ent_home, (size_t)cap * sizeof(uint2)));
+        CU(s, cudaMalloc(&sg.ent_tags, (size_t)cap * 8));
+        CU(s, cudaMalloc(&sg.cell_of, (size_t)cap * 4));
+        sg.cap = cap;
+    }
+    v.entries = sg.entries; v.ent_box = sg.ent_box; v.ent_home = sg.ent_home; v.ent_tags = sg.ent_tags; v.cap_entries = sg.cap;
+    k_scan<false><<<(d.n_cells + 1 + kScanTile - 1) / kScanTile, kScanBlock, 0, st>>>(sg.cell, d.n_cells + 1, d.tile_state, &d.ctr->scan_ticket,
+                                                                                     d.multi, &d.ctr->n_multi, d.cap_multi, nullptr);
+    if (items) k_scatter<<<blocks_for(items, kGridBlock, gcap), kGridBlock, 0, st>>>(v);
+    k_cellsort<<<blocks_for(std::min<uint32_t>(d.n_cells, d.cap_multi), kGridBlock, gcap), kGridBlock, 0, st>>>(v);
+    k_entboxes<<<gcap, kGridBlock, 0, st>>>(v, 0u);   // (tags always: later frames may or may not use filters)
+    k_static_cells<<<blocks_for(d.n_cells, kGridBlock, gcap), kGridBlock, 0, st>>>(sg.cell, d.n_cells, sg.cell_of, sg.cap);
+    CU(s, cudaGetLastError());
+    CU(s, cudaStreamSynchronize(st));
+    d.n_dyn = n_dyn;
+    d.static_entries = Rs;
+    d.static_testers = (uint32_t)hc->n_testers;
+    s->static_valid = true;
+    return RSV_OK;
+}
+
+int32_t rsv_static_invalidate(rsv_space* s) {
+    if (!s) return RSV_ERR_BAD_ARG;
+    s->static_valid = false;
+    return RSV_OK;
+}
+
+int32_t rsv_static_info(rsv_space* s, uint32_t* static_entries, uint32_t* n_dynamic) {
+    if (!s) return RSV_ERR_BAD_ARG;
+    if (static_entries) *static_entries = s->static_valid ? s->d.static_entries : 0u;
+    if (n_dynamic) *n_dynamic = s->static_valid ? s->d.n_dyn : s->n_shapes;
+    return RSV_OK;
+}
+
 int32_t rsv_frame_launch(rsv_space* s, int32_t margin, uint32_t flags) {
     if (!s) return RSV_ERR_BAD_ARG;
     if (margin < 0 || margin > (1 << 20)) return fail(s, RSV_ERR_BAD_ARG, "rsv_frame: margin %d out of range", margin);
     CU(s, cudaSetDevice(s->device));
+    // Incremental frames: single-device Spaces only (strip frames rebuild fully: their ghost set changes every frame).
+    bool inc = (flags & RSV_FRAME_INCREMENTAL) && !s->strip_mode && !s->d.n_ghosts && s->d.n_shapes;
+    if (inc && !s->static_valid) {
+        const int32_t rc = build_static(s);
+        if (rc != RSV_OK) return rc;
+    }
+    // mostly dynamic worlds are cheaper to rebuild in one go
+    if (inc && (unsigned long long)s->d.n_dyn * 2ull > s->d.n_shapes) inc = false;
+    s->d.subset = inc ? kSubsetDynamic : kSubsetAll;
     DevView& d = s->d;
     cudaStream_t st = s->stream;
     rsv_space::FrameSlot& sl = s->slot[s->launch_slot];

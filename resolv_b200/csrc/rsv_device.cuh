@@ -69,6 +69,13 @@ struct DevView {
     uint32_t* n_ghosts;              // device-side count of `ghosts` (nullptr: none)
     uint32_t cap_ghosts;
     int32_t home_lo, home_hi;        // rows whose shapes run IntersectionTest here (default [0, H))
+    // ---- incremental grid (rsv_grid.cuh, RSV_FRAME_INCREMENTAL): which shapes the grid kernels of this launch visit
+    uint32_t subset;                 // kSubsetAll, kSubsetStaticBuild or kSubsetDynamic
+    uint32_t* dyn_list;              // slots that are re-registered every frame (not RSV_META_STATIC, or static orphan testers)
+    uint32_t* n_dyn_dev;             // device-side length of dyn_list (written by the static build)
+    uint32_t n_dyn;                  // its value on the host (valid in kSubsetDynamic frames)
+    uint32_t static_entries;         // registrations / testers held by the cached static grid
+    uint32_t static_testers;
     // ---- results
     rsv_hit* hits;
     uint32_t* kind_queue;            // [cap_pairs]: record indices grouped by narrowphase bin
@@ -107,6 +114,8 @@ __device__ __forceinline__ float4 float_box(const Box& b) {
     return make_float4(__double2float_rd(b.minx), __double2float_rd(b.miny), __double2float_ru(b.maxx),
                        __double2float_ru(b.maxy));
 }
+
+constexpr uint32_t kSubsetAll = 0u, kSubsetStaticBuild = 1u, kSubsetDynamic = 2u;
 
 constexpr int kClampCell = 1 << 30;
 

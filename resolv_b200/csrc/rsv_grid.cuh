@@ -26,11 +26,14 @@ __device__ __forceinline__ bool clamp_rect(const DevView& d, int4 r, int& x0, in
 
 // The shapes a frame processes: the owned slot range plus the halo ("ghost") slots received this frame. For a
 // single-GPU Space the owned range is [0, n_shapes) and there are no ghosts.
+// In the per-frame part of an incremental frame (kSubsetDynamic) they are the slots of dyn_list instead.
 __device__ __forceinline__ uint32_t n_items(const DevView& d) {
+    if (d.subset == kSubsetDynamic) return d.n_dyn;
     uint32_t ng = d.n_ghosts ? min(*d.n_ghosts, d.cap_ghosts) : 0u;
     return (d.own_hi - d.own_lo) + ng;
 }
 __device__ __forceinline__ uint32_t item_slot(const DevView& d, uint32_t j) {
+    if (d.subset == kSubsetDynamic) return d.dyn_list[j];
     const uint32_t n_own = d.own_hi - d.own_lo;
     return j < n_own ? d.own_lo + j : d.ghosts[j - n_own];
 }
@@ -78,11 +81,12 @@ __global__ void __launch_bounds__(kGridBlock) k_bounds(DevView d, int margin) {
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t j0 = blockIdx.x * blockDim.x; j0 < n; j0 += stride) {  // (warp-uniform trip count)
         const uint32_t j = j0 + threadIdx.x;
-        bool big = false;
+        bool big = false, listed = false;
         int x0 = 0, y0 = 0, x1 = -1, y1 = -1;
-        uint32_t base = 0;
+        uint32_t base = 0, islot = 0;
         if (j < n) {
         const uint32_t i = item_slot(d, j);
+        islot = i;
         uint32_t meta = __ldg(d.meta + i);
         double2 p = __ldg(d.pos + i);
         Box lb = load_box(d.laabb + i);
@@ -98,8 +102,16 @@ __global__ void __launch_bounds__(kGridBlock) k_bounds(DevView d, int margin) {
         d.tester_count[i] = 0;
         const bool tester = (meta & RSV_META_TESTER) && !(meta & RSV_META_ABSENT) && is_home(d, r);
         if (tester) my_testers++;
-        const bool in_grid = clamp_rect(d, r, x0, y0, x1, y1);
-        if (tester && !in_grid) {
+        bool in_grid = clamp_rect(d, r, x0, y0, x1, y1);
+        if (d.subset == kSubsetStaticBuild && !((meta & RSV_META_STATIC) && in_grid)) {
+            // Static build: only RSV_META_STATIC shapes that hold cells go into the cached grid. Non-static shapes are
+            // appended to dyn_list and handled by the per-frame part; a static tester outside the grid is listed too
+            // (it may be an orphan tester, whose list is rebuilt every frame, and it has no registrations to repeat).
+            listed = !(meta & RSV_META_ABSENT) && (!(meta & RSV_META_STATIC) || tester);
+            in_grid = false;      // not counted here
+            if (tester) my_testers--;   // (a tester that is not cached is always listed: counted per frame)
+        }
+        if (tester && !in_grid && d.subset != kSubsetStaticBuild) {
             // SelectTouchingCells(margin) can still reach stored cells (shape.go:220-237): k_pairs finds testers
             // through their home registration, so these go to a side list.
             int qx0 = max(r.x - margin, 0), qx1 = min(r.z + margin, d.W - 1);
@@ -121,6 +133,13 @@ __global__ void __launch_bounds__(kGridBlock) k_bounds(DevView d, int margin) {
         warp_big_rects(big, x0, y0, x1, y1, 0u, base, [&](int x, int y, int, int, int, int, uint32_t, uint32_t bb) {
             atomicAdd(d.cell + bb + (uint32_t)(y - d.row_lo) * (uint32_t)d.W + x + 1, 1u);
         });
+        if (d.subset == kSubsetStaticBuild) {   // warp-aggregated append keeps dyn_list nearly in slot order
+            const uint32_t lm = __ballot_sync(0xffffffffu, listed);
+            uint32_t b0 = 0;
+            if ((threadIdx.x & 31) == 0 && lm) b0 = atomicAdd(d.n_dyn_dev, (uint32_t)__popc(lm));
+            b0 = __shfl_sync(0xffffffffu, b0, 0);
+            if (listed) d.dyn_list[b0 + __popc(lm & ((1u << (threadIdx.x & 31)) - 1u))] = islot;
+        }
     }
     // block reduction of the two statistics -> one atomic each per block
     for (int o = 16; o > 0; o >>= 1) {
@@ -134,6 +153,7 @@ __global__ void __launch_bounds__(kGridBlock) k_bounds(DevView d, int margin) {
     if (threadIdx.x == 0) {
         unsigned long long e = 0, t = 0;
         for (int w = 0; w < kGridBlock / 32; w++) { e += s_e[w]; t += s_t[w]; }
+        if (d.subset == kSubsetDynamic && blockIdx.x == 0) { e += d.static_entries; t += d.static_testers; }
         if (e) atomicAdd(&d.ctr->n_entries, e);
         if (t) atomicAdd(&d.ctr->n_testers, t);
     }
@@ -167,9 +187,17 @@ __device__ __forceinline__ void st_state(unsigned long long* p, unsigned long lo
 // In-place exclusive scan of the per-cell counters (data[c + 1] = count of cell c on entry, = first entry of cell c on
 // exit; data[0] = 0). Also appends every cell that holds two or more entries to `multi` — the only cells whose
 // entries k_cellsort has to order.
+//
+// MERGE (incremental frames): `data` holds the counts of the DYNAMIC registrations only and `scell` is the cached
+// static grid (scell[c] .. scell[c+1] = static entries of cell c). The scan runs over dynamic + static counts, and
+// data[c + 1] is left at "first entry of cell c + its static count": the static entries are copied to the front of
+// the cell by k_static_place and the cursor atomics of k_scatter append the dynamic ones behind them. `multi` then
+// lists the cells that received at least one dynamic registration (k_cellfix).
+template <bool MERGE>
 __global__ void __launch_bounds__(kScanBlock) k_scan(uint32_t* __restrict__ data, uint32_t n,
                                                      unsigned long long* __restrict__ state, unsigned int* ticket,
-                                                     uint32_t* __restrict__ multi, unsigned int* n_multi, uint32_t cap_multi) {
+                                                     uint32_t* __restrict__ multi, unsigned int* n_multi, uint32_t cap_multi,
+                                                     const uint32_t* __restrict__ scell) {
     __shared__ uint32_t s_tile, s_prefix, s_warp[kScanBlock / 32];
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
@@ -191,10 +219,11 @@ __global__ void __launch_bounds__(kScanBlock) k_scan(uint32_t* __restrict__ data
             q[g].w = 0u;
         }
     }
-    // cells with >= 2 entries (array index e holds the count of cell e - 1)
+    // cells with >= 2 entries (array index e holds the count of cell e - 1); MERGE: cells with a dynamic entry
+    constexpr uint32_t kListed = MERGE ? 1u : 2u;
     uint32_t m = 0;
 #pragma unroll
-    for (int g = 0; g < kGroups; g++) m += (q[g].x >= 2u) + (q[g].y >= 2u) + (q[g].z >= 2u) + (q[g].w >= 2u);
+    for (int g = 0; g < kGroups; g++) m += (q[g].x >= kListed) + (q[g].y >= kListed) + (q[g].z >= kListed) + (q[g].w >= kListed);
     uint32_t minc = m;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -209,10 +238,30 @@ __global__ void __launch_bounds__(kScanBlock) k_scan(uint32_t* __restrict__ data
 #pragma unroll
         for (int g = 0; g < kGroups; g++) {
             const uint32_t e0 = wbase + (g * 32 + lane) * 4;
-            if (q[g].x >= 2u) { if (mbase < cap_multi) multi[mbase] = e0 - 1; mbase++; }
-            if (q[g].y >= 2u) { if (mbase < cap_multi) multi[mbase] = e0; mbase++; }
-            if (q[g].z >= 2u) { if (mbase < cap_multi) multi[mbase] = e0 + 1; mbase++; }
-            if (q[g].w >= 2u) { if (mbase < cap_multi) multi[mbase] = e0 + 2; mbase++; }
+            if (q[g].x >= kListed) { if (mbase < cap_multi) multi[mbase] = e0 - 1; mbase++; }
+            if (q[g].y >= kListed) { if (mbase < cap_multi) multi[mbase] = e0; mbase++; }
+            if (q[g].z >= kListed) { if (mbase < cap_multi) multi[mbase] = e0 + 1; mbase++; }
+            if (q[g].w >= kListed) { if (mbase < cap_multi) multi[mbase] = e0 + 2; mbase++; }
+        }
+    }
+    // MERGE: static counts of the same cells (index e: static entries of cell e - 1; index 0: none)
+    uint4 sc[MERGE ? kGroups : 1];
+    if (MERGE) {
+        const uint4* ssrc = reinterpret_cast<const uint4*>(scell + wbase) + lane;
+#pragma unroll
+        for (int g = 0; g < kGroups; g++) {
+            const uint32_t e0 = wbase + (g * 32 + lane) * 4;
+            uint4 c4 = make_uint4(0u, 0u, 0u, 0u);
+            if (e0 < n) {
+                const uint4 S = ssrc[g * 32];
+                const uint32_t prev = e0 ? __ldg(scell + e0 - 1) : 0u;
+                c4 = make_uint4(e0 ? S.x - prev : 0u, S.y - S.x, S.z - S.y, S.w - S.z);
+                if (e0 + 1 >= n) c4.y = 0u;
+                if (e0 + 2 >= n) c4.z = 0u;
+                if (e0 + 3 >= n) c4.w = 0u;
+            }
+            sc[g] = c4;
+            q[g].x += c4.x; q[g].y += c4.y; q[g].z += c4.z; q[g].w += c4.w;   // totals from here on
         }
     }
     // warp-level exclusive scan in memory order: groups are g-major, lanes within a group
@@ -279,6 +328,7 @@ __global__ void __launch_bounds__(kScanBlock) k_scan(uint32_t* __restrict__ data
             o.y = run; run += q[g].y;
             o.z = run; run += q[g].z;
             o.w = run;
+            if (MERGE) { o.x += sc[g].x; o.y += sc[g].y; o.z += sc[g].z; o.w += sc[g].w; }
             dst[g * 32] = o;
         }
     }
@@ -314,7 +364,10 @@ __global__ void __launch_bounds__(kGridBlock) k_scatter(DevView d) {
                 tag = (i << kEntShift) | (((meta & RSV_META_TESTER) && is_home(d, r)) ? kEntTester : 0u) |
                       ((meta & RSV_META_USE_ANY) ? kEntUseAny : 0u);
                 big = (long long)(x1 - x0 + 1) * (long long)(y1 - y0 + 1) > kBigCells;
-                if (!big)
+                // (static build: only the RSV_META_STATIC shapes are placed)
+                const bool skip = d.subset == kSubsetStaticBuild && !(meta & RSV_META_STATIC);
+                if (skip) big = false;
+                if (!big && !skip)
                     for (int y = y0; y <= y1; y++)
                         for (int x = x0; x <= x1; x++) place(x, y, x0, y0, x1, y1, tag, base);
             }
@@ -360,6 +413,81 @@ __global__ void __launch_bounds__(kGridBlock) k_entboxes(DevView d, uint32_t fla
             clamp_rect(d, d.crect[i], x0, y0, x1, y1);
             const uint32_t c = cell_base(d, i) + (uint32_t)(y0 - d.row_lo) * (uint32_t)d.W + (uint32_t)x0;
             d.ent_home[k] = make_uint2(c, (uint32_t)(x1 - x0) | ((uint32_t)(y1 - y0) << 16));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Incremental grid (RSV_FRAME_INCREMENTAL): the registrations of RSV_META_STATIC shapes are kept from a one-off
+// static build (same kernels, kSubsetStaticBuild, into the s* arrays below); a frame only re-registers the shapes
+// of dyn_list. Mirrors what the reference does for a mostly static world: ShapeBase.update (shape.go:239-242)
+// unregisters / re-registers the shape that moved and leaves every other cell membership alone. The merged grid
+// is bit-identical to a full rebuild (same cell contents, ascending slot within a cell).
+struct StaticGrid {
+    uint32_t* cell = nullptr;      // [n_cells + 1] (whole scan tiles): offsets into the arrays below
+    uint32_t* entries = nullptr;   // static registrations, cell-major, ascending slot within a cell
+    float4* ent_box = nullptr;
+    uint2* ent_home = nullptr;
+    unsigned long long* ent_tags = nullptr;
+    uint32_t* cell_of = nullptr;   // per static registration: its cell
+    uint32_t cap = 0;              // capacity of the per-registration arrays
+};
+
+// Cell of every static registration (static build only).
+__global__ void __launch_bounds__(kGridBlock) k_static_cells(const uint32_t* __restrict__ scell, uint32_t n_cells,
+                                                             uint32_t* __restrict__ cell_of, uint32_t cap) {
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += gridDim.x * blockDim.x) {
+        const uint32_t s = scell[c], e = min(scell[c + 1], cap);
+        for (uint32_t k = s; k < e; k++) cell_of[k] = c;
+    }
+}
+
+// Copies the static registrations (entry word, float box, home record, tags) to the front of their cells in this
+// frame's grid. After k_scan<true>, d.cell[c + 1] = first entry of cell c + static count of c, so static entry ks of
+// cell c lands at ks + (d.cell[c + 1] - scell[c + 1]): fully coalesced reads, piecewise-contiguous writes.
+__global__ void __launch_bounds__(kGridBlock) k_static_place(DevView d, StaticGrid sg, uint32_t flags) {
+    const bool filters = !(flags & RSV_FRAME_NO_TAG_FILTERS);
+    const uint32_t Rs = min(d.static_entries, sg.cap);
+    for (uint32_t ks = blockIdx.x * blockDim.x + threadIdx.x; ks < Rs; ks += gridDim.x * blockDim.x) {
+        const uint32_t c = __ldg(sg.cell_of + ks);
+        const uint32_t dst = ks + (d.cell[c + 1] - __ldg(sg.cell + c + 1));
+        if (dst >= d.cap_entries) continue;
+        d.entries[dst] = __ldg(sg.entries + ks);
+        d.ent_box[dst] = __ldg(sg.ent_box + ks);
+        d.ent_home[dst] = __ldg(sg.ent_home + ks);
+        if (filters) d.ent_tags[dst] = __ldg(sg.ent_tags + ks);
+    }
+}
+
+// Cells that received dynamic registrations this frame (listed by k_scan<true>): order the cell by slot (its static
+// prefix is already in order) and refill the per-entry records of the whole cell, as k_cellsort + k_entboxes do for
+// every cell in a full rebuild.
+__global__ void __launch_bounds__(kGridBlock) k_cellfix(DevView d, uint32_t flags) {
+    const bool filters = !(flags & RSV_FRAME_NO_TAG_FILTERS);
+    const uint32_t nm = min(d.ctr->n_multi, d.cap_multi);
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nm; t += gridDim.x * blockDim.x) {
+        const uint32_t c = d.multi[t];
+        const uint32_t s = d.cell[c], e = d.cell[c + 1];
+        if (e <= s || e > d.cap_entries) continue;
+        uint32_t* a = d.entries + s;
+        const uint32_t n = e - s;
+        for (uint32_t i = 1; i < n; i++) {
+            const uint32_t key = a[i];
+            uint32_t j = i;
+            while (j > 0 && a[j - 1] > key) { a[j] = a[j - 1]; j--; }
+            a[j] = key;
+        }
+        for (uint32_t k = s; k < e; k++) {
+            const uint32_t ent = d.entries[k];
+            const uint32_t i = ent >> kEntShift;
+            d.ent_box[k] = float_box(load_box_nc(d.aabb + i));
+            if (filters) d.ent_tags[k] = __ldg(d.tags + i);
+            if ((ent & (kEntFirstRow | kEntFirstCol)) == (kEntFirstRow | kEntFirstCol)) {
+                int x0, y0, x1, y1;
+                clamp_rect(d, d.crect[i], x0, y0, x1, y1);
+                const uint32_t hc = cell_base(d, i) + (uint32_t)(y0 - d.row_lo) * (uint32_t)d.W + (uint32_t)x0;
+                d.ent_home[k] = make_uint2(hc, (uint32_t)(x1 - x0) | ((uint32_t)(y1 - y0) << 16));
+            }
         }
     }
 }

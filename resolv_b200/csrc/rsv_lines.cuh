@@ -283,12 +283,25 @@ struct RayWarpSmem {
     double rs[8][32];            // per ray: S.x S.y E.x E.y vu.x vu.y start.x start.y
     uint32_t qB[kRayQueue];      // item: shape slot
     uint32_t qMeta[kRayQueue];   // item: owner lane | generation rank << 5
-    uint32_t qN[kRayQueue];      // item: contacts (T1)
+    uint16_t qN[kRayQueue];      // item: contacts (T1); its class while the processing order is built
     uint32_t qPos[kRayQueue];    // item: index of its hit record within the ray's records | first contact within the ray's << 10
     uint32_t hbase[32], cbase[32];  // per ray: first hit record / first contact of the ray
     uint32_t segB[kRaySeg][32];  // the first items of each ray, kept from the count walk (saves the second walk)
     uint32_t segRank[kRaySeg][32];
+    uint16_t perm[kRayQueue];    // processing order of the round's items: binned by shape kind / edge count
+    uint32_t bin[16];            // bin cursors of that counting sort
 };
+
+// Processing class of a shape for the exact tests: 0 = circle, otherwise min(number of lines, kRayBins - 1). Lanes of a
+// warp step that work on items of one class run the same trip counts.
+constexpr int kRayBins = 10;
+__device__ __forceinline__ uint32_t ray_item_class(const DevView& d, uint32_t B) {
+    const uint32_t meta = __ldg(d.meta + B);
+    if (!(meta & RSV_META_POLYGON)) return 0u;
+    const int nv = (int)(meta >> RSV_META_NV_SHIFT);
+    const int nl = ((meta & RSV_META_CLOSED) && nv > 2) ? nv : max(nv - 1, 0);
+    return (uint32_t)min(nl + 1, kRayBins - 1);
+}
 
 __device__ __forceinline__ Ray ray_from_smem(const RayWarpSmem& sm, int o) {
     Ray r{};
@@ -421,11 +434,47 @@ __global__ void __launch_bounds__(kLinesBlock, 3) k_linetest(DevView d, LinesVie
                     rank++;
                 });
             }
+            if (lane < 16) sm.bin[lane] = 0u;
+            __syncwarp();
+            // ---- order of processing: a counting sort of the items by shape class (the queue itself stays in
+            //      generation order; mixed circles / 3..8-gons ran the tests at ~5 active threads per instruction)
+            for (uint32_t j = lane; j < n_items; j += 32) {
+                const uint32_t c = ray_item_class(d, sm.qB[j]);
+                sm.qN[j] = (uint16_t)c;
+                atomicAdd(&sm.bin[c], 1u);
+            }
+            __syncwarp();
+            {
+                const uint32_t v = lane < 16 ? sm.bin[lane] : 0u;
+                uint32_t inc = v;
+#pragma unroll
+                for (int o = 1; o < 16; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                __syncwarp();
+                if (lane < 16) sm.bin[lane] = inc - v;
+            }
+            __syncwarp();
+            for (uint32_t j = lane; j < n_items; j += 32) sm.perm[atomicAdd(&sm.bin[sm.qN[j]], 1u)] = (uint16_t)j;
             __syncwarp();
             // ---- T1: contacts per item
-            for (uint32_t j = lane; j < n_items; j += 32) {
+            for (uint32_t x = lane; x < n_items; x += 32) {
+                const uint32_t j = sm.perm[x];
                 const Ray r = ray_from_smem(sm, (int)(sm.qMeta[j] & 31u));
-                sm.qN[j] = ray_vs_shape<0>(d, r, sm.qB[j], nullptr, nullptr);
+                sm.qN[j] = (uint16_t)min(ray_vs_shape<0>(d, r, sm.qB[j], nullptr, nullptr), 0xffffu);
+            }
+            __syncwarp();
+            // the items that hit, compacted in place (still grouped by class): T2 runs with full warps
+            uint32_t n_hit_items = 0;
+            for (uint32_t x0 = 0; x0 < n_items; x0 += 32) {
+                const uint32_t x = x0 + lane;
+                const uint32_t j = x < n_items ? sm.perm[x] : 0u;
+                const bool hit = x < n_items && sm.qN[j] != 0u;
+                const uint32_t m = __ballot_sync(0xffffffffu, hit);
+                __syncwarp();
+                if (hit) sm.perm[n_hit_items + __popc(m & ((1u << lane) - 1u))] = (uint16_t)j;
+                n_hit_items += __popc(m);
             }
             __syncwarp();
             // ---- per ray: hits, contacts, positions of its items
@@ -464,8 +513,8 @@ __global__ void __launch_bounds__(kLinesBlock, 3) k_linetest(DevView d, LinesVie
             __syncwarp();
             // ---- T2: contacts and hit records
             if (room) {
-                for (uint32_t j = lane; j < n_items; j += 32) {
-                    if (!sm.qN[j]) continue;
+                for (uint32_t x = lane; x < n_hit_items; x += 32) {
+                    const uint32_t j = sm.perm[x];
                     const uint32_t m = sm.qMeta[j];
                     const int o = (int)(m & 31u);
                     const Ray r = ray_from_smem(sm, o);

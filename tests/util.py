@@ -68,11 +68,11 @@ def bits(a):
     return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
 
 
-def compare_frame(ds, ob, margin, check_candidates=True, check_rank=True):
+def compare_frame(ds, ob, margin, check_candidates=True, check_rank=True, extra_flags=0):
     """Runs one frame on both sides and asserts: candidate set (with generation rank) bit-exact, hit set bit-exact,
     contacts/MTV within 1e-9 absolute (the north-star tolerance) — and reports whether they are bit-identical."""
     from resolv_b200 import _abi
-    flags = _abi.FRAME_DOWNLOAD | (_abi.FRAME_ALL_CANDIDATES if check_candidates else 0)
+    flags = _abi.FRAME_DOWNLOAD | (_abi.FRAME_ALL_CANDIDATES if check_candidates else 0) | extra_flags
     c = ds.frame(margin, flags, grow=True)
     tot, cands, oh = ob.frame(margin)
     hits, con = ds.results()
