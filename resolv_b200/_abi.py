@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libresolv_b200.so")
+LIB_PATH = os.environ.get("RSV_LIB_PATH") or os.path.join(_HERE, "libresolv_b200.so")   # (RSV_LIB_PATH: tuning experiments)
 
 RSV_OK, RSV_ERR_BAD_ARG, RSV_ERR_OOM, RSV_ERR_CUDA, RSV_ERR_CAPACITY, RSV_ERR_NO_DEVICE = 0, -1, -2, -3, -4, -5
 (BUF_POS, BUF_LOCAL_AABB, BUF_RADIUS, BUF_TAGS, BUF_META, BUF_VERT_OFF, BUF_VERTS, BUF_QMASK, BUF_SPACE_IDX) = range(9)

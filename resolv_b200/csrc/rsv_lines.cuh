@@ -274,11 +274,32 @@ __device__ __forceinline__ void ray_candidates(const DevView& d, const Ray& ray,
 //       per ray: number of hits / contacts, positions of its items; one warp-aggregated allocation per round
 //   T2  per hit item: contacts + hit record at its final position          (balanced)
 // A single ray with more than kRayQueue items is handled by its lane alone (ray_serial), like the first version.
-constexpr int kRayQueue = 448;   // (qPos packs the hit index in 10 bits)
-static_assert(kRayQueue <= 1024, "qPos packing");
+// The kernel is instantiated per iterator, each with its own occupancy target and queue size (measured, 4 M rays of
+// 16-512 px over the 1 M-shape mixed world, profiles/README.md): the cell walks are chains of dependent loads, so
+// resident warps matter more than spill-free code. RECT visits ~11 candidates per ray and wants a long queue; DDA
+// queues ~1.3 gated items per ray and runs best at 8 blocks per SM with 64 registers.
+#ifndef RSV_LINES_MINB_RECT
+#define RSV_LINES_MINB_RECT 4
+#endif
+#ifndef RSV_RAY_QUEUE_RECT
+#define RSV_RAY_QUEUE_RECT 448
+#endif
+#ifndef RSV_LINES_MINB_DDA
+#define RSV_LINES_MINB_DDA 8
+#endif
+#ifndef RSV_RAY_QUEUE_DDA
+#define RSV_RAY_QUEUE_DDA 96
+#endif
+template <bool DDA>
+struct LinesCfg {
+    static constexpr int kMinBlocks = DDA ? RSV_LINES_MINB_DDA : RSV_LINES_MINB_RECT;
+    static constexpr int kQueue = DDA ? RSV_RAY_QUEUE_DDA : RSV_RAY_QUEUE_RECT;   // (qPos packs the hit index in 10 bits)
+    static_assert(kQueue <= 1024, "qPos packing");
+};
 constexpr int kLinesWarps = kLinesBlock / 32;
 constexpr int kRaySeg = 8;
 
+template <int kRayQueue>
 struct RayWarpSmem {
     double rs[8][32];            // per ray: S.x S.y E.x E.y vu.x vu.y start.x start.y
     uint32_t qB[kRayQueue];      // item: shape slot
@@ -303,7 +324,8 @@ __device__ __forceinline__ uint32_t ray_item_class(const DevView& d, uint32_t B)
     return (uint32_t)min(nl + 1, kRayBins - 1);
 }
 
-__device__ __forceinline__ Ray ray_from_smem(const RayWarpSmem& sm, int o) {
+template <int Q>
+__device__ __forceinline__ Ray ray_from_smem(const RayWarpSmem<Q>& sm, int o) {
     Ray r{};
     r.S = V2{sm.rs[0][o], sm.rs[1][o]}; r.E = V2{sm.rs[2][o], sm.rs[3][o]};
     r.vu = V2{sm.rs[4][o], sm.rs[5][o]}; r.start = V2{sm.rs[6][o], sm.rs[7][o]};
@@ -365,11 +387,14 @@ __device__ __noinline__ uint32_t ray_serial(const DevView d, const LinesView L, 
     return nh;
 }
 
-__global__ void __launch_bounds__(kLinesBlock, 3) k_linetest(DevView d, LinesView L, uint32_t flags) {
-    __shared__ RayWarpSmem s_warp[kLinesWarps];
+template <bool DDA>
+__global__ void __launch_bounds__(kLinesBlock, LinesCfg<DDA>::kMinBlocks) k_linetest(DevView d, LinesView L, uint32_t flags) {
+    constexpr int kRayQueue = LinesCfg<DDA>::kQueue;
+    __shared__ RayWarpSmem<kRayQueue> s_warp[kLinesWarps];
     const int lane = threadIdx.x & 31;
-    RayWarpSmem& sm = s_warp[threadIdx.x >> 5];
-    const bool dda = (flags & RSV_LINE_DDA) != 0, home_only = (flags & RSV_LINE_HOME_ONLY) != 0;
+    RayWarpSmem<kRayQueue>& sm = s_warp[threadIdx.x >> 5];
+    constexpr bool dda = DDA;
+    const bool home_only = (flags & RSV_LINE_HOME_ONLY) != 0;
     unsigned long long my_cands = 0, my_hits = 0;
     const uint32_t stride = gridDim.x * kLinesBlock;
     for (uint32_t base = blockIdx.x * kLinesBlock + (threadIdx.x & ~31u); base < L.n_rays; base += stride) {

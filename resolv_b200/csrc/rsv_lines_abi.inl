@@ -68,7 +68,8 @@ int32_t rsv_linetest_launch(rsv_space* s, uint32_t n_rays, uint32_t flags) {
     CU(s, cudaEventRecord(L.ev[0], st));
     if (n_rays) {
         int blocks = blocks_for(n_rays, kLinesBlock, s->sm_count * 16);
-        k_linetest<<<blocks, kLinesBlock, 0, st>>>(s->d, v, flags);
+        if (flags & RSV_LINE_DDA) k_linetest<true><<<blocks, kLinesBlock, 0, st>>>(s->d, v, flags);
+        else k_linetest<false><<<blocks, kLinesBlock, 0, st>>>(s->d, v, flags);
     }
     CU(s, cudaEventRecord(L.ev[1], st));
     CU(s, cudaGetLastError());

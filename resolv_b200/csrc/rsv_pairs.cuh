@@ -55,6 +55,7 @@ constexpr int kItemRound = RSV_ITEM_ROUND;   // items staged through shared memo
 constexpr int kCandWords = 60;    // super-round = kCandWords * 32 items = 12 rounds
 constexpr uint32_t kSuper = kCandWords * 32;
 static_assert(kSuper % kItemRound == 0, "super-rounds are whole rounds");
+static_assert(kItemRound % 32 == 0, "a round is whole warp steps (one candidate-bit word per step)");
 constexpr uint32_t kNoEntry = 0xffffffffu;
 
 // Number of set bits of the candidate words in the item range [lo, hi) (indices relative to the super-round).
