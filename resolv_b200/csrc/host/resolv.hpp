@@ -81,8 +81,8 @@ public:
     uint32_t ID() const { return id_; }
     Tags& GetTags() { return tags_; }
     Vector Position() const { return pos_; }
-    void SetPosition(double x, double y) { pos_ = {x, y}; update(); }   // shape.go:115-119
-    void Move(double x, double y) { pos_.X += x; pos_.Y += y; update(); }  // shape.go:98-102
+    void SetPosition(double x, double y) { pos_ = {x, y}; updatePosition(); }   // shape.go:115-119
+    void Move(double x, double y) { pos_.X += x; pos_.Y += y; updatePosition(); }  // shape.go:98-102
     void MoveVec(Vector v) { Move(v.X, v.Y); }
     Space* GetSpace() const { return space_; }
     virtual Bounds GetBounds() const = 0;
@@ -94,7 +94,8 @@ public:
 
 protected:
     friend class Space;
-    inline void update();   // shape.go:239-242: marks the staged row dirty
+    inline void update();          // shape.go:239-242: marks the staged row dirty (shape data changed)
+    inline void updatePosition();  // same, when only the position changed: 16 bytes to upload, registrations of others kept
     Vector pos_;
     Tags tags_ = 0;
     uint32_t id_ = 0;
@@ -238,6 +239,7 @@ public:
         if (shapes_.size() >= maxShapes_) throw std::runtime_error("resolv: Space capacity exceeded");
         s->space_ = this; s->id_ = nextId_++; s->slot_ = (uint32_t)shapes_.size();
         shapes_.push_back(s);
+        moved_.push_back(1); still_.push_back(0);
         writeRow(s, true);
         rsv_set_counts(h_, (uint32_t)shapes_.size(), nVerts_);
         stale_ = true; fullCommit_ = true;
@@ -256,14 +258,17 @@ public:
     }
     ShapeFilter FilterShapes() { ShapeFilter f; f.space = this; return f; }  // space.go:106-110
 
-    // One device frame for all shapes (additive API).
+    // One device frame for all shapes (additive API). Frames are incremental (RSV_FRAME_INCREMENTAL):
+    // shapes that stood still for kStillFrames Steps are flagged RSV_META_STATIC and keep their cell registrations on
+    // the device, like shapes whose update() never runs keep theirs in the reference (shape.go:239-242).
     void Step(int margin) {
-        commit();
+        prepare();
+        const uint32_t flags = RSV_FRAME_DOWNLOAD | RSV_FRAME_TESTER_TABLE | RSV_FRAME_NO_TAG_FILTERS | RSV_FRAME_INCREMENTAL;
         rsv_counts c{};
-        int32_t rc = rsv_frame(h_, margin, RSV_FRAME_DOWNLOAD | RSV_FRAME_TESTER_TABLE | RSV_FRAME_NO_TAG_FILTERS, &c);
+        int32_t rc = rsv_frame(h_, margin, flags, &c);
         for (int tries = 0; rc == RSV_ERR_CAPACITY && tries < 3; tries++) {
             rsv_reserve(h_, (uint32_t)(c.n_entries * 5 / 4 + 1024), (uint32_t)(c.n_gated * 5 / 4 + 1024), (uint32_t)(c.n_contacts * 5 / 4 + 1024));
-            rc = rsv_frame(h_, margin, RSV_FRAME_DOWNLOAD | RSV_FRAME_TESTER_TABLE | RSV_FRAME_NO_TAG_FILTERS, &c);
+            rc = rsv_frame(h_, margin, flags, &c);
         }
         if (rc != RSV_OK) throw std::runtime_error(std::string("resolv: ") + rsv_last_error(h_));
         first_.resize(shapes_.size()); count_.resize(shapes_.size());
@@ -271,6 +276,8 @@ public:
         rsv_results_view(h_, &res_);
         margin_ = margin; stale_ = false; counts_ = c;
     }
+    // (static registrations cached on the device, shapes re-registered per frame) — see rsv_static_info
+    std::pair<uint32_t, uint32_t> StaticInfo() { uint32_t a = 0, b = 0; rsv_static_info(h_, &a, &b); return {a, b}; }
     const rsv_counts& LastCounts() const { return counts_; }
     rsv_space* Handle() { return h_; }
 
@@ -278,7 +285,45 @@ private:
     friend class Shape;
     friend class ConvexPolygon;
     friend bool LineTest(const LineTestSettings&);
-    void markDirty(Shape* s) { writeRow(s, false); stale_ = true; }
+    static constexpr uint32_t kStillFrames = 2, kPromoteEvery = 4;
+    void markDirty(Shape* s) { writeRow(s, false); moved_[s->slot_] = 1; stale_ = true; }
+    void markMoved(Shape* s) {
+        const uint32_t i = s->slot_;
+        pos_[2 * i] = s->pos_.X; pos_[2 * i + 1] = s->pos_.Y;
+        moved_[i] = 1;
+        if (meta_[i] & RSV_META_STATIC) { meta_[i] &= ~RSV_META_STATIC; metaDirty_ = true; }   // demotion is immediate
+        posLo_ = std::min(posLo_, i); posHi_ = std::max(posHi_, i + 1);
+        stale_ = true;
+    }
+    // Static / dynamic classification + upload of what changed; runs before every device frame.
+    void prepare() {
+        const uint32_t n = (uint32_t)shapes_.size();
+        uint32_t pending = 0;
+        bool tagsDirty = false;
+        for (uint32_t i = 0; i < n; i++) {
+            if (moved_[i]) still_[i] = 0;
+            else if (still_[i] < 0xffffffffu) still_[i]++;
+            moved_[i] = 0;
+            if (still_[i] >= kStillFrames && !(meta_[i] & (RSV_META_STATIC | RSV_META_ABSENT))) pending++;
+            if (tags_[i] != shapes_[i]->tags_) { tags_[i] = shapes_[i]->tags_; tagsDirty = true; }   // Tags() hands out a mutable reference
+        }
+        // promotions rewrite META (which drops the device's static cache): batch them
+        if (pending && (metaDirty_ || fullCommit_ || frameNo_ % kPromoteEvery == 0)) {
+            for (uint32_t i = 0; i < n; i++)
+                if (still_[i] >= kStillFrames && !(meta_[i] & RSV_META_ABSENT)) meta_[i] |= RSV_META_STATIC;
+            metaDirty_ = true;
+        }
+        frameNo_++;
+        if (fullCommit_) {
+            rsv_commit(h_, (1u << RSV_BUF_COUNT) - 1, 0, n);
+        } else {
+            uint32_t mask = (metaDirty_ ? 1u << RSV_BUF_META : 0u) | (tagsDirty ? 1u << RSV_BUF_TAGS : 0u);
+            if (mask) rsv_commit(h_, mask | (posHi_ > posLo_ ? 1u << RSV_BUF_POS : 0u), 0, n);
+            else if (posHi_ > posLo_) rsv_commit(h_, 1u << RSV_BUF_POS, posLo_, posHi_);
+        }
+        fullCommit_ = false; metaDirty_ = false;
+        posLo_ = 0xffffffffu; posHi_ = 0;
+    }
     void writeRow(Shape* s, bool isNew) {
         uint32_t i = s->slot_;
         pos_[2 * i] = s->pos_.X; pos_[2 * i + 1] = s->pos_.Y;
@@ -300,12 +345,6 @@ private:
         }
         fullCommit_ = true;
     }
-    void commit() {
-        if (!fullCommit_) return;
-        for (auto* s : shapes_) tags_[s->slot_] = s->tags_;  // Tags() hands out a mutable reference
-        rsv_commit(h_, (1u << RSV_BUF_COUNT) - 1, 0, (uint32_t)shapes_.size());
-        fullCommit_ = false;
-    }
     void ensureFrame(int margin) { if (stale_ || margin != margin_) Step(margin); }
 
     rsv_space* h_ = nullptr;
@@ -315,14 +354,18 @@ private:
     uint64_t* tags_;
     uint32_t *meta_, *voff_;
     uint32_t nVerts_ = 0, nextId_ = 0, maxShapes_, maxVerts_;
-    bool stale_ = true, fullCommit_ = true;
+    bool stale_ = true, fullCommit_ = true, metaDirty_ = false;
     int margin_ = -1;
+    std::vector<uint8_t> moved_;     // update() ran since the last device frame
+    std::vector<uint32_t> still_;    // device frames since the shape last moved
+    uint32_t posLo_ = 0xffffffffu, posHi_ = 0, frameNo_ = 0;
     std::vector<uint32_t> first_, count_;
     rsv_results res_{};
     rsv_counts counts_{};
 };
 
 inline void Shape::update() { if (space_) space_->markDirty(this); }
+inline void Shape::updatePosition() { if (space_) space_->markMoved(this); }
 
 inline ShapeFilter Shape::SelectTouchingCells(int margin) {
     ShapeFilter f;
@@ -398,7 +441,7 @@ inline IntersectionSet Shape::Intersection(Shape& other) {
 inline bool LineTest(const LineTestSettings& st) {
     if (!st.TestAgainst || !st.TestAgainst->space) return false;
     Space& sp = *st.TestAgainst->space;
-    if (sp.stale_) { sp.commit(); rsv_counts c{}; rsv_frame(sp.h_, 1, RSV_FRAME_GRID_ONLY, &c); }
+    if (sp.stale_) { sp.prepare(); rsv_counts c{}; rsv_frame(sp.h_, 1, RSV_FRAME_GRID_ONLY | RSV_FRAME_INCREMENTAL, &c); }
     size_t n;
     double* seg = (double*)rsv_ray_staging(sp.h_, 0, &n);
     uint64_t* msk = (uint64_t*)rsv_ray_staging(sp.h_, 1, &n);

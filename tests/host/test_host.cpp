@@ -53,6 +53,8 @@ int main() {
         st.OnIntersect = [&](const IntersectionSet& set) { print_set("IC", k, set); return true; };
         ball->IntersectionTest(st);
     }
+    // (the walls never moved: the host layer flagged them static and the device kept their registrations)
+    { auto si = space->StaticInfo(); printf("SI %u %u\n", si.first, si.second); }
     // 3. LineTest against the whole Space
     {
         auto all = space->FilterShapes().ByTags(Platform);
@@ -92,5 +94,6 @@ int main() {
         st.OnIntersect = [&](const IntersectionSet& set) { print_set("RM", 0, set); return true; };
         printf("RMR %d\n", (int)player->IntersectionTest(st));
     }
+    { auto si = space->StaticInfo(); printf("SI %u %u\n", si.first, si.second); }
     return 0;
 }

@@ -118,3 +118,6 @@ def test_host_layer_transcript_equals_oracle(tmp_path):
     ora = _sets(hits, hits.a == player)
     dev = [(r[2], r[3], r[4]) for r in recs if r[0] == "RM"]
     _same(dev, ora, "RM")
+    # the frames above were incremental: shapes that stood still were flagged static by the host layer on its own
+    si = [r[1] for r in recs if r[0] == "SI"]
+    assert len(si) == 2 and si[0][0] > 0 and si[0][1] < n, si
