@@ -158,3 +158,45 @@ def test_incremental_frames_replay_as_a_graph_and_feed_linetest():
     finally:
         ds.close()
         full.close()
+
+
+def test_many_small_random_worlds_incremental_equals_full_and_oracle():
+    """Randomised sweep: random static subsets (0 .. 100 %), shapes off the grid, non-testers, batched Spaces, several
+    frames in which dynamic shapes move (sometimes across many cells) and static shapes are re-flagged."""
+    rs = np.random.default_rng(11)
+    hits = 0
+    for trial in range(30):
+        if trial % 5 == 4:
+            w = worlds.make_platformer_batch(int(rs.integers(1, 5)), seed=int(rs.integers(1, 1 << 30)), n_tiles=int(rs.integers(140, 300)),
+                                             n_bodies=int(rs.integers(1, 40)))
+        else:
+            n = int(rs.integers(2, 400))
+            size = int(rs.choice([64, 257, 600]))
+            cell = int(rs.choice([7, 16, 33]))
+            w = worlds.make_mixed(n, seed=int(rs.integers(1, 1 << 30)), space=size, cell=cell, filtered=bool(trial % 2))
+            w.pos = w.pos * 1.3 - 0.15 * size          # part of the shapes off-grid
+            w.tester[:] = rs.integers(0, 2, n) | (rs.random(n) < 0.5)
+            w.finalize()
+        static = rs.random(w.n) < rs.choice([0.0, 0.5, 0.9, 1.0])
+        margin = int(rs.integers(0, 4))
+        ds, full = space_for_world(w), space_for_world(w)
+        try:
+            ds.set_static(static)
+            for f in range(3):
+                if f:
+                    step = rs.normal(0.0, 1.0, (w.n, 2)) * float(rs.choice([2.0, 40.0]))
+                    w.pos[~static] += step[~static]
+                    if f == 2:                             # a few static shapes become dynamic and the other way round
+                        flip = rs.random(w.n) < 0.1
+                        static = static ^ flip
+                        ds.set_static(static)
+                    ds.set_positions(w.pos)
+                    full.set_positions(w.pos)
+                _assert_same(_snapshot(ds, margin, INC), _snapshot(full, margin, 0))
+            c, exact = compare_frame(ds, OracleBatch(w), margin, check_rank=True, extra_flags=INC)
+            assert exact
+            hits += c.n_hits
+        finally:
+            ds.close()
+            full.close()
+    assert hits > 200
