@@ -340,7 +340,7 @@ int32_t rsv_destroy(rsv_space* s) {
     }
     for (auto& g : s->graph) drop_graph(g);
     {
-        void* sv[] = {s->sg.cell, s->sg.entries, s->sg.ent_box, s->sg.ent_home, s->sg.ent_tags, s->sg.cell_of, d.dyn_list, d.n_dyn_dev};
+        void* sv[] = {s->sg.cell, s->sg.count, s->sg.entries, s->sg.ent_box, s->sg.ent_home, s->sg.ent_tags, s->sg.cell_of, d.dyn_list, d.n_dyn_dev};
         for (void* p : sv) if (p) cudaFree(p);
     }
     if (s->mailbox) cudaFree(s->mailbox);
@@ -480,7 +480,7 @@ static int32_t enqueue_frame(rsv_space* s, const DevView& d, int32_t margin, uin
     mark(RSV_K_SCAN);
     const int scan_blocks = (d.n_cells + 1 + kScanTile - 1) / kScanTile;
     if (inc) k_scan<true><<<scan_blocks, kScanBlock, 0, st>>>(d.cell, d.n_cells + 1, d.tile_state, &d.ctr->scan_ticket, d.multi,
-                                                              &d.ctr->n_multi, d.cap_multi, s->sg.cell);
+                                                              &d.ctr->n_multi, d.cap_multi, s->sg.count);
     else k_scan<false><<<scan_blocks, kScanBlock, 0, st>>>(d.cell, d.n_cells + 1, d.tile_state, &d.ctr->scan_ticket, d.multi,
                                                            &d.ctr->n_multi, d.cap_multi, nullptr);
     mark(RSV_K_SCATTER);
@@ -564,6 +564,8 @@ static int32_t build_static(rsv_space* s) {
     StaticGrid& sg = s->sg;
     const size_t cell_bytes = (size_t)s->n_tiles * kScanTile * 4;
     if (!sg.cell) CU(s, cudaMalloc(&sg.cell, cell_bytes));
+    if (!sg.count) CU(s, cudaMalloc(&sg.count, cell_bytes));
+    CU(s, cudaMemsetAsync(sg.count, 0, cell_bytes, st));
     if (!d.dyn_list) CU(s, cudaMalloc(&d.dyn_list, (size_t)s->cfg.max_shapes * 4));
     if (!d.n_dyn_dev) CU(s, cudaMalloc(&d.n_dyn_dev, 4));
     for (auto& g : s->graph) drop_graph(g);
@@ -604,7 +606,7 @@ static int32_t build_static(rsv_space* s) {
     if (items) k_scatter<<<blocks_for(items, kGridBlock, gcap), kGridBlock, 0, st>>>(v);
     k_cellsort<<<blocks_for(std::min<uint32_t>(d.n_cells, d.cap_multi), kGridBlock, gcap), kGridBlock, 0, st>>>(v);
     k_entboxes<<<gcap, kGridBlock, 0, st>>>(v, 0u);   // (tags always: later frames may or may not use filters)
-    k_static_cells<<<blocks_for(d.n_cells, kGridBlock, gcap), kGridBlock, 0, st>>>(sg.cell, d.n_cells, sg.cell_of, sg.cap);
+    k_static_cells<<<blocks_for(d.n_cells, kGridBlock, gcap), kGridBlock, 0, st>>>(sg.cell, d.n_cells, sg.cell_of, sg.count, sg.cap);
     CU(s, cudaGetLastError());
     CU(s, cudaStreamSynchronize(st));
     d.n_dyn = n_dyn;
