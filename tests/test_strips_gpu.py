@@ -83,6 +83,62 @@ def test_two_strips_equal_one_space(kind, transport):
         ref.close()
 
 
+def test_shapes_that_migrate_into_the_neighbour_strip_are_rehomed_by_the_exchange():
+    """"shapes that migrate across a strip boundary are re-homed in the same exchange". A shape is a tester
+    where its first cell row is home, whoever owns its slot: owned shapes that wander deep into the neighbour's strip
+    travel as halo records and run their IntersectionTest THERE (and only there); the union stays the single Space."""
+    import torch
+    n, size, world = 12000, 7200, 2
+    ranks = [strips.StripRank("cfg3", n, r, world, 0, size=size, cap_halo=8192) for r in range(world)]
+    ref_world = strips.concat_worlds([strips.tile_world("cfg3", n, t, size=size) for t in range(world)], size * world)
+    ref = space_for_world(ref_world)
+    rs = np.random.default_rng(3)
+    try:
+        movers = [rs.choice(n, 300, replace=False) + r * n for r in range(world)]        # global slots
+        ref_world.pos[movers[0], 1] += size * rs.uniform(0.6, 1.2, 300)                     # rank 0's shapes go deep into strip 1
+        ref_world.pos[movers[1], 1] -= size * rs.uniform(0.6, 1.2, 300)                     # and the other way round
+        ref.set_positions(ref_world.pos)
+        for r, sr in enumerate(ranks):
+            sr.ds.buf[_abi.BUF_POS][2 * n:4 * n] = ref_world.pos[r * n:(r + 1) * n].reshape(-1)
+            sr.ds.commit(1 << _abi.BUF_POS, n, 2 * n)
+        for sr in ranks:
+            sr.pack()
+        torch.cuda.synchronize()
+        ranks[1].recv_up.copy_(ranks[0].send_dn)
+        ranks[0].recv_dn.copy_(ranks[1].send_up)
+        torch.cuda.synchronize()
+        tables, P, testers = [], 0, 0
+        for sr in ranks:
+            sr.apply()
+            c = sr.ds.frame(1, sr.flags | _abi.FRAME_DOWNLOAD | _abi.FRAME_ALL_CANDIDATES, grow=True)
+            P += c.n_candidates
+            testers += c.n_testers
+            hits, con = sr.ds.results()
+            tables.append((sr.global_slot(hits["a"]), sr.global_slot(hits["b"]), (hits["count_rank"] >> 8).astype(np.int64),
+                           (hits["count_rank"] & 0x7f).astype(np.int64), hits["mtv"].copy()))
+        cr = ref.frame(1, _abi.FRAME_DOWNLOAD | _abi.FRAME_ALL_CANDIDATES, grow=True)
+        rh, _ = ref.results()
+        assert P == cr.n_candidates and testers == cr.n_testers == world * n
+        a = np.concatenate([t[0] for t in tables]); b = np.concatenate([t[1] for t in tables])
+        o, ro = np.lexsort((b, a)), np.lexsort((rh["b"], rh["a"]))
+        assert np.array_equal(a[o], rh["a"][ro]) and np.array_equal(b[o], rh["b"][ro]), "candidate sets differ"
+        assert np.array_equal(np.concatenate([t[2] for t in tables])[o], (rh["count_rank"][ro] >> 8)), "generation ranks differ"
+        assert np.array_equal(np.concatenate([t[3] for t in tables])[o], (rh["count_rank"][ro] & 0x7f))
+        assert np.array_equal(bits(np.concatenate([t[4] for t in tables])[o]), bits(rh["mtv"][ro]))
+        # every record of a migrated shape was produced by the rank it moved to
+        rows = np.floor((ref_world.pos[:, 1] + ref_world.local_aabb[:, 1]) / float(ref_world.cell_h))
+        H = ranks[0].plan.H
+        home_rank = (np.clip(rows, 0, H - 1) >= ranks[1].plan.home_lo).astype(np.int64)
+        assert (home_rank[movers[0]] == 1).sum() > 250 and (home_rank[movers[1]] == 0).sum() > 250
+        for r, t in enumerate(tables):
+            assert np.all(home_rank[t[0]] == r), "a tester was run away from its home strip"
+        assert sum(int(np.isin(t[0], np.concatenate(movers)).sum()) for t in tables) > 100
+    finally:
+        for sr in ranks:
+            sr.close()
+        ref.close()
+
+
 @pytest.mark.parametrize("dda", [False, True])
 def test_rays_across_two_strips(dda):
     """Every rank tests all rays against the shapes homed on it (RSV_LINE_HOME_ONLY); the union over ranks must be the
