@@ -88,15 +88,25 @@ struct Ray {
     bool homeOnly;  // RSV_LINE_HOME_ONLY
 };
 
-// Tests one shape against the cast line. PASS 0 counts contacts; PASS 1 writes them to out[0..n), sorts them and
-// fills the hit record. Returns the number of contacts.
+// Result of the count pass for one (ray, shape) item, 16 bits: for a polygon of at most kRayMaskEdges lines the set
+// of lines the cast line hits (bit i = line i), for a circle 0 / 1 / 3 (= 0, 1 or 2 points); otherwise
+// kRayEncCount | number of contacts. The write pass then evaluates only the lines that hit, so its cost no longer
+// depends on the polygon's size (items of different shapes diverged there, and most of a polygon's lines miss).
+constexpr int kRayMaskEdges = 15;
+constexpr uint32_t kRayEncCount = 0x8000u;
+__device__ __forceinline__ uint32_t ray_enc_contacts(uint32_t enc) {
+    return (enc & kRayEncCount) ? (enc & 0x7fffu) : (uint32_t)__popc(enc);
+}
+
+// Tests one shape against the cast line. PASS 0 counts contacts and returns the encoding above; PASS 1 is given that
+// encoding, writes the contacts to out[0..n), sorts them, fills the hit record and returns the number of contacts.
 template <int PASS>
 __device__ __forceinline__ uint32_t ray_vs_shape(const DevView& d, const Ray& ray, uint32_t B, rsv_contact* out,
-                                                 rsv_ray_hit* rec) {
+                                                 rsv_ray_hit* rec, uint32_t enc = kRayEncCount) {
     const uint32_t meta = __ldg(d.meta + B);
     const double2 pb2 = __ldg(d.pos + B);
     const V2 pb{pb2.x, pb2.y};
-    uint32_t n = 0;
+    uint32_t n = 0, mask = 0;
     V2 sum{0.0, 0.0};
     if (!(meta & RSV_META_POLYGON)) {
         const double rad = __ldg(d.radius + B);
@@ -109,11 +119,25 @@ __device__ __forceinline__ uint32_t ray_vs_shape(const DevView& d, const Ray& ra
             }
             n++;
         }
+        mask = k == 2 ? 3u : (k == 1 ? 1u : 0u);
     } else {
         const int nv = (int)(meta >> RSV_META_NV_SHIFT);
         const int nl = ((meta & RSV_META_CLOSED) && nv > 2) ? nv : max(nv - 1, 0);
         const double2* lv = d.verts + __ldg(d.vert_off + B);
-        if (nl > 0) {
+        if (PASS == 1 && !(enc & kRayEncCount)) {
+            // only the lines that hit (ascending line index == generation order, utils.go:313-324)
+            for (uint32_t m = enc; m; m &= m - 1) {
+                const int i = __ffs(m) - 1;
+                const double2 qs = __ldg(lv + i), qe = __ldg(lv + (i + 1 < nv ? i + 1 : 0));
+                const V2 s{dadd(qs.x, pb.x), dadd(qs.y, pb.y)}, e{dadd(qe.x, pb.x), dadd(qe.y, pb.y)};
+                V2 pt;
+                if (line_x_line(ray.start, ray.E, s, e, pt)) {
+                    store_contact(out + n, pt, edge_normal(s, e));
+                    sum = vadd(sum, pt);
+                    n++;
+                }
+            }
+        } else if (nl > 0) {
             double2 q = __ldg(lv);
             const V2 first{dadd(q.x, pb.x), dadd(q.y, pb.y)};
             V2 s = first;
@@ -129,11 +153,13 @@ __device__ __forceinline__ uint32_t ray_vs_shape(const DevView& d, const Ray& ra
                         store_contact(out + n, pt, edge_normal(s, e));
                         sum = vadd(sum, pt);
                     }
+                    if (i < kRayMaskEdges) mask |= 1u << i;
                     n++;
                 }
                 s = e;
             }
         }
+        if (nl > kRayMaskEdges) mask = kRayEncCount | min(n, 0x7fffu);
     }
     if (PASS == 1 && n) {
         // Center (utils.go:332-337), then sort by d2 to settings.Start (utils.go:340-342; n <= 12 -> insertion sort)
@@ -145,7 +171,7 @@ __device__ __forceinline__ uint32_t ray_vs_shape(const DevView& d, const Ray& ra
         rec->center_x = center.x; rec->center_y = center.y;
         rec->key = vdist2(p0, ray.start);
     }
-    return n;
+    return PASS == 0 ? mask : n;
 }
 
 __device__ __forceinline__ bool ray_filter(const DevView& d, const Ray& ray, uint32_t B) {
@@ -304,7 +330,7 @@ struct RayWarpSmem {
     double rs[8][32];            // per ray: S.x S.y E.x E.y vu.x vu.y start.x start.y
     uint32_t qB[kRayQueue];      // item: shape slot
     uint32_t qMeta[kRayQueue];   // item: owner lane | generation rank << 5
-    uint16_t qN[kRayQueue];      // item: contacts (T1); its class while the processing order is built
+    uint16_t qN[kRayQueue];      // item: hit lines / contacts (T1, ray_enc_contacts); its class while the processing order is built
     uint32_t qPos[kRayQueue];    // item: index of its hit record within the ray's records | first contact within the ray's << 10
     uint32_t hbase[32], cbase[32];  // per ray: first hit record / first contact of the ray
     uint32_t segB[kRaySeg][32];  // the first items of each ray, kept from the count walk (saves the second walk)
@@ -357,7 +383,7 @@ __device__ __noinline__ uint32_t ray_serial(const DevView d, const LinesView L, 
     ray_candidates(d, ray, dda, space, [&](uint32_t B, uint32_t k) {
         if (!ray_filter(d, ray, B)) return;
         if (dda && !ray_box_gate(ray, d.ent_box[k])) return;
-        const uint32_t n = ray_vs_shape<0>(d, ray, B, nullptr, nullptr);
+        const uint32_t n = ray_enc_contacts(ray_vs_shape<0>(d, ray, B, nullptr, nullptr));
         if (n) { nh++; nc += n; }
     });
     uint32_t bh = 0, bc = 0;
@@ -373,10 +399,12 @@ __device__ __noinline__ uint32_t ray_serial(const DevView d, const LinesView L, 
         uint32_t wh = 0, wc = 0, rank = 0;
         ray_candidates(d, ray, dda, space, [&](uint32_t B, uint32_t k) {
             if (!ray_filter(d, ray, B)) return;
-            if (!(dda && !ray_box_gate(ray, d.ent_box[k])) && ray_vs_shape<0>(d, ray, B, nullptr, nullptr)) {
+            uint32_t enc = 0;
+            if (!(dda && !ray_box_gate(ray, d.ent_box[k])) && (enc = ray_vs_shape<0>(d, ray, B, nullptr, nullptr)) != 0 &&
+                ray_enc_contacts(enc)) {
                 rsv_ray_hit rec;
                 rec.ray = i; rec.b = B; rec.first_contact = bc + wc; rec.pad = 0.0;
-                const uint32_t n = ray_vs_shape<1>(d, ray, B, L.contacts + bc + wc, &rec);
+                const uint32_t n = ray_vs_shape<1>(d, ray, B, L.contacts + bc + wc, &rec, enc);
                 rec.count_rank = (n & 0xffu) | (rank << 8);
                 L.hits[bh + wh] = rec;
                 wh++; wc += n;
@@ -487,7 +515,7 @@ __global__ void __launch_bounds__(kLinesBlock, LinesCfg<DDA>::kMinBlocks) k_line
             for (uint32_t x = lane; x < n_items; x += 32) {
                 const uint32_t j = sm.perm[x];
                 const Ray r = ray_from_smem(sm, (int)(sm.qMeta[j] & 31u));
-                sm.qN[j] = (uint16_t)min(ray_vs_shape<0>(d, r, sm.qB[j], nullptr, nullptr), 0xffffu);
+                sm.qN[j] = (uint16_t)ray_vs_shape<0>(d, r, sm.qB[j], nullptr, nullptr);   // hit-line mask / contact count (ray_enc_contacts)
             }
             __syncwarp();
             // the items that hit, compacted in place (still grouped by class): T2 runs with full warps
@@ -495,7 +523,7 @@ __global__ void __launch_bounds__(kLinesBlock, LinesCfg<DDA>::kMinBlocks) k_line
             for (uint32_t x0 = 0; x0 < n_items; x0 += 32) {
                 const uint32_t x = x0 + lane;
                 const uint32_t j = x < n_items ? sm.perm[x] : 0u;
-                const bool hit = x < n_items && sm.qN[j] != 0u;
+                const bool hit = x < n_items && ray_enc_contacts(sm.qN[j]) != 0u;
                 const uint32_t m = __ballot_sync(0xffffffffu, hit);
                 __syncwarp();
                 if (hit) sm.perm[n_hit_items + __popc(m & ((1u << lane) - 1u))] = (uint16_t)j;
@@ -506,7 +534,7 @@ __global__ void __launch_bounds__(kLinesBlock, LinesCfg<DDA>::kMinBlocks) k_line
             uint32_t nh = 0, nc = 0;
             if (mine) {
                 for (uint32_t j = off; j < off + cnt; j++) {
-                    const uint32_t n = sm.qN[j];
+                    const uint32_t n = ray_enc_contacts(sm.qN[j]);
                     sm.qPos[j] = nh | (nc << 10);   // nh < kRayQueue <= 1024, nc <= 255 * kRayQueue < 2^22
                     nh += n ? 1u : 0u; nc += n;
                 }
@@ -547,7 +575,7 @@ __global__ void __launch_bounds__(kLinesBlock, LinesCfg<DDA>::kMinBlocks) k_line
                     const uint32_t c0 = sm.cbase[o] + (qp >> 10);
                     rsv_ray_hit rec;
                     rec.ray = base + (uint32_t)o; rec.b = sm.qB[j]; rec.first_contact = c0; rec.pad = 0.0;
-                    const uint32_t n = ray_vs_shape<1>(d, r, rec.b, L.contacts + c0, &rec);
+                    const uint32_t n = ray_vs_shape<1>(d, r, rec.b, L.contacts + c0, &rec, sm.qN[j]);
                     rec.count_rank = (n & 0xffu) | ((m >> 5) << 8);
                     L.hits[sm.hbase[o] + (qp & 1023u)] = rec;
                 }
