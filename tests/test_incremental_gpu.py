@@ -56,6 +56,11 @@ def test_platformer_batch_tiles_static_bodies_dynamic():
             assert device_cells(ds, c.n_entries) == OracleBatch(w).cells()
         ob.set_positions(w.pos)                   # the moved oracle (history-dependent in-cell order): sets only
         compare_frame(ds, ob, w.margin, check_rank=False, extra_flags=INC)
+        # nothing moves any more: every shape static, no dynamic list at all
+        ds.set_static(np.ones(w.n, dtype=bool))
+        for _ in range(2):
+            _assert_same(_snapshot(ds, w.margin, INC), _snapshot(full, w.margin, 0))
+        assert ds.static_info()[1] == 0
     finally:
         ds.close()
         full.close()
