@@ -324,15 +324,31 @@ __global__ void __launch_bounds__(256) k_bin_scatter(DevView d) {
     const uint32_t n_rec = min(d.ctr->pair_cursor, d.cap_pairs);
     const int lane = threadIdx.x & 31;
     const uint32_t stride = gridDim.x * blockDim.x;
+    // A block first counts its records per bin and reserves its share of every bin with ONE global atomic per bin
+    // (a mixed world has ~10 bins: an atomic per warp step and bin on 10 hot words took 15 us for 170 k records),
+    // then places the records through shared-memory cursors.
+    __shared__ uint32_t s_cnt[kNarrowBins], s_cur[kNarrowBins];
+    if (threadIdx.x < kNarrowBins) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n_rec; base += stride) {
+        const uint32_t p = base + threadIdx.x;
+        const uint32_t bin = p < n_rec ? d.hits[p].first_contact : kNoBin;
+        const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+        if (bin != kNoBin && lane == __ffs(peers) - 1) atomicAdd(&s_cnt[bin], __popc(peers));
+    }
+    __syncthreads();
+    if (threadIdx.x < kNarrowBins)
+        s_cur[threadIdx.x] = s_off[threadIdx.x] + (s_cnt[threadIdx.x] ? atomicAdd(&d.ctr->kind_cursor[threadIdx.x], s_cnt[threadIdx.x]) : 0u);
+    __syncthreads();
     for (uint32_t base = blockIdx.x * blockDim.x; base < n_rec; base += stride) {
         const uint32_t p = base + threadIdx.x;
         const uint32_t bin = p < n_rec ? d.hits[p].first_contact : kNoBin;
         const uint32_t peers = __match_any_sync(0xffffffffu, bin);
         const int leader = __ffs(peers) - 1;
         uint32_t at = 0;
-        if (bin != kNoBin && lane == leader) at = atomicAdd(&d.ctr->kind_cursor[bin], __popc(peers));
+        if (bin != kNoBin && lane == leader) at = atomicAdd(&s_cur[bin], __popc(peers));
         at = __shfl_sync(0xffffffffu, at, leader);
-        if (bin != kNoBin) d.kind_queue[s_off[bin] + at + __popc(peers & ((1u << lane) - 1u))] = p;
+        if (bin != kNoBin) d.kind_queue[at + __popc(peers & ((1u << lane) - 1u))] = p;
         else if (p < n_rec) d.hits[p].first_contact = 0u;  // an empty set owns no contacts
     }
 }

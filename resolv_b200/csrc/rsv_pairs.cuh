@@ -51,6 +51,9 @@ constexpr int kPairsWarps = kPairsBlock / 32;
 #ifndef RSV_PAIRS_CHUNK
 #define RSV_PAIRS_CHUNK 256
 #endif
+#ifndef RSV_PAIRS_ONE_CHUNK_FACTOR
+#define RSV_PAIRS_ONE_CHUNK_FACTOR 2u
+#endif
 constexpr int kPairsChunk = RSV_PAIRS_CHUNK;  // entries per grabbed chunk
 constexpr int kPairStage = 96;    // staged records per warp batch
 constexpr int kRowGroup = 4;      // query-rect rows flattened together
@@ -410,7 +413,7 @@ __global__ void __launch_bounds__(kPairsBlock) k_pairs(DevView d, int margin, ui
     // second helping (config 4 per GPU: 298 entries per warp; 256-entry chunks left 17 % of the warps with two: 80 -> 71 us)
     const uint32_t n_warps = gridDim.x * kPairsWarps;
     const uint32_t per_warp = max(32u, ((R + n_warps - 1) / n_warps + 31u) & ~31u);
-    const uint32_t chunk_sz = per_warp <= 2u * (uint32_t)kPairsChunk ? per_warp : (uint32_t)kPairsChunk;
+    const uint32_t chunk_sz = per_warp <= RSV_PAIRS_ONE_CHUNK_FACTOR * (uint32_t)kPairsChunk ? per_warp : (uint32_t)kPairsChunk;
     const uint32_t n_chunks = (R + chunk_sz - 1) / chunk_sz;
     uint32_t qn = 0;
     for (;;) {

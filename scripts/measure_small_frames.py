@@ -10,7 +10,10 @@ out = {"lib": os.path.basename(_abi.LIB_PATH)}
 for name, w, fl in (("cfg4_512", worlds.make_platformer_batch(512), 0), ("cfg4_64", worlds.make_platformer_batch(64), 0),
                     ("bouncer", worlds.make_bouncer(294), _abi.FRAME_NO_TAG_FILTERS),
                     ("cfg2_100k", worlds.make_rects(100_000, space=20736), _abi.FRAME_NO_TAG_FILTERS),
+                    ("cfg2_300k", worlds.make_rects(300_000, space=35904), _abi.FRAME_NO_TAG_FILTERS),
+                    ("cfg2_400k", worlds.make_rects(400_000, space=41440), _abi.FRAME_NO_TAG_FILTERS),
                     ("cfg2_500k", worlds.make_rects(500_000, space=46336), _abi.FRAME_NO_TAG_FILTERS),
+                    ("cfg2_650k", worlds.make_rects(650_000, space=52832), _abi.FRAME_NO_TAG_FILTERS),
                     ("cfg2_1M", worlds.make_rects(1_000_000), _abi.FRAME_NO_TAG_FILTERS)):
     ds = space_for_world(w)
     for _ in range(6):
