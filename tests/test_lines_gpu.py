@@ -242,3 +242,62 @@ def test_platformer_probes_on_a_batch_of_spaces():
             assert n_dev > 0
     finally:
         ds.close()
+
+
+@pytest.mark.parametrize("dda", [False, True])
+def test_rays_against_large_polygons_polylines_and_lines(dda):
+    """Shapes on both sides of the hit-line mask of the count pass (rsv_lines.cuh: polygons of up to 15 lines carry a
+    mask, larger ones a count): 3..40-gons, open polylines of 2..20 points, two-point lines, circles — and rays long
+    enough to cut several lines of one shape."""
+    rs = np.random.default_rng(23)
+    rows = []
+    for i in range(500):
+        x, y = rs.uniform(0, 600), rs.uniform(0, 600)
+        k = i % 4
+        if k == 0:
+            n = int(rs.integers(3, 41))
+            ang = np.sort(rs.uniform(0, 2 * np.pi, n))
+            r = rs.uniform(8, 40)
+            rows.append(dict(kind=1, pos=(x, y), radius=0.0, verts=np.stack([np.cos(ang) * r, np.sin(ang) * r], -1), tags=1))
+        elif k == 1:
+            n = int(rs.integers(2, 21))
+            pts = np.cumsum(rs.uniform(-12, 12, (n, 2)), 0)
+            rows.append(dict(kind=1, pos=(x, y), radius=0.0, closed=0, verts=pts - pts.mean(0), tags=2))
+        elif k == 2:
+            d = rs.uniform(-30, 30, 2)
+            rows.append(dict(kind=1, pos=(x, y), radius=0.0, verts=np.array([-d, d]), tags=1))
+        else:
+            rows.append(dict(kind=0, pos=(x, y), radius=rs.uniform(3, 25), tags=2))
+    w = worlds._from_rows(rows, (600, 600), (32, 32), "raymix").finalize()
+    ds = space_for_world(w, max_rays=4000)
+    try:
+        ds.frame(1, _abi.FRAME_GRID_ONLY)
+        sp = OracleBatch(w).spaces[0]
+        rays = worlds.make_rays(4000, 31, w.space_w, w.space_h, min_len=8.0, max_len=300.0)
+        c = ds.linetest(rays, flags=_abi.FRAME_DOWNLOAD | (_abi.LINE_DDA if dda else 0))
+        hits, con, first, count = ds.ray_results()
+        fc, oh = sp.linetest(rays, mode="rect" if not dda else "all")
+        h, n, dc = _canon_dev(hits, con)
+        o, oc = _canon_ora(oh)
+        if not dda:
+            assert c.n_candidates == fc.candidates and c.n_hits == fc.hits and c.n_contacts == fc.contacts
+            sel = np.arange(len(o))
+        else:
+            # every reported set is one of the brute-force sets (missing ones are phantoms of the +1 fudge: the DDA test above)
+            key_o = oh.a[o].astype(np.int64) * w.n + oh.b[o].astype(np.int64)
+            key_d = h["ray"].astype(np.int64) * w.n + h["b"].astype(np.int64)
+            sel = np.searchsorted(key_o, key_d)
+            assert np.all(sel < len(key_o)) and np.array_equal(key_o[sel], key_d)
+            assert len(key_d) > 0.9 * len(key_o)
+        assert np.array_equal(h["ray"], oh.a[o][sel]) and np.array_equal(h["b"], oh.b[o][sel])
+        assert np.array_equal(n, oh.count[o][sel])
+        starts = (np.cumsum(oh.count[o]) - oh.count[o])[sel]
+        oc_sel = np.concatenate([oc[s:s + k] for s, k in zip(starts, oh.count[o][sel])]) if len(sel) else np.zeros((0, 4))
+        for name, dev, ora in (("contacts", dc, oc_sel), ("mtv", h["mtv"], oh.mtv[o][sel]), ("center", h["center"], oh.center[o][sel]),
+                               ("key", h["key"], oh.dist[o][sel])):
+            assert np.array_equal(bits(dev), bits(ora)), name
+        assert int((n > 2).sum()) > 20, "no ray cut more than two lines of one shape"
+        big = w.nv[h["b"]] > 16
+        assert int(big.sum()) > 50, "no hits on polygons beyond the mask width"
+    finally:
+        ds.close()
