@@ -190,7 +190,48 @@ def cases():
         pos, rays = add(w, frames, n_rays, seed)
         w.pos = p0
         out.append((w, pos, rays))
+    # config 4: one platformer Space (tiles + bodies, SelectTouchingCells(4).ByTags(SolidWall)) with the bodies' probe rays
+    w = worlds.make_platformer_batch(1)
+    w.name = "cfg4_platformer_1"
+    p0 = w.pos.copy()
+    pos, _ = add(w, 3, 0, 0)
+    w.pos = p0
+    out.append((w, pos, worlds.make_platformer_probes(w)[0]))
+    # shape zoo: 3..40-gons, open polylines, two-point lines, circles, part of them off the grid; long rays
+    out.append(_zoo())
     return out
+
+
+def _zoo():
+    from resolv_b200 import worlds
+    rs = np.random.default_rng(23)
+    rows = []
+    for i in range(240):
+        x, y = rs.uniform(-40, 640), rs.uniform(-40, 640)
+        k = i % 4
+        if k == 0:
+            n = int(rs.integers(3, 41))
+            ang = np.sort(rs.uniform(0, 2 * np.pi, n))
+            r = rs.uniform(8, 40)
+            rows.append(dict(kind=1, pos=(x, y), radius=0.0, verts=np.stack([np.cos(ang) * r, np.sin(ang) * r], -1), tags=1))
+        elif k == 1:
+            n = int(rs.integers(2, 21))
+            pts = np.cumsum(rs.uniform(-12, 12, (n, 2)), 0)
+            rows.append(dict(kind=1, pos=(x, y), radius=0.0, closed=0, verts=pts - pts.mean(0), tags=2))
+        elif k == 2:
+            d = rs.uniform(-30, 30, 2)
+            rows.append(dict(kind=1, pos=(x, y), radius=0.0, verts=np.array([-d, d]), tags=1))
+        else:
+            rows.append(dict(kind=0, pos=(x, y), radius=rs.uniform(3, 25), tags=2))
+    w = worlds._from_rows(rows, (600, 600), (32, 32), "zoo_240").finalize()
+    w.vel = rs.uniform(-6, 6, (w.n, 2))
+    p0 = w.pos.copy()
+    pos = []
+    for f in range(1, 3):
+        worlds.advance(w, f)
+        pos.append(w.pos.copy())
+    w.pos = p0
+    return w, pos, worlds.make_rays(48, 105, w.space_w, w.space_h, 8.0, 300.0)
 
 
 def export():
