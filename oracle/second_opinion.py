@@ -1,0 +1,488 @@
+"""A SECOND, independent restatement of resolv's narrowphase and LineTest — in plain Python floats.
+
+TEST INFRASTRUCTURE ONLY (same rule as the rest of oracle/): nothing under resolv_b200/ may import this.
+
+Why it exists: the reference (resolv v0.8.0, Go) cannot run in this image and ships no golden vectors, so the C++ oracle
+(oracle/resolv_oracle.cpp) is "parity unpinned". This file is a separate line-by-line transcription of the same Go
+sources, made without looking at the C++ oracle, in a different language with different data structures (tuples and
+lists, no SoA, no scratch reuse). Python floats are IEEE-754 doubles, `*` and `+` are never fused, `math.sqrt` is
+correctly rounded — the same arithmetic Go/amd64 does. tests/test_oracle_second_opinion.py demands that the two
+restatements agree BIT FOR BIT on seeded random shapes; a transcription slip in either one shows up as a mismatch.
+It narrows "unpinned" to "two independent readings of the source agree"; only parity/go run against real resolv pins it.
+
+Go stdlib behaviour restated here: math.Min (NaN / signed zero), sort.Slice for n <= 12 (insertion sort, stable),
+math.Pow(x, 2) == x*x for finite non-overflowing x.
+"""
+import math
+
+MAXF = 1.7976931348623157e308  # math.MaxFloat64
+
+
+# ---------------------------------------------------------------- vector.go
+def v_sub(a, b):                      # vector.go:72-77
+    return (a[0] - b[0], a[1] - b[1])
+
+
+def v_add(a, b):                      # vector.go:54-58
+    return (a[0] + b[0], a[1] + b[1])
+
+
+def v_scale(a, s):                    # vector.go:272-276
+    return (a[0] * s, a[1] * s)
+
+
+def v_invert(a):                      # vector.go:104-108
+    return (-a[0], -a[1])
+
+
+def v_mag(a):                         # vector.go:111-113
+    return math.sqrt(a[0] * a[0] + a[1] * a[1])
+
+
+def v_dot(a, b):                      # vector.go:286-288
+    return a[0] * b[0] + a[1] * b[1]
+
+
+def v_dist2(a, b):                    # vector.go:152-156
+    x = a[0] - b[0]
+    y = a[1] - b[1]
+    return x * x + y * y
+
+
+def v_unit(a):                        # vector.go:167-175
+    l = v_mag(a)
+    if l < 1e-8 or l == 1:
+        return a
+    return (a[0] / l, a[1] / l)
+
+
+def go_min(x, y):                     # Go math.Min: NaN wins, Min(-0, +0) = -0
+    if math.isinf(x) and x < 0 or math.isinf(y) and y < 0:
+        return -math.inf
+    if x != x or y != y:
+        return math.nan
+    if x == 0 and x == y:
+        return x if math.copysign(1.0, x) < 0 else y
+    return x if x < y else y
+
+
+def go_max(x, y):                     # Go math.Max
+    if math.isinf(x) and x > 0 or math.isinf(y) and y > 0:
+        return math.inf
+    if x != x or y != y:
+        return math.nan
+    if x == 0 and x == y:
+        return y if math.copysign(1.0, x) < 0 else x
+    return x if x > y else y
+
+
+def go_sort_small(items, less):       # sort.Slice, n <= 12: insertionSortLessFunc
+    assert len(items) <= 12, "pdqsort territory: compare as a multiset instead"
+    for i in range(1, len(items)):
+        j = i
+        while j > 0 and less(items[j], items[j - 1]):
+            items[j], items[j - 1] = items[j - 1], items[j]
+            j -= 1
+
+
+# ---------------------------------------------------------------- utils.go: Bounds
+def b_move(b, x, y):                  # utils.go:137-143
+    return ((b[0][0] + x, b[0][1] + y), (b[1][0] + x, b[1][1] + y))
+
+
+def b_center(b):                      # utils.go:100-102
+    return v_add(b[0], v_scale(v_sub(b[1], b[0]), 0.5))
+
+
+def b_is_intersecting(b, o):          # utils.go:150-175 (IsEmpty subtracts Min.X from Max.Y: kept)
+    if o[1][0] < b[0][0] or o[0][0] > b[1][0] or o[1][1] < b[0][1] or o[0][1] > b[1][1]:
+        mn, mx = (0.0, 0.0), (0.0, 0.0)
+    else:
+        mx = (go_min(o[1][0], b[1][0]), go_min(o[1][1], b[1][1]))
+        mn = (go_max(o[0][0], b[0][0]), go_max(o[0][1], b[0][1]))
+    empty = (mx[0] - mn[0] == 0) and (mx[1] - mn[0] == 0)
+    return not empty
+
+
+def overlap(pa, pb):                  # utils.go:75-77
+    return go_min(pa[1] - pb[0], pb[1] - pa[0])
+
+
+# ---------------------------------------------------------------- shapes
+class Circle:                         # circle.go:4-17
+    def __init__(self, x, y, r):
+        self.pos = (float(x), float(y))
+        self.r = float(r)
+
+    def bounds(self):                 # circle.go:32-38
+        return ((self.pos[0] - self.r, self.pos[1] - self.r), (self.pos[0] + self.r, self.pos[1] + self.r))
+
+    def project(self, axis):          # circle.go:40-53
+        axis = v_unit(axis)
+        pc = v_dot(axis, self.pos)
+        pr = v_mag(axis) * self.r
+        lo = pc - pr
+        hi = pc + pr
+        if lo > hi:
+            lo, hi = hi, lo
+        return (lo, hi)
+
+
+class Polygon:                        # convexPolygon.go:12-46, scale 1, rotation 0
+    def __init__(self, x, y, pts, closed=True):
+        self.pos = (float(x), float(y))
+        self.points = [(float(pts[i]), float(pts[i + 1])) for i in range(0, len(pts), 2)]
+        self.closed = closed
+        self.update_bounds()
+
+    def transformed(self):            # convexPolygon.go:144-154 (scale (1,1): x*1 is exact; rotation 0 skipped)
+        return [(p[0] * 1.0 + self.pos[0], p[1] * 1.0 + self.pos[1]) for p in self.points]
+
+    def update_bounds(self):          # convexPolygon.go:163-197
+        t = self.transformed()
+        tlx, tly = t[0]
+        brx, bry = t[0]
+        for p in t:
+            if p[0] < tlx:
+                tlx = p[0]
+            elif p[0] > brx:
+                brx = p[0]
+            if p[1] < tly:
+                tly = p[1]
+            elif p[1] > bry:
+                bry = p[1]
+        self.local = b_move(((tlx, tly), (brx, bry)), -self.pos[0], -self.pos[1])
+
+    def bounds(self):                 # convexPolygon.go:158-161
+        return b_move(self.local, self.pos[0], self.pos[1])
+
+    def center(self):                 # convexPolygon.go:200-214
+        return b_center(self.bounds())
+
+    def lines(self):                  # convexPolygon.go:117-141
+        v = self.transformed()
+        out = []
+        for i in range(len(v)):
+            start, end = v[i], v[0]
+            if i < len(v) - 1:
+                end = v[i + 1]
+            elif (not self.closed) or len(self.points) <= 2:
+                break
+            out.append((start, end))
+        return out
+
+    def project(self, axis):          # convexPolygon.go:217-231
+        axis = v_unit(axis)
+        v = self.transformed()
+        lo = v_dot(axis, v[0])
+        hi = lo
+        for i in range(1, len(v)):
+            p = v_dot(axis, v[i])
+            if p < lo:
+                lo = p
+            elif p > hi:
+                hi = p
+        return (lo, hi)
+
+    def sat_axes(self):               # convexPolygon.go:234-242
+        return [line_normal(l) for l in self.lines()]
+
+
+def rectangle(x, y, w, h):            # convexPolygon.go:616-632
+    hw = w / 2
+    hh = h / 2
+    return Polygon(x, y, [-hw, -hh, hw, -hh, hw, hh, -hw, hh])
+
+
+def line_shape(x1, y1, x2, y2):       # convexPolygon.go:671-684
+    cx = x1 + ((x2 - x1) / 2)
+    cy = y1 + ((y2 - y1) / 2)
+    return Polygon(cx, cy, [cx - x1, cy - y1, cx - x2, cy - y2])
+
+
+# ---------------------------------------------------------------- collidingLine
+def line_vector(l):                   # convexPolygon.go:709-711
+    return v_unit(v_sub(l[1], l[0]))
+
+
+def line_normal(l):                   # convexPolygon.go:704-707
+    v = line_vector(l)
+    return v_unit((v[1], -v[0]))
+
+
+def line_x_line(l, o):                # convexPolygon.go:714-744
+    (sx, sy), (ex, ey) = l
+    (osx, osy), (oex, oey) = o
+    det = (ex - sx) * (oey - osy) - (oex - osx) * (ey - sy)
+    if det != 0:
+        lam = (((sy - osy) * (oex - osx)) - ((sx - osx) * (oey - osy)) + 1) / det
+        gam = (((sy - osy) * (ex - sx)) - ((sx - osx) * (ey - sy)) + 1) / det
+        if (0 < lam and lam < 1) and (0 < gam and gam < 1):
+            dx = ex - sx
+            dy = ey - sy
+            return (sx + (lam * dx), sy + (lam * dy))
+    return None
+
+
+def line_x_circle(l, c):              # convexPolygon.go:747-789
+    pts = []
+    ls = v_sub(l[0], c.pos)
+    le = v_sub(l[1], c.pos)
+    d = v_sub(le, ls)
+    a = d[0] * d[0] + d[1] * d[1]
+    b = 2 * ((d[0] * ls[0]) + (d[1] * ls[1]))
+    cc = (ls[0] * ls[0]) + (ls[1] * ls[1]) - (c.r * c.r)
+    det = b * b - (4 * a * cc)
+    if det < 0:
+        pass
+    elif det == 0:
+        t = _div(-b, 2 * a)
+        if t >= 0 and t <= 1:
+            pts.append((l[0][0] + t * d[0], l[0][1] + t * d[1]))
+    else:
+        t = _div(-b + math.sqrt(det), 2 * a)
+        if t >= 0 and t <= 1:
+            pts.append((l[0][0] + t * d[0], l[0][1] + t * d[1]))
+        t = _div(-b - math.sqrt(det), 2 * a)
+        if t >= 0 and t <= 1:
+            pts.append((l[0][0] + t * d[0], l[0][1] + t * d[1]))
+    return pts
+
+
+def _div(x, y):                       # Go float division: x/0 is ±Inf or NaN, never a panic
+    if y == 0:
+        if x == 0 or x != x:
+            return math.nan
+        return math.copysign(math.inf, x) * math.copysign(1.0, y)
+    return x / y
+
+
+# ---------------------------------------------------------------- calculateMTV (convexPolygon.go:418-514)
+def calculate_mtv(cp, other):
+    smallest = (MAXF, 0.0)
+    if isinstance(other, Polygon):
+        for axes in (cp.sat_axes(), other.sat_axes()):
+            for axis in axes:
+                ov = overlap(cp.project(axis), other.project(axis))
+                if ov <= 0:
+                    return None
+                if v_mag(smallest) > ov:
+                    smallest = v_scale(axis, ov)
+        if v_dot(v_sub(cp.center(), other.center()), smallest) < 0:
+            smallest = v_invert(smallest)
+    else:
+        verts = list(cp.transformed())
+        center = other.pos
+        go_sort_small(verts, lambda p, q: v_mag(v_sub(p, center)) < v_mag(v_sub(q, center)))
+        axis = (center[0] - verts[0][0], center[1] - verts[0][1])
+        ov = overlap(cp.project(axis), other.project(axis))
+        if ov <= 0:
+            return None
+        smallest = v_scale(v_unit(axis), ov)
+        for axis in cp.sat_axes():
+            ov = overlap(cp.project(axis), other.project(axis))
+            if ov <= 0:
+                return None
+            if v_mag(smallest) > ov:
+                smallest = v_scale(axis, ov)
+        if v_dot(v_sub(cp.center(), other.pos), smallest) < 0:
+            smallest = v_invert(smallest)
+    delta = smallest
+    if v_dot(v_sub(other.pos, cp.pos), delta) > 0:
+        delta = v_invert(delta)
+    return delta
+
+
+# ---------------------------------------------------------------- the four pair tests (shape.go:318-479)
+def intersection(a, b):
+    """a.Intersection(b) -> (mtv, [(point, normal), ...], sorted: bool). `sorted` is False when the contact order could
+    not be restated (more than 12 contacts: pdqsort) — compare those as multisets."""
+    mtv = (0.0, 0.0)
+    cons = []
+    ordered = True
+    if isinstance(a, Circle) and isinstance(b, Circle):          # shape.go:399-436
+        if not b_is_intersecting(a.bounds(), b.bounds()):
+            return mtv, cons, ordered
+        dx = b.pos[0] - a.pos[0]
+        dy = b.pos[1] - a.pos[1]
+        d = math.sqrt(dx * dx + dy * dy)
+        if d > a.r + b.r or d < abs(a.r - b.r) or d == 0:
+            return mtv, cons, ordered
+        aa = (a.r * a.r - b.r * b.r + d * d) / (2 * d)
+        h = math.sqrt(a.r * a.r - aa * aa) if a.r * a.r - aa * aa >= 0 else math.nan
+        x2 = a.pos[0] + aa * (b.pos[0] - a.pos[0]) / d
+        y2 = a.pos[1] + aa * (b.pos[1] - a.pos[1]) / d
+        pts = [(x2 + h * (b.pos[1] - a.pos[1]) / d, y2 - h * (b.pos[0] - a.pos[0]) / d),
+               (x2 - h * (b.pos[1] - a.pos[1]) / d, y2 + h * (b.pos[0] - a.pos[0]) / d)]
+        cons = [(p, v_unit(v_sub(p, a.pos))) for p in pts]
+        m = (a.pos[0] - b.pos[0], a.pos[1] - b.pos[1])
+        dist = v_mag(m)
+        mtv = v_scale(v_unit(m), a.r + b.r - dist)
+        return mtv, cons, ordered
+    if isinstance(a, Circle):                                    # shape.go:318-354 circle -> convex
+        if not b_is_intersecting(b.bounds(), a.bounds()):
+            return mtv, cons, ordered
+        for l in b.lines():
+            for p in line_x_circle(l, a):
+                cons.append((p, line_normal(l)))
+        if cons:
+            m = calculate_mtv(b, a)
+            if m is not None:
+                mtv = v_invert(m)
+        return mtv, cons, ordered
+    if isinstance(b, Circle):                                    # shape.go:356-397 convex -> circle
+        if not b_is_intersecting(a.bounds(), b.bounds()):
+            return mtv, cons, ordered
+        for l in a.lines():
+            for p in line_x_circle(l, b):
+                cons.append((p, v_unit(v_sub(p, b.pos))))
+        if cons:
+            if len(cons) <= 12:
+                go_sort_small(cons, lambda s, t: v_dist2(s[0], b.pos) < v_dist2(t[0], b.pos))
+            else:
+                ordered = False
+            m = calculate_mtv(a, b)
+            if m is not None:
+                mtv = m
+        return mtv, cons, ordered
+    if not b_is_intersecting(a.bounds(), b.bounds()):            # shape.go:438-479 convex -> convex
+        return mtv, cons, ordered
+    for ol in b.lines():
+        for l in a.lines():
+            p = line_x_line(l, ol)
+            if p is not None:
+                cons.append((p, line_normal(ol)))
+    if cons:
+        center = a.center()
+        if len(cons) <= 12:
+            go_sort_small(cons, lambda s, t: v_dist2(s[0], center) < v_dist2(t[0], center))
+        else:
+            ordered = False
+        m = calculate_mtv(a, b)
+        if m is not None:
+            mtv = m
+    return mtv, cons, ordered
+
+
+# ---------------------------------------------------------------- LineTest against ONE shape (utils.go:276-370)
+def linetest_one(start, end, shape):
+    """The IntersectionSet LineTest builds for `shape`, or None: (mtv, center, [(point, normal)...] sorted, sort key)."""
+    vu = v_unit(v_sub(end, start))
+    st = v_sub(start, v_scale(vu, 0.01))
+    line = (st, end)
+    cons = []
+    if isinstance(shape, Circle):
+        for p in line_x_circle(line, shape):
+            cons.append((p, v_unit(v_sub(p, shape.pos))))
+    else:
+        for ol in shape.lines():
+            p = line_x_line(line, ol)
+            if p is not None:
+                cons.append((p, line_normal(ol)))
+    if not cons:
+        return None
+    c = (0.0, 0.0)
+    for p, _ in cons:
+        c = v_add(c, p)
+    c = (c[0] / float(len(cons)), c[1] / float(len(cons)))
+    go_sort_small(cons, lambda s, t: v_dist2(s[0], start) < v_dist2(t[0], start))
+    mtv = v_sub(v_sub(cons[0][0], start), v_scale(vu, 0.01))
+    key = v_dist2(cons[0][0], st)
+    return mtv, c, cons, key
+
+
+# ---------------------------------------------------------------- broadphase: Space, Cell, CellSelection, IntersectionTest
+class Space:
+    """space.go:7-46 with cell.go's per-cell lists kept as a dict of Python lists (append / swap-remove), so the
+    candidate ORDER after motion — which depends on the register/unregister history — is reproduced too."""
+
+    def __init__(self, space_w, space_h, cell_w, cell_h):          # space.go:16-30
+        self.cw, self.ch = cell_w, cell_h
+        self.w = int(math.ceil(float(space_w) / float(cell_w)))
+        self.h = int(math.ceil(float(space_h) / float(cell_h)))
+        self.cells = {}                                             # (cx, cy) -> [shape, ...]; only in-grid keys
+        self.shapes = []
+
+    def to_cell_space(self, b):                                     # utils.go:85-95
+        return (int(math.floor(b[0][0] / float(self.cw))), int(math.floor(b[0][1] / float(self.ch))),
+                int(math.floor(b[1][0] / float(self.cw))), int(math.floor(b[1][1] / float(self.ch))))
+
+    def cell(self, cx, cy):                                         # space.go:134-142 (nil outside the grid)
+        if 0 <= cy < self.h and 0 <= cx < self.w:
+            return self.cells.setdefault((cx, cy), [])
+        return None
+
+    def add(self, shape, tags=0):                                   # space.go:33-46
+        shape.tags = tags
+        shape.touching = []
+        shape.id = len(self.shapes)
+        self.update(shape)
+        self.shapes.append(shape)
+        return shape.id
+
+    def update(self, shape):                                        # shape.go:183-214, 239-242
+        for c in shape.touching:                                    # cell.go:26-38: swap-remove
+            for i, o in enumerate(c):
+                if o is shape:
+                    c[i] = c[-1]
+                    c.pop()
+                    break
+        shape.touching = []
+        cx, cy, ex, ey = self.to_cell_space(shape.bounds())
+        for y in range(cy, ey + 1):
+            for x in range(cx, ex + 1):
+                c = self.cell(x, y)
+                if c is not None:
+                    if not any(o is shape for o in c):              # cell.go:19-23
+                        c.append(shape)
+                    shape.touching.append(c)
+
+    def set_position(self, shape, x, y):                            # shape.go:115-119
+        shape.pos = (float(x), float(y))
+        self.update(shape)
+
+    def candidates(self, shape, margin, use_any=False, any_mask=0, none_mask=0):
+        """SelectTouchingCells(margin).FilterShapes()[.ByTags(any)][.NotByTags(none)] walked as IntersectionTest walks
+        it (shape.go:220-237, cell.go:86-121, shapefilter.go:26-61, shape.go:277-288): [(other, distance²)] in
+        generation order."""
+        cx, cy, ex, ey = self.to_cell_space(shape.bounds())
+        cx -= margin
+        cy -= margin
+        ex += margin
+        ey += margin
+        seen = []
+        out = []
+        for y in range(cy, ey + 1):
+            for x in range(cx, ex + 1):
+                c = self.cell(x, y)
+                if c is None:
+                    continue
+                for s in c:
+                    if s is shape:
+                        continue
+                    if s.id in seen:
+                        continue
+                    seen.append(s.id)                               # filtered-out shapes enter the set as well
+                    if use_any and not ((s.tags & any_mask) > 0):   # tags.go:29-31
+                        continue
+                    if (s.tags & none_mask) > 0:
+                        continue
+                    out.append((s, v_dist2(s.pos, shape.pos)))      # shape.go:179-181: other.DistanceSquaredTo(self)
+        return out
+
+    def intersection_test(self, shape, margin, **filters):
+        """shape.go:273-316 with OnIntersect returning true: the non-empty sets in callback order, or in an order
+        flagged as unspecified when the candidate sort is pdqsort territory (> 12 candidates) AND has exact ties."""
+        cand = self.candidates(shape, margin, **filters)
+        keys = [d for _, d in cand]
+        defined = len(cand) <= 12 or len(set(keys)) == len(keys)
+        if len(cand) <= 12:
+            go_sort_small(cand, lambda p, q: p[1] < q[1])
+        else:
+            cand = sorted(cand, key=lambda p: p[1])                 # any correct sort agrees when keys are distinct
+        sets = []
+        for other, d in cand:
+            mtv, cons, ordered = intersection(shape, other)
+            if cons:
+                sets.append((other.id, d, mtv, cons, ordered))
+        return sets, defined
