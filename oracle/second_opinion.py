@@ -273,7 +273,13 @@ def calculate_mtv(cp, other):
     else:
         verts = list(cp.transformed())
         center = other.pos
-        go_sort_small(verts, lambda p, q: v_mag(v_sub(p, center)) < v_mag(v_sub(q, center)))
+        if len(verts) <= 12:
+            go_sort_small(verts, lambda p, q: v_mag(v_sub(p, center)) < v_mag(v_sub(q, center)))
+        else:
+            # pdqsort territory, but only verts[0] is used: any correct sort puts the unique nearest vertex first
+            keys = [v_mag(v_sub(p, center)) for p in verts]
+            assert keys.count(min(keys)) == 1, "nearest vertex not unique among > 12: order is pdqsort's to decide"
+            verts = [verts[keys.index(min(keys))]]
         axis = (center[0] - verts[0][0], center[1] - verts[0][1])
         ov = overlap(cp.project(axis), other.project(axis))
         if ov <= 0:
@@ -486,3 +492,133 @@ class Space:
             if cons:
                 sets.append((other.id, d, mtv, cons, ordered))
         return sets, defined
+
+    def filter_cells(self, bounds):
+        """space.FilterCells(bounds).FilterShapes() (space.go:181-195, cell.go:73-121): shapes in walk order."""
+        cx, cy, ex, ey = self.to_cell_space(bounds)
+        seen, out = [], []
+        for y in range(cy, ey + 1):
+            for x in range(cx, ex + 1):
+                c = self.cell(x, y)
+                if c is None:
+                    continue
+                for s in c:
+                    if s.id in seen:
+                        continue
+                    seen.append(s.id)
+                    out.append(s)
+        return out
+
+
+def linetest(start, end, against):
+    """utils.go:276-370 with OnIntersect returning true: [(other id, mtv, center, contacts)] in callback order, and
+    whether that order is defined by the restated part of sort.Slice (n <= 12, or no exact key ties)."""
+    sets = []
+    for shape in against:
+        r = linetest_one(start, end, shape)
+        if r is not None:
+            sets.append((shape.id,) + r)
+    keys = [s[4] for s in sets]
+    defined = len(sets) <= 12 or len(set(keys)) == len(keys)
+    if len(sets) <= 12:
+        go_sort_small(sets, lambda p, q: p[4] < q[4])
+    else:
+        sets.sort(key=lambda p: p[4])
+    return sets, defined
+
+
+# ---------------------------------------------------------------- the parity kit's dump, from this restatement
+def _unhex(tok):
+    import struct
+    return struct.unpack("<d", struct.pack("<Q", int(tok, 16)))[0]
+
+
+def _hx(x):
+    import struct
+    return "%016x" % struct.unpack("<Q", struct.pack("<d", float(x)))[0]
+
+
+def dump_world(path):
+    """Python twin of parity/go/dump/main.go running on this restatement instead of the real package: reads a
+    parity/worlds/*.world file (own parser) and returns (dump text, set of line numbers whose ORDER is unspecified
+    because Go's pdqsort would have to break exact ties among more than 12 items)."""
+    with open(path) as fh:
+        rows = [l.split() for l in fh.read().splitlines() if l and not l.startswith("#")]
+    assert rows[0] == ["RESOLVWORLD", "1"]
+    it = iter(rows[1:])
+    name = next(it)[1]
+    sw, sh, cw, ch = (int(t) for t in next(it)[1:5])
+    margin = int(next(it)[1])
+    n = int(next(it)[1])
+    sp = Space(sw, sh, cw, ch)
+    recs = []
+    for _ in range(n):
+        t = next(it)
+        pos0 = (_unhex(t[8]), _unhex(t[9]))
+        pos = (_unhex(t[10]), _unhex(t[11]))
+        if t[1] == "C":
+            s = Circle(pos[0], pos[1], _unhex(t[12]))
+        else:
+            nv = int(t[13])
+            s = Polygon(pos0[0], pos0[1], [_unhex(x) for x in t[14:14 + 2 * nv]], closed=(t[3] == "1"))
+            s.pos = pos                       # SetPosition before Space.Add: no cells yet, cached bounds kept
+        sp.add(s, tags=int(t[5], 16))
+        recs.append(dict(shape=s, tester=t[2] == "1", use_any=t[4] == "1", any_mask=int(t[6], 16), none_mask=int(t[7], 16)))
+    frames = int(next(it)[1])
+    frame_pos = []
+    for f in range(1, frames):
+        assert next(it) == ["pos", str(f)]
+        frame_pos.append([tuple(_unhex(x) for x in next(it)[:2]) for _ in range(n)])
+    m = int(next(it)[1])
+    rays = [[_unhex(x) for x in next(it)[1:5]] for _ in range(m)]
+
+    out = [f"RESOLVDUMP 1 {name}"]
+    loose = set()
+
+    def set_text(other, mtv, cons, center=None):
+        s = f" {other} {_hx(mtv[0])} {_hx(mtv[1])}"
+        if center is not None:
+            s += f" {_hx(center[0])} {_hx(center[1])}"
+        s += f" {len(cons)}"
+        for p, q in cons:
+            s += f" {_hx(p[0])} {_hx(p[1])} {_hx(q[0])} {_hx(q[1])}"
+        return s
+
+    for f in range(frames):
+        if f:
+            for i, p in enumerate(frame_pos[f - 1]):
+                sp.set_position(recs[i]["shape"], p[0], p[1])
+        out.append(f"frame {f}")
+        for cy in range(sp.h):
+            for cx in range(sp.w):
+                c = sp.cells.get((cx, cy))
+                if c:
+                    out.append(f"cell {cy} {cx} " + " ".join(str(s.id) for s in c))
+        for a, rec in enumerate(recs):
+            if not rec["tester"]:
+                continue
+            flt = dict(use_any=rec["use_any"], any_mask=rec["any_mask"], none_mask=rec["none_mask"])
+            cands = sp.candidates(rec["shape"], margin, **flt)
+            out.append(f"test {a} {len(cands)}" + "".join(f" {o.id}" for o, _ in cands))
+            sets, defined = sp.intersection_test(rec["shape"], margin, **flt)
+            for k, (other, _, mtv, cons, ordered) in enumerate(sets):
+                if not (defined and ordered):
+                    loose.add(len(out))
+                out.append(f"hit {a} {k}" + set_text(other, mtv, cons))
+    for mode in ("all", "rect"):
+        for r, ray in enumerate(rays):
+            start, end = (ray[0], ray[1]), (ray[2], ray[3])
+            if mode == "all":
+                against = sp.shapes
+            else:
+                vu = v_unit(v_sub(end, start))
+                pulled = v_sub(start, v_scale(vu, 0.01))
+                against = sp.filter_cells(((go_min(pulled[0], end[0]), go_min(pulled[1], end[1])),
+                                           (go_max(pulled[0], end[0]), go_max(pulled[1], end[1]))))
+            out.append(f"ray {r} {mode}")
+            sets, defined = linetest(start, end, against)
+            for k, (other, mtv, center, cons, _key) in enumerate(sets):
+                if not defined:
+                    loose.add(len(out))
+                out.append(f"rhit {r} {k}" + set_text(other, mtv, cons, center))
+    return "\n".join(out) + "\n", loose
