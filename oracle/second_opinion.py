@@ -622,3 +622,43 @@ def dump_world(path):
                     loose.add(len(out))
                 out.append(f"rhit {r} {k}" + set_text(other, mtv, cons, center))
     return "\n".join(out) + "\n", loose
+
+
+def shape_linetest(space, cp, vec, start_offset=(0.0, 0.0), include_all=False, margin=1, **filters):
+    """ConvexPolygon.ShapeLineTest (convexPolygon.go:322-415) with TestAgainst = cp.SelectTouchingCells(margin)
+    .FilterShapes()[.ByTags][.NotByTags] and no `Lines` selection. The reference walks its vertex SET in Go-map order
+    (random); like the C++ oracle, the vertices are taken in insertion order here — the definition the host layer
+    adopts. Returns [(other id, mtv, center, contacts)] sorted by |MTV|^2 (insertion sort: <= 12 sets)."""
+    verts = []
+
+    def add(v):                       # Set[Vector]: Go map keys compare with ==
+        if not any(o[0] == v[0] and o[1] == v[1] for o in verts):
+            verts.append(v)
+
+    if not include_all:
+        for l in cp.lines():
+            if v_dot(line_normal(l), vec) < 0.01:
+                continue
+            v = v_invert(v_scale(line_vector(l), 0.5))
+            add(v_sub(l[0], v))
+            add(v_sub(l[1], v_invert(v)))
+    else:
+        for v in cp.transformed():
+            add(v)
+    vu = v_unit(vec)
+    results = []
+    for p in verts:
+        start = v_sub(p, v_add(vu, start_offset))
+        against = [o for o, _ in space.candidates(cp, margin, **filters)]   # callingShape is excluded by the selection
+        sets, _ = linetest(start, v_add(p, vec), against)
+        for other, mtv, center, cons, _key in sets:
+            for r in results:
+                if r[0] == other:
+                    r[3].extend(cons)
+                    if mtv[0] * mtv[0] + mtv[1] * mtv[1] < r[1][0] * r[1][0] + r[1][1] * r[1][1]:
+                        r[1] = mtv
+                    break
+            else:
+                results.append([other, mtv, center, list(cons)])
+    go_sort_small(results, lambda a, b: a[1][0] * a[1][0] + a[1][1] * a[1][1] < b[1][0] * b[1][0] + b[1][1] * b[1][1])
+    return results

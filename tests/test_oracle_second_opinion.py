@@ -223,3 +223,28 @@ def test_broadphase_and_intersection_test_agree_after_motion(seed, margin):
         total_c += k
         total_h += h
     assert total_c > 1000 and total_h > 200, (total_c, total_h)
+
+
+def test_shape_linetest_agrees_bit_for_bit():
+    """ConvexPolygon.ShapeLineTest (convexPolygon.go:322-415): leading-edge vertices, per-OtherShape merge, smallest
+    |MTV| first — what the platformer calls (examples/worldPlatformer.go:221-246)."""
+    rng, space, sp2, shapes = _world(8821, n=220)
+    n_sets = n_calls = 0
+    for i, s in enumerate(shapes):
+        if not isinstance(s, so.Polygon):
+            continue
+        for vec, inc in (((0.0, 14.0), False), ((9.0, -5.0), False), ((-6.0, 0.0), True)):
+            off = (0.0, 0.0) if i % 2 else (0.5, -0.25)
+            use_any, any_mask = bool(i % 3 == 0), 0b0110
+            got = space.shape_linetest(i, vec, start_offset=off, include_all=inc, margin=2, use_any=use_any, any_mask=any_mask)
+            exp = so.shape_linetest(sp2, s, vec, start_offset=off, include_all=inc, margin=2, use_any=use_any, any_mask=any_mask)
+            assert len(exp) == len(got.b), (i, vec)
+            for k, (other, mtv, center, cons) in enumerate(exp):
+                f, c = int(got.first[k]), int(got.count[k])
+                assert int(got.b[k]) == other and same(got.mtv[k][0], mtv[0]) and same(got.mtv[k][1], mtv[1])
+                assert same(got.center[k][0], center[0]) and same(got.center[k][1], center[1])
+                assert [tuple(bits(v) for v in r) for r in got.contacts[f:f + c]] == \
+                       [tuple(bits(v) for v in (p[0], p[1], q[0], q[1])) for p, q in cons]
+            n_sets += len(exp)
+            n_calls += 1
+    assert n_calls > 200 and n_sets > 150, (n_calls, n_sets)
