@@ -81,7 +81,7 @@ struct rsv_space {
     int narrow_blocks = 148 * 4;
     int narrow_blocks1 = 148 * 4;
     int pairs_blocks[2] = {148 * 8, 148 * 8};  // k_pairs<false> (no tag filters), k_pairs<true>
-    int pairs_blocks_own = 148 * 8;            // k_pairs_own (RSV_FRAME_OWN_RECT)
+    int pairs_blocks_own[2] = {148 * 8, 148 * 8};  // k_pairs_own<0>, k_pairs_own<1> (RSV_FRAME_OWN_RECT)
     uint4* ent_pref = nullptr;                 // [cap_entries + 1] prefix counts of the entry flags (RSV_FRAME_OWN_RECT)
     uint4* pref_tiles = nullptr;
     uint32_t n_pref_tiles = 0;
@@ -323,8 +323,10 @@ int32_t rsv_create(const rsv_config* cfg, rsv_space** out) {
         s->pairs_blocks[0] = s->sm_count * occ;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pairs<true>, kPairsBlock, 0) == cudaSuccess && occ > 0)
         s->pairs_blocks[1] = s->sm_count * occ;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pairs_own, kPairsBlock, 0) == cudaSuccess && occ > 0)
-        s->pairs_blocks_own = s->sm_count * occ;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pairs_own<0>, kPairsBlock, 0) == cudaSuccess && occ > 0)
+        s->pairs_blocks_own[0] = s->sm_count * occ;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pairs_own<1>, kPairsBlock, 0) == cudaSuccess && occ > 0)
+        s->pairs_blocks_own[1] = s->sm_count * occ;
     CUC(cudaStreamSynchronize(s->stream));
 #undef CUC
     *out = s;
@@ -519,7 +521,9 @@ static int32_t enqueue_frame(rsv_space* s, const DevView& d, int32_t margin, uin
             k_pref_tiles<<<s->n_pref_tiles, kPrefBlock, 0, st>>>(d, s->pref_tiles);
             k_pref_scan_tiles<<<1, 1024, 0, st>>>(s->pref_tiles, s->n_pref_tiles);
             k_pref_write<<<s->n_pref_tiles, kPrefBlock, 0, st>>>(d, s->pref_tiles, s->ent_pref);
-            k_pairs_own<<<s->pairs_blocks_own, kPairsBlock, 0, st>>>(d, s->ent_pref, margin, flags);
+            // (0x10000: experiment switch, first form of the batch)
+            if (flags & 0x10000u) k_pairs_own<0><<<s->pairs_blocks_own[0], kPairsBlock, 0, st>>>(d, s->ent_pref, margin, flags);
+            else k_pairs_own<1><<<s->pairs_blocks_own[1], kPairsBlock, 0, st>>>(d, s->ent_pref, margin, flags);
         } else if (flags & RSV_FRAME_NO_TAG_FILTERS) k_pairs<false><<<s->pairs_blocks[0], kPairsBlock, 0, st>>>(d, margin, flags);
         else k_pairs<true><<<s->pairs_blocks[1], kPairsBlock, 0, st>>>(d, margin, flags);
     }
@@ -549,7 +553,7 @@ static int32_t frame_via_graph(rsv_space* s, const DevView& d, int32_t margin, u
                                rsv_space::FrameGraph& g, cudaStream_t st) {
     rsv_space::FrameGraph::Key key{};
     key.margin = margin; key.flags = flags; key.stream = st; key.n_tiles = s->n_tiles;
-    key.blocks[0] = s->pairs_blocks[0] ^ (s->pairs_blocks[1] << 16) ^ (s->pairs_blocks_own << 8); key.blocks[1] = s->narrow_blocks; key.blocks[2] = s->narrow_blocks1;
+    key.blocks[0] = s->pairs_blocks[0] ^ (s->pairs_blocks[1] << 16) ^ (s->pairs_blocks_own[0] << 8) ^ (s->pairs_blocks_own[1] << 4); key.blocks[1] = s->narrow_blocks; key.blocks[2] = s->narrow_blocks1;
     const bool same = g.seen && memcmp(&key, &g.key, sizeof key) == 0 && memcmp(&d, &g.view, sizeof d) == 0;
     if (!same) {
         drop_graph(g);

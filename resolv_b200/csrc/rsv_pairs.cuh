@@ -680,6 +680,242 @@ __device__ __forceinline__ bool pairs_batch_own(const DevView& d, const uint4* _
     return true;
 }
 
+// Second form of the own-rect batch: the same results with shorter chains of dependent loads. The offsets of the
+// first kOwnRows rows of the walk and of the own rows are requested together, then all prefix counts together; the
+// per-row counts stay in shared memory for the rank phase (no second pass over the rows); the walk takes two entries
+// of a lane's row per step; the entry of B in a small cell is found with one round of loads.
+constexpr int kOwnRows = 4;
+struct OwnWarpSmem2 {
+    int4 q[32];
+    uint32_t hk[32];
+    int32_t x0[32], y0[32];
+    uint32_t base[32];
+    uint32_t stK[kPairStage];
+    int32_t stY[kPairStage];
+    uint2 rs[kOwnRows][32];     // per (row of the walk, tester): (s0, s1), clamped to the entry capacity
+    uint32_t rc[kOwnRows][32];  // candidates of the whole row
+    uint32_t ru[kOwnRows][32];  // first row of the walk: FC(s1); other rows: FR(s0)
+    uint32_t rv[kOwnRows][32];  // candidates of the row's first cell
+    uint32_t rw[kOwnRows][32];  // H(s1)
+};
+static_assert(sizeof(OwnWarpSmem2) <= offsetof(PairsWarpSmem<false>, queue), "OwnWarpSmem2 must end before PairsWarpSmem::queue");
+
+__device__ __forceinline__ bool pairs_batch_own2(const DevView& d, const uint4* __restrict__ P, int margin, uint32_t flags, bool have,
+                                                 uint32_t hk, PairsWarpSmem<false>& sm, unsigned long long& my_cands) {
+    OwnWarpSmem2& os = *reinterpret_cast<OwnWarpSmem2*>(&sm);
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t cap = d.cap_entries;
+    uint32_t A = 0, base = 0, ncand = 0;
+    float4 fa = make_float4(0.f, 0.f, 0.f, 0.f);
+    int x0 = 0, y0 = 0, sx = 0, sy = -1, qx0 = 0, qx1 = -1, qy0 = 0, qy1 = -1;
+    if (have) {
+        const uint32_t ent = d.entries[hk];
+        A = ent >> kEntShift;
+        fa = d.ent_box[hk];
+        const uint2 hm = d.ent_home[hk];
+        const uint32_t local = hm.x % d.cells_per_space;
+        base = hm.x - local;
+        x0 = (int)(local % (uint32_t)d.W); y0 = d.row_lo + (int)(local / (uint32_t)d.W);
+        sx = (int)(hm.y & 0xffffu); sy = (int)(hm.y >> 16);
+        qx0 = max(x0 - margin, 0); qx1 = min(x0 + sx + margin, d.W - 1);
+        qy0 = max(y0 - margin, d.row_lo); qy1 = min(y0 + sy + margin, d.row_hi - 1);
+    }
+    const int rows = have ? qy1 - qy0 + 1 : 0;
+    const uint32_t* cell0 = d.cell + (size_t)base;
+    // ---- one round of offset loads: the first kOwnRows rows of the walk and of the own rect
+    uint32_t s0[kOwnRows], s1[kOwnRows], e[kOwnRows], oa[kOwnRows], ob[kOwnRows], oc[kOwnRows];
+#pragma unroll
+    for (int r = 0; r < kOwnRows; r++) {
+        s0[r] = s1[r] = e[r] = oa[r] = ob[r] = oc[r] = 0u;
+        if (r < rows) {
+            const uint32_t* row = cell0 + (size_t)(qy0 + r - d.row_lo) * (size_t)d.W + (size_t)qx0;
+            s0[r] = row[0]; s1[r] = row[1]; e[r] = qx1 > qx0 ? row[qx1 - qx0 + 1] : s1[r];
+        }
+        if (have && r <= sy) {
+            const uint32_t* row = cell0 + (size_t)(y0 + r - d.row_lo) * (size_t)d.W + (size_t)x0;
+            oa[r] = row[0]; ob[r] = row[1]; oc[r] = sx > 0 ? row[sx + 1] : ob[r];
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kOwnRows; r++) {
+        s0[r] = min(s0[r], cap); s1[r] = min(s1[r], cap); e[r] = min(e[r], cap);
+        oa[r] = min(oa[r], cap); ob[r] = min(ob[r], cap); oc[r] = min(oc[r], cap);
+    }
+    // ---- one round of prefix-count loads
+    uint4 p0[kOwnRows], p1[kOwnRows], pe[kOwnRows];
+#pragma unroll
+    for (int r = 0; r < kOwnRows; r++) {
+        p0[r] = p1[r] = pe[r] = make_uint4(0u, 0u, 0u, 0u);
+        if (r < rows) { p0[r] = P[s0[r]]; p1[r] = P[s1[r]]; pe[r] = P[e[r]]; }
+    }
+#pragma unroll
+    for (int r = 0; r < kOwnRows; r++) {
+        uint32_t u = 0, v = 0, cnt = 0;
+        if (r < rows) {
+            if (r == 0) { v = s1[r] - s0[r]; cnt = v + (pe[r].x - p1[r].x); u = p1[r].x; }
+            else { v = p1[r].y - p0[r].y; cnt = v + (pe[r].z - p1[r].z); u = p0[r].y; }
+            ncand += cnt;
+        }
+        os.rs[r][lane] = make_uint2(s0[r], s1[r]);
+        os.rc[r][lane] = cnt; os.ru[r][lane] = u; os.rv[r][lane] = v; os.rw[r][lane] = p1[r].z;
+    }
+    if (have) {
+        for (int y = qy0 + kOwnRows; y <= qy1; y++) ncand += own_row_count(d, P, base, y, qx0, qx1, qy0, 0xffffffffu);
+        ncand -= 1u;  // the tester's own home entry (cell.go:101)
+    }
+    sm.A[lane] = A;
+    sm.gated[lane] = 0;
+    os.q[lane] = make_int4(qx0, qy0, qx1, qy1);
+    os.hk[lane] = hk; os.x0[lane] = x0; os.y0[lane] = y0; os.base[lane] = base;
+    __syncwarp();
+    // ---- walk the own rect, two entries of the lane's current row per warp step
+    int ry = 0;
+    uint32_t k = 0, kend = 0, fs1 = 0;
+    bool active = have;
+    auto set_row = [&]() {
+        uint32_t a, b, c;
+        if (ry < kOwnRows) {
+            a = ry == 0 ? oa[0] : (ry == 1 ? oa[1] : (ry == 2 ? oa[2] : oa[3]));
+            b = ry == 0 ? ob[0] : (ry == 1 ? ob[1] : (ry == 2 ? ob[2] : ob[3]));
+            c = ry == 0 ? oc[0] : (ry == 1 ? oc[1] : (ry == 2 ? oc[2] : oc[3]));
+        } else {
+            const uint32_t* row = cell0 + (size_t)(y0 + ry - d.row_lo) * (size_t)d.W + (size_t)x0;
+            a = min(row[0], cap); b = min(row[1], cap); c = sx > 0 ? min(row[sx + 1], cap) : b;
+        }
+        k = a; fs1 = b; kend = c;
+    };
+    if (active) set_row();
+    uint32_t produced = 0;
+    for (;;) {
+        while (active && k >= kend) {
+            if (++ry > sy) active = false;
+            else set_row();
+        }
+        if (!__any_sync(0xffffffffu, active)) break;
+        bool rec0 = false, rec1 = false;
+        uint32_t B0 = 0, B1 = 0;
+        const bool two = active && k + 1 < kend;
+        if (active) {
+            const uint32_t ent0 = d.entries[k];
+            const float4 fb0 = d.ent_box[k];
+            uint32_t ent1 = 0;
+            float4 fb1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (two) { ent1 = d.entries[k + 1]; fb1 = d.ent_box[k + 1]; }
+            B0 = ent0 >> kEntShift;
+            B1 = ent1 >> kEntShift;
+            const bool c0 = B0 != A && ((ent0 & kEntFirstCol) || k < fs1) && ((ent0 & kEntFirstRow) || ry == 0);
+            const bool c1 = two && B1 != A && ((ent1 & kEntFirstCol) || k + 1 < fs1) && ((ent1 & kEntFirstRow) || ry == 0);
+            rec0 = c0 && !(fb0.z < fa.x || fb0.x > fa.z || fb0.w < fa.y || fb0.y > fa.w);
+            rec1 = c1 && !(fb1.z < fa.x || fb1.x > fa.z || fb1.w < fa.y || fb1.y > fa.w);
+        }
+        const uint32_t m0 = __ballot_sync(0xffffffffu, rec0), m1 = __ballot_sync(0xffffffffu, rec1);
+        if (rec0) {
+            const uint32_t slot = produced + __popc(m0 & lt);
+            if (slot < kPairStage) { sm.stB[slot] = B0; sm.stT[slot] = (uint32_t)lane << 24; os.stK[slot] = k; os.stY[slot] = y0 + ry; }
+        }
+        if (rec1) {
+            const uint32_t slot = produced + __popc(m0) + __popc(m1 & lt);
+            if (slot < kPairStage) { sm.stB[slot] = B1; sm.stT[slot] = (uint32_t)lane << 24; os.stK[slot] = k + 1; os.stY[slot] = y0 + ry; }
+        }
+        produced += __popc(m0) + __popc(m1);
+        if (active) k += two ? 2u : 1u;
+    }
+    if (produced > kPairStage) return false;
+    __syncwarp();
+    // ---- generation rank of every staged record, one record per lane
+    for (uint32_t r = lane; r < produced; r += 32) {
+        const uint32_t t = sm.stT[r] >> 24, B = sm.stB[r], kk = os.stK[r];
+        const int yk = os.stY[r];
+        const int4 q = os.q[t];
+        const uint32_t bs = os.base[t];
+        const int4 cr = d.crect[B];
+        const uint32_t entk = d.entries[kk];
+        int bx0, by0, bx1, by1;
+        clamp_rect(d, cr, bx0, by0, bx1, by1);
+        const int fx = max(bx0, q.x), fy = max(by0, q.y);   // B's first occurrence in the walk
+        const int xk = (entk & kEntFirstCol) ? bx0 : os.x0[t];
+        uint32_t kb = kk;
+        if (fx != xk || fy != yk) {
+            const uint32_t* cp = d.cell + (size_t)bs + (size_t)(fy - d.row_lo) * (size_t)d.W + (size_t)fx;
+            uint32_t lo = min(cp[0], cap), hi = min(cp[1], cap);
+            if (hi - lo <= 4u) {   // entry words ascend with the slot inside a cell: count the ones below B
+                const uint32_t e0 = lo < hi ? d.entries[lo] : 0xffffffffu, e1 = lo + 1 < hi ? d.entries[lo + 1] : 0xffffffffu;
+                const uint32_t e2 = lo + 2 < hi ? d.entries[lo + 2] : 0xffffffffu, e3 = lo + 3 < hi ? d.entries[lo + 3] : 0xffffffffu;
+                kb = lo + ((e0 >> kEntShift) < B) + ((e1 >> kEntShift) < B) + ((e2 >> kEntShift) < B) + ((e3 >> kEntShift) < B);
+            } else {
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if ((d.entries[mid] >> kEntShift) < B) lo = mid + 1;
+                    else hi = mid;
+                }
+                kb = lo;
+            }
+        }
+        const int ri = fy - q.y;
+        uint32_t rank = 0;
+        if (ri < kOwnRows) {
+#pragma unroll
+            for (int rr = 0; rr < kOwnRows - 1; rr++)
+                if (rr < ri) rank += os.rc[rr][t];
+            const uint2 ss = os.rs[ri][t];
+            const uint32_t u = os.ru[ri][t], v = os.rv[ri][t], w = os.rw[ri][t];
+            const uint4 pk = P[kb];
+            if (ri == 0) rank += kb < ss.y ? kb - ss.x : v + (pk.x - u);
+            else rank += kb < ss.y ? pk.y - u : v + (pk.z - w);
+        } else {
+            for (int yy = q.y; yy < fy; yy++) rank += own_row_count(d, P, bs, yy, q.x, q.z, q.y, 0xffffffffu);
+            rank += own_row_count(d, P, bs, fy, q.x, q.z, q.y, kb);
+        }
+        const int y0t = os.y0[t];
+        if (y0t < fy || (y0t == fy && os.hk[t] < kb)) rank -= 1u;
+        sm.stR[r] = rank << 8;
+    }
+    __syncwarp();
+    // ---- order each tester's records by rank (generation order); ranks of one tester are distinct
+    for (uint32_t r = lane; r < produced; r += 32) {
+        const uint32_t t = sm.stT[r] >> 24, rk = sm.stR[r];
+        uint32_t pos = 0, cnt = 0;
+        for (uint32_t r2 = 0; r2 < produced; r2++)
+            if ((sm.stT[r2] >> 24) == t) {
+                cnt++;
+                if (sm.stR[r2] < rk) pos++;
+            }
+        sm.stT[r] = (t << 24) | pos;   // (the top byte, which other lanes are reading, does not change)
+        if (pos == 0) sm.gated[t] = cnt;
+    }
+    __syncwarp();
+    const uint32_t cnt = sm.gated[lane];
+    if (have) my_cands += ncand;
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    uint32_t chunk = 0;
+    if (lane == 0 && total) {
+        chunk = atomicAdd(&d.ctr->pair_cursor, total);
+        if (chunk + total > d.cap_pairs || chunk + total < chunk) atomicOr(&d.ctr->overflow, RSV_OVF_PAIRS);
+    }
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    sm.excl[lane] = inc - cnt;
+    if (have && (flags & RSV_FRAME_TESTER_TABLE)) {
+        d.tester_start[A] = chunk + (inc - cnt);
+        d.tester_count[A] = cnt;
+    }
+    __syncwarp();
+    for (uint32_t r = lane; r < produced; r += 32) {
+        const uint32_t tt = sm.stT[r], t = tt >> 24;
+        const unsigned long long pos = (unsigned long long)chunk + sm.excl[t] + (tt & 0xffffffu);
+        if (pos < d.cap_pairs) *reinterpret_cast<uint4*>(d.hits + pos) = make_uint4(sm.A[t], sm.stB[r], 0u, sm.stR[r]);
+    }
+    __syncwarp();
+    return true;
+}
+
+template <int FORM>
 __global__ void __launch_bounds__(kPairsBlock) k_pairs_own(DevView d, const uint4* __restrict__ pref, int margin, uint32_t flags) {
     __shared__ PairsWarpSmem<false> s_warp[kPairsWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -710,8 +946,9 @@ __global__ void __launch_bounds__(kPairsBlock) k_pairs_own(DevView d, const uint
             if (qn >= 32) {
                 const uint32_t hk = q[lane];
                 __syncwarp();
-                if (!pairs_batch_own(d, pref, margin, flags, true, hk, sm, my_cands))
-                    pairs_batch<false>(d, margin, flags, true, hk, 0u, sm, my_cands);
+                const bool done = FORM ? pairs_batch_own2(d, pref, margin, flags, true, hk, sm, my_cands)
+                                       : pairs_batch_own(d, pref, margin, flags, true, hk, sm, my_cands);
+                if (!done) pairs_batch<false>(d, margin, flags, true, hk, 0u, sm, my_cands);
                 if (lane + 32 < qn) { const uint32_t t = q[lane + 32]; q[lane] = t; }
                 qn -= 32;
                 __syncwarp();
@@ -720,8 +957,9 @@ __global__ void __launch_bounds__(kPairsBlock) k_pairs_own(DevView d, const uint
     }
     if (qn) {
         const uint32_t hk = lane < qn ? q[lane] : kNoEntry;
-        if (!pairs_batch_own(d, pref, margin, flags, lane < qn, hk, sm, my_cands))
-            pairs_batch<false>(d, margin, flags, lane < qn, hk, 0u, sm, my_cands);
+        const bool done = FORM ? pairs_batch_own2(d, pref, margin, flags, lane < qn, hk, sm, my_cands)
+                               : pairs_batch_own(d, pref, margin, flags, lane < qn, hk, sm, my_cands);
+        if (!done) pairs_batch<false>(d, margin, flags, lane < qn, hk, 0u, sm, my_cands);
     }
     // testers with no stored cell whose margin still reaches the grid: the full walk (their own rect is empty, yet a
     // shape straddling the border can still pass the Bounds gate)

@@ -64,7 +64,7 @@ def compare(name, w, margins=(1,), extra=0):
 def timing(name, w, flags):
     out = {}
     ds = space_for_world(w)
-    for label, fl in (("walk", flags), ("own", flags | _abi.FRAME_OWN_RECT)):
+    for label, fl in (("walk", flags), ("own_first_form", flags | _abi.FRAME_OWN_RECT | 0x10000), ("own", flags | _abi.FRAME_OWN_RECT)):
         for _ in range(4):
             ds.frame(1, fl, grow=True)
         ds.timer_start()
@@ -97,6 +97,8 @@ if __name__ == "__main__":
     ok &= compare("platformer batch 16", worlds.make_platformer_batch(16), (1, 4))
     ok &= compare("platformer incremental", worlds.make_platformer_batch(8), (4,), extra=_abi.FRAME_INCREMENTAL)
     ok &= compare("rects 200k", worlds.make_rects(200_000, space=29312, cell=32), (1,))
+    ok &= compare("rects tall/wide (> 4 rows)", worlds.make_rects(300, space=1024, cell=16, lo=10.0, hi=150.0), (0, 1, 5))
+    ok &= compare("first form: rects dense", w, (1,), extra=0x10000)
     print("PARITY", "OK" if ok else "MISMATCH", f"({time.time() - t0:.1f} s)", flush=True)
     res = {"parity": ok}
     res["cfg2"] = timing("cfg2", worlds.make_rects(1_000_000), _abi.FRAME_NO_TAG_FILTERS)
