@@ -522,7 +522,8 @@ static int32_t enqueue_frame(rsv_space* s, const DevView& d, int32_t margin, uin
             k_pref_scan_tiles<<<1, 1024, 0, st>>>(s->pref_tiles, s->n_pref_tiles);
             k_pref_write<<<s->n_pref_tiles, kPrefBlock, 0, st>>>(d, s->pref_tiles, s->ent_pref);
             // (0x10000: experiment switch, first form of the batch)
-            if (flags & 0x10000u) k_pairs_own<0><<<s->pairs_blocks_own[0], kPairsBlock, 0, st>>>(d, s->ent_pref, margin, flags);
+            if (flags & 0x80000u) k_pairs<false><<<s->pairs_blocks[0], kPairsBlock, 0, st>>>(d, margin, flags);   // (timing: prefix passes + regular walk)
+            else if (flags & 0x10000u) k_pairs_own<0><<<s->pairs_blocks_own[0], kPairsBlock, 0, st>>>(d, s->ent_pref, margin, flags);
             else k_pairs_own<1><<<s->pairs_blocks_own[1], kPairsBlock, 0, st>>>(d, s->ent_pref, margin, flags);
         } else if (flags & RSV_FRAME_NO_TAG_FILTERS) k_pairs<false><<<s->pairs_blocks[0], kPairsBlock, 0, st>>>(d, margin, flags);
         else k_pairs<true><<<s->pairs_blocks[1], kPairsBlock, 0, st>>>(d, margin, flags);

@@ -721,7 +721,8 @@ __device__ __forceinline__ bool pairs_batch_own2(const DevView& d, const uint4* 
         qx0 = max(x0 - margin, 0); qx1 = min(x0 + sx + margin, d.W - 1);
         qy0 = max(y0 - margin, d.row_lo); qy1 = min(y0 + sy + margin, d.row_hi - 1);
     }
-    const int rows = have ? qy1 - qy0 + 1 : 0;
+    // (timing experiments, results meaningless: 0x20000 no rank phase, 0x40000 no walk, 0x100000 no row counts)
+    const int rows = (have && !(flags & 0x100000u)) ? qy1 - qy0 + 1 : 0;
     const uint32_t* cell0 = d.cell + (size_t)base;
     // ---- one round of offset loads: the first kOwnRows rows of the walk and of the own rect
     uint32_t s0[kOwnRows], s1[kOwnRows], e[kOwnRows], oa[kOwnRows], ob[kOwnRows], oc[kOwnRows];
@@ -760,7 +761,7 @@ __device__ __forceinline__ bool pairs_batch_own2(const DevView& d, const uint4* 
         os.rs[r][lane] = make_uint2(s0[r], s1[r]);
         os.rc[r][lane] = cnt; os.ru[r][lane] = u; os.rv[r][lane] = v; os.rw[r][lane] = p1[r].z;
     }
-    if (have) {
+    if (have && !(flags & 0x100000u)) {
         for (int y = qy0 + kOwnRows; y <= qy1; y++) ncand += own_row_count(d, P, base, y, qx0, qx1, qy0, 0xffffffffu);
         ncand -= 1u;  // the tester's own home entry (cell.go:101)
     }
@@ -772,7 +773,7 @@ __device__ __forceinline__ bool pairs_batch_own2(const DevView& d, const uint4* 
     // ---- walk the own rect, two entries of the lane's current row per warp step
     int ry = 0;
     uint32_t k = 0, kend = 0, fs1 = 0;
-    bool active = have;
+    bool active = have && !(flags & 0x40000u);
     auto set_row = [&]() {
         uint32_t a, b, c;
         if (ry < kOwnRows) {
@@ -829,6 +830,7 @@ __device__ __forceinline__ bool pairs_batch_own2(const DevView& d, const uint4* 
         const int yk = os.stY[r];
         const int4 q = os.q[t];
         const uint32_t bs = os.base[t];
+        if (flags & 0x20000u) { sm.stR[r] = r << 8; continue; }
         const int4 cr = d.crect[B];
         const uint32_t entk = d.entries[kk];
         int bx0, by0, bx1, by1;

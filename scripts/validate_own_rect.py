@@ -61,10 +61,15 @@ def compare(name, w, margins=(1,), extra=0):
     return ok
 
 
-def timing(name, w, flags):
+def timing(name, w, flags, diag=False):
     out = {}
     ds = space_for_world(w)
-    for label, fl in (("walk", flags), ("own_first_form", flags | _abi.FRAME_OWN_RECT | 0x10000), ("own", flags | _abi.FRAME_OWN_RECT)):
+    O = flags | _abi.FRAME_OWN_RECT
+    variants = [("walk", flags), ("own", O)]
+    if diag:   # experiment switches of rsv_pairs.cuh (results meaningless, timing only)
+        variants += [("prefix+walk", O | 0x80000), ("own-rank", O | 0x20000), ("own-walk-rank", O | 0x40000),
+                     ("own-walk-rank-rows", O | 0x40000 | 0x100000)]
+    for label, fl in variants:
         for _ in range(4):
             ds.frame(1, fl, grow=True)
         ds.timer_start()
@@ -101,7 +106,7 @@ if __name__ == "__main__":
     ok &= compare("first form: rects dense", w, (1,), extra=0x10000)
     print("PARITY", "OK" if ok else "MISMATCH", f"({time.time() - t0:.1f} s)", flush=True)
     res = {"parity": ok}
-    res["cfg2"] = timing("cfg2", worlds.make_rects(1_000_000), _abi.FRAME_NO_TAG_FILTERS)
+    res["cfg2"] = timing("cfg2", worlds.make_rects(1_000_000), _abi.FRAME_NO_TAG_FILTERS, diag=True)
     res["cfg3_unfiltered"] = timing("cfg3u", worlds.make_mixed(1_000_000, filtered=False), _abi.FRAME_NO_TAG_FILTERS)
     print(json.dumps(res), flush=True)
     print(f"total {time.time() - t0:.1f} s")
