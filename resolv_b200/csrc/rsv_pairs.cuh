@@ -936,13 +936,9 @@ __global__ void __launch_bounds__(kPairsBlock) k_pairs_own(DevView d, const uint
         c = __shfl_sync(0xffffffffu, c, 0);
         if (c >= n_chunks) break;
         const uint32_t lo = c * chunk_sz, hi = min(lo + chunk_sz, R);
-        // the entry words are requested three steps ahead: a step is otherwise one exposed memory round trip
-        auto ld = [&](uint32_t k0) { const uint32_t kk = k0 + lane; return kk < hi ? d.entries[kk] : 0u; };
-        uint32_t e0 = ld(lo), e1 = ld(lo + 32), e2 = ld(lo + 64);
         for (uint32_t base = lo; base < hi; base += 32) {
             const uint32_t k = base + lane;
-            const uint32_t ent = e0;
-            e0 = e1; e1 = e2; e2 = ld(base + 96);
+            const uint32_t ent = k < hi ? d.entries[k] : 0u;
             const uint32_t want = kEntTester | kEntFirstCol | kEntFirstRow;
             const bool home = (ent & want) == want;
             const uint32_t m = __ballot_sync(0xffffffffu, home);
@@ -1007,13 +1003,9 @@ __global__ void __launch_bounds__(kPairsBlock) k_pairs(DevView d, int margin, ui
         c = __shfl_sync(0xffffffffu, c, 0);
         if (c >= n_chunks) break;
         const uint32_t lo = c * chunk_sz, hi = min(lo + chunk_sz, R);
-        // the entry words are requested three steps ahead: a step is otherwise one exposed memory round trip
-        auto ld = [&](uint32_t k0) { const uint32_t kk = k0 + lane; return kk < hi ? d.entries[kk] : 0u; };
-        uint32_t e0 = ld(lo), e1 = ld(lo + 32), e2 = ld(lo + 64);
         for (uint32_t base = lo; base < hi; base += 32) {
             uint32_t k = base + lane;
-            uint32_t ent = e0;
-            e0 = e1; e1 = e2; e2 = ld(base + 96);
+            uint32_t ent = k < hi ? d.entries[k] : 0u;
             const uint32_t want = kEntTester | kEntFirstCol | kEntFirstRow;   // the tester's home registration
             bool home = (ent & want) == want;
             uint32_t m = __ballot_sync(0xffffffffu, home);
