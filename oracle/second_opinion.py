@@ -10,7 +10,7 @@ correctly rounded — the same arithmetic Go/amd64 does. tests/test_oracle_secon
 restatements agree BIT FOR BIT on seeded random shapes; a transcription slip in either one shows up as a mismatch.
 It narrows "unpinned" to "two independent readings of the source agree"; only parity/go run against real resolv pins it.
 
-Go stdlib behaviour restated here: math.Min (NaN / signed zero), sort.Slice for n <= 12 (insertion sort, stable),
+Go stdlib behaviour restated here: math.Min (NaN / signed zero), sort.Slice (pdqsort_func, full),
 math.Pow(x, 2) == x*x for finite non-overflowing x.
 """
 import math
@@ -76,13 +76,206 @@ def go_max(x, y):                     # Go math.Max
     return x if x > y else y
 
 
-def go_sort_small(items, less):       # sort.Slice, n <= 12: insertionSortLessFunc
-    assert len(items) <= 12, "pdqsort territory: compare as a multiset instead"
-    for i in range(1, len(items)):
-        j = i
-        while j > 0 and less(items[j], items[j - 1]):
-            items[j], items[j - 1] = items[j - 1], items[j]
+def go_sort_slice(data, less):
+    """sort.Slice(data, less): pdqsort_func of Go >= 1.19 (sort/zsortfunc.go; resolv's go.mod says go 1.20), restated from
+    the published algorithm, separately from the C++ oracle's restatement: insertion sort up to 12 items, else
+    pattern-defeating quicksort (choosePivot with ninther from 50 items, partialInsertionSort, partitionEqual for runs of
+    duplicates, breakPatterns with an xorshift seeded by the length, heapsort when the limit runs out). In place."""
+    n = len(data)
+
+    def swap(i, j):
+        data[i], data[j] = data[j], data[i]
+
+    def lt(i, j):
+        return less(data[i], data[j])
+
+    def insertion(a, b):
+        for i in range(a + 1, b):
+            j = i
+            while j > a and lt(j, j - 1):
+                swap(j, j - 1)
+                j -= 1
+
+    def sift_down(lo, hi, first):
+        root = lo
+        while True:
+            child = 2 * root + 1
+            if child >= hi:
+                return
+            if child + 1 < hi and lt(first + child, first + child + 1):
+                child += 1
+            if not lt(first + root, first + child):
+                return
+            swap(first + root, first + child)
+            root = child
+
+    def heap_sort(a, b):
+        first, lo, hi = a, 0, b - a
+        for i in range((hi - 1) // 2, -1, -1):
+            sift_down(i, hi, first)
+        for i in range(hi - 1, -1, -1):
+            swap(first, first + i)
+            sift_down(lo, i, first)
+
+    def order2(a, b, sw):
+        if lt(b, a):
+            sw[0] += 1
+            return b, a
+        return a, b
+
+    def median(a, b, c, sw):
+        a, b = order2(a, b, sw)
+        b, c = order2(b, c, sw)
+        a, b = order2(a, b, sw)
+        return b
+
+    def choose_pivot(a, b):
+        l = b - a
+        sw = [0]
+        i, j, k = a + l // 4 * 1, a + l // 4 * 2, a + l // 4 * 3
+        if l >= 8:
+            if l >= 50:
+                i = median(i - 1, i, i + 1, sw)
+                j = median(j - 1, j, j + 1, sw)
+                k = median(k - 1, k, k + 1, sw)
+            j = median(i, j, k, sw)
+        if sw[0] == 0:
+            return j, 1          # increasingHint
+        if sw[0] == 12:
+            return j, 2          # decreasingHint
+        return j, 0
+
+    def reverse_range(a, b):
+        i, j = a, b - 1
+        while i < j:
+            swap(i, j)
+            i += 1
             j -= 1
+
+    def partial_insertion(a, b):
+        i = a + 1
+        for _ in range(5):
+            while i < b and not lt(i, i - 1):
+                i += 1
+            if i == b:
+                return True
+            if b - a < 50:
+                return False
+            swap(i, i - 1)
+            if i - a >= 2:
+                j = i - 1
+                while j >= 1:
+                    if not lt(j, j - 1):
+                        break
+                    swap(j, j - 1)
+                    j -= 1
+            if b - i >= 2:
+                j = i + 1
+                while j < b:
+                    if not lt(j, j - 1):
+                        break
+                    swap(j, j - 1)
+                    j += 1
+        return False
+
+    def break_patterns(a, b):
+        length = b - a
+        if length >= 8:
+            rnd = length
+            modulus = 1 << length.bit_length()
+            idx = a + (length // 4) * 2 - 1
+            for i in range(3):
+                rnd ^= (rnd << 13) & 0xFFFFFFFFFFFFFFFF
+                rnd ^= rnd >> 7
+                rnd ^= (rnd << 17) & 0xFFFFFFFFFFFFFFFF
+                other = rnd & (modulus - 1)
+                if other >= length:
+                    other -= length
+                swap(idx - 1 + i, a + other)
+
+    def partition_equal(a, b, pivot):
+        swap(a, pivot)
+        i, j = a + 1, b - 1
+        while True:
+            while i <= j and not lt(a, i):
+                i += 1
+            while i <= j and lt(a, j):
+                j -= 1
+            if i > j:
+                break
+            swap(i, j)
+            i += 1
+            j -= 1
+        return i
+
+    def partition(a, b, pivot):
+        swap(a, pivot)
+        i, j = a + 1, b - 1
+        while i <= j and lt(i, a):
+            i += 1
+        while i <= j and not lt(j, a):
+            j -= 1
+        if i > j:
+            swap(j, a)
+            return j, True
+        swap(i, j)
+        i += 1
+        j -= 1
+        while True:
+            while i <= j and lt(i, a):
+                i += 1
+            while i <= j and not lt(j, a):
+                j -= 1
+            if i > j:
+                break
+            swap(i, j)
+            i += 1
+            j -= 1
+        swap(j, a)
+        return j, False
+
+    def pdq(a, b, limit):
+        was_balanced = was_partitioned = True
+        while True:
+            length = b - a
+            if length <= 12:
+                insertion(a, b)
+                return
+            if limit == 0:
+                heap_sort(a, b)
+                return
+            if not was_balanced:
+                break_patterns(a, b)
+                limit -= 1
+            pivot, hint = choose_pivot(a, b)
+            if hint == 2:
+                reverse_range(a, b)
+                pivot = (b - 1) - (pivot - a)
+                hint = 1
+            if was_balanced and was_partitioned and hint == 1:
+                if partial_insertion(a, b):
+                    return
+            if a > 0 and not lt(a - 1, pivot):
+                a = partition_equal(a, b, pivot)
+                continue
+            mid, already = partition(a, b, pivot)
+            was_partitioned = already
+            left, right = mid - a, b - mid
+            thr = length // 8
+            if left < right:
+                was_balanced = left >= thr
+                pdq(a, mid, limit)
+                a = mid + 1
+            else:
+                was_balanced = right >= thr
+                pdq(mid + 1, b, limit)
+                b = mid
+
+    pdq(0, n, n.bit_length())
+
+
+def go_sort_small(items, less):       # kept name: every sort.Slice call of the reference goes through here
+    go_sort_slice(items, less)
 
 
 # ---------------------------------------------------------------- utils.go: Bounds
@@ -273,13 +466,7 @@ def calculate_mtv(cp, other):
     else:
         verts = list(cp.transformed())
         center = other.pos
-        if len(verts) <= 12:
-            go_sort_small(verts, lambda p, q: v_mag(v_sub(p, center)) < v_mag(v_sub(q, center)))
-        else:
-            # pdqsort territory, but only verts[0] is used: any correct sort puts the unique nearest vertex first
-            keys = [v_mag(v_sub(p, center)) for p in verts]
-            assert keys.count(min(keys)) == 1, "nearest vertex not unique among > 12: order is pdqsort's to decide"
-            verts = [verts[keys.index(min(keys))]]
+        go_sort_small(verts, lambda p, q: v_mag(v_sub(p, center)) < v_mag(v_sub(q, center)))
         axis = (center[0] - verts[0][0], center[1] - verts[0][1])
         ov = overlap(cp.project(axis), other.project(axis))
         if ov <= 0:
@@ -343,10 +530,7 @@ def intersection(a, b):
             for p in line_x_circle(l, b):
                 cons.append((p, v_unit(v_sub(p, b.pos))))
         if cons:
-            if len(cons) <= 12:
-                go_sort_small(cons, lambda s, t: v_dist2(s[0], b.pos) < v_dist2(t[0], b.pos))
-            else:
-                ordered = False
+            go_sort_small(cons, lambda s, t: v_dist2(s[0], b.pos) < v_dist2(t[0], b.pos))
             m = calculate_mtv(a, b)
             if m is not None:
                 mtv = m
@@ -360,10 +544,7 @@ def intersection(a, b):
                 cons.append((p, line_normal(ol)))
     if cons:
         center = a.center()
-        if len(cons) <= 12:
-            go_sort_small(cons, lambda s, t: v_dist2(s[0], center) < v_dist2(t[0], center))
-        else:
-            ordered = False
+        go_sort_small(cons, lambda s, t: v_dist2(s[0], center) < v_dist2(t[0], center))
         m = calculate_mtv(a, b)
         if m is not None:
             mtv = m
@@ -480,12 +661,8 @@ class Space:
         """shape.go:273-316 with OnIntersect returning true: the non-empty sets in callback order, or in an order
         flagged as unspecified when the candidate sort is pdqsort territory (> 12 candidates) AND has exact ties."""
         cand = self.candidates(shape, margin, **filters)
-        keys = [d for _, d in cand]
-        defined = len(cand) <= 12 or len(set(keys)) == len(keys)
-        if len(cand) <= 12:
-            go_sort_small(cand, lambda p, q: p[1] < q[1])
-        else:
-            cand = sorted(cand, key=lambda p: p[1])                 # any correct sort agrees when keys are distinct
+        defined = True
+        go_sort_small(cand, lambda p, q: p[1] < q[1])
         sets = []
         for other, d in cand:
             mtv, cons, ordered = intersection(shape, other)
@@ -518,13 +695,8 @@ def linetest(start, end, against):
         r = linetest_one(start, end, shape)
         if r is not None:
             sets.append((shape.id,) + r)
-    keys = [s[4] for s in sets]
-    defined = len(sets) <= 12 or len(set(keys)) == len(keys)
-    if len(sets) <= 12:
-        go_sort_small(sets, lambda p, q: p[4] < q[4])
-    else:
-        sets.sort(key=lambda p: p[4])
-    return sets, defined
+    go_sort_small(sets, lambda p, q: p[4] < q[4])
+    return sets, True
 
 
 # ---------------------------------------------------------------- the parity kit's dump, from this restatement

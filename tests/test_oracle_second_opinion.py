@@ -248,3 +248,34 @@ def test_shape_linetest_agrees_bit_for_bit():
             n_sets += len(exp)
             n_calls += 1
     assert n_calls > 200 and n_sets > 150, (n_calls, n_sets)
+
+
+def test_the_two_restatements_of_gos_pdqsort_agree():
+    """sort.Slice is pdqsort_func (unstable beyond 12 items): the C++ oracle and second_opinion.py each restate it from
+    the published algorithm; they must produce the same permutation, ties included, for every input shape that steers
+    it (random, few distinct keys, sorted, reversed, half sorted, constant; 0-400 items: insertion sort, ninther pivots,
+    partialInsertionSort, partitionEqual, breakPatterns)."""
+    from oracle.oracle import go_sort
+    rng = np.random.default_rng(8831)
+    beyond = 0
+    for trial in range(1200):
+        n = int(rng.integers(0, 400))
+        mode = trial % 6
+        if mode == 0:
+            keys = rng.integers(0, 5, n).astype(float)
+        elif mode == 1:
+            keys = rng.random(n)
+        elif mode == 2:
+            keys = np.sort(rng.integers(0, 50, n)).astype(float)
+        elif mode == 3:
+            keys = np.sort(rng.random(n))[::-1].copy()
+        elif mode == 4:
+            keys = np.concatenate([np.sort(rng.random(n // 2)), rng.integers(0, 3, n - n // 2).astype(float)])
+        else:
+            keys = np.zeros(n)
+        items = list(range(n))
+        so.go_sort_slice(items, lambda i, j: keys[i] < keys[j])
+        assert items == [int(x) for x in go_sort(keys)], (trial, n, mode)
+        assert all(keys[items[i]] <= keys[items[i + 1]] for i in range(n - 1))
+        beyond += n > 12
+    assert beyond > 1000
