@@ -237,6 +237,8 @@ int32_t rsv_timer_stop(rsv_space* s, float* ms);
  * generation ranks that the grown walk of cell.go:86-121 yields are computed in closed form from prefix counts of the
  * entry flags (rsv_pairs.cuh). Same records, ranks and counts as without the flag. */
 #define RSV_FRAME_OWN_RECT 0x80u
+/* Frame flag bits 16..20 are reserved for timing experiments of the candidate kernels (rsv_pairs.cuh); results of a
+ * frame launched with any of them are undefined. Hosts must leave them clear. */
 int32_t rsv_static_invalidate(rsv_space* s);
 /* Registrations held by the cached static grid and number of shapes re-registered per frame (0 / n_shapes while no
  * cache exists). */
