@@ -279,3 +279,56 @@ def test_the_two_restatements_of_gos_pdqsort_agree():
         assert all(keys[items[i]] <= keys[items[i + 1]] for i in range(n - 1))
         beyond += n > 12
     assert beyond > 1000
+
+
+def test_lattice_shapes_agree_bit_for_bit():
+    """Small-integer coordinates: exact tangencies (the det == 0 branch of IntersectionPointsCircle), coincident and
+    collinear edges (det == 0 in IntersectionPointsLine), unit-length axes (the l == 1 exit of Vector.Unit), zero
+    overlaps, distance ties in every sort, shapes sharing vertices."""
+    rng = np.random.default_rng(8841)
+    space = OracleSpace(64, 64, 8, 8)
+    both = []
+    for i in range(70):
+        kind = i % 5
+        cx, cy = (float(v) for v in rng.integers(8, 40, size=2))
+        if kind == 0:
+            spec = ("circle", (cx, cy, float(rng.integers(1, 7))))
+        elif kind == 1:
+            spec = ("rect", (cx, cy, float(2 * rng.integers(1, 6)), float(2 * rng.integers(1, 6))))
+        elif kind == 2:                                   # lattice triangle / quad, clockwise on screen (y down)
+            r = float(rng.integers(2, 7))
+            pts = [-r, -r, r, -r, r, r] if i % 2 else [0.0, -r, r, 0.0, 0.0, r, -r, 0.0]
+            spec = ("poly", (cx, cy, pts))
+        elif kind == 3:
+            dx, dy = (float(v) for v in rng.integers(-8, 9, size=2))
+            spec = ("line", (cx, cy, cx + dx, cy + dy))   # includes zero-length lines
+        else:
+            r = float(rng.integers(2, 6))
+            spec = ("polyline", (cx, cy, [-r, 0.0, 0.0, -r, r, 0.0, r, r]))
+        both.append(add_both(space, spec))
+    stats = dict(pairs=0, hits=0, mtv=0)
+    for a, (ia, sa) in enumerate(both):
+        for b, (ib, sb) in enumerate(both):
+            if a != b:
+                check_pair(space, ia, ib, sa, sb, stats)
+    assert stats["hits"] > 300 and stats["hits"] - stats["mtv"] > 20, stats   # (sets with a zero MTV: calculateMTV said "no overlap")
+    # rays along lattice lines: through vertices, along edges, tangent to circles
+    rays = np.array([[float(a), float(b), float(c), float(d)] for a, b, c, d in rng.integers(0, 48, size=(250, 4))])
+    _, hits = space.linetest(rays, mode="all")
+    got = {(int(hits.a[k]), int(hits.b[k])): k for k in range(len(hits.a))}
+    n_sets = 0
+    for r, ray in enumerate(rays):
+        for ib, sb in both:
+            exp = so.linetest_one((ray[0], ray[1]), (ray[2], ray[3]), sb)
+            k = got.get((r, ib))
+            assert (exp is None) == (k is None), (r, ib)
+            if exp is None:
+                continue
+            mtv, center, cons, key = exp
+            f, c = int(hits.first[k]), int(hits.count[k])
+            assert same(mtv[0], hits.mtv[k][0]) and same(mtv[1], hits.mtv[k][1]) and same(key, hits.dist[k])
+            assert same(center[0], hits.center[k][0]) and same(center[1], hits.center[k][1])
+            assert [tuple(bits(v) for v in row) for row in hits.contacts[f:f + c]] == \
+                   [tuple(bits(v) for v in (p[0], p[1], q[0], q[1])) for p, q in cons]
+            n_sets += 1
+    assert n_sets > 300, n_sets
