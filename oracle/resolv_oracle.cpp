@@ -8,7 +8,11 @@
 // fixtures for this path and no Go toolchain exists in this
 // image, so this restatement has been pinned only against the hand-derived
 // known-answer tests of SURVEY.md §8c (tests/test_oracle_kat.py) and against
-// independent property checks (closed-form candidate predicate, brute force).
+// independent property checks (closed-form candidate predicate, brute force),
+// and cross-checked bit for bit against a second, separately written restatement
+// (oracle/second_opinion.py, tests/test_oracle_second_opinion.py). Two readings
+// of the source that agree are still not the reference: only parity/go run
+// against real resolv pins it.
 //
 // Every function cites the reference file:line (relative to /root/reference)
 // whose algorithm it follows. Data structures mirror the reference on purpose
