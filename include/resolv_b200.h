@@ -231,14 +231,6 @@ int32_t rsv_timer_stop(rsv_space* s, float* ms);
  * shape); the next incremental frame rebuilds it (synchronously). Ignored (full rebuild) for strip-partitioned
  * spaces and when more than half of the shapes are dynamic. */
 #define RSV_FRAME_INCREMENTAL 0x40u
-/* Unfiltered frames only (needs RSV_FRAME_NO_TAG_FILTERS, ignored with RSV_FRAME_ALL_CANDIDATES): a tester visits the
- * entries of its own cell rect instead of the margin-grown rect of SelectTouchingCells (shape.go:220-237) — every
- * shape that can pass the Bounds gate (utils.go:146-173) is registered there — and the candidate count and the
- * generation ranks that the grown walk of cell.go:86-121 yields are computed in closed form from prefix counts of the
- * entry flags (rsv_pairs.cuh). Same records, ranks and counts as without the flag. */
-#define RSV_FRAME_OWN_RECT 0x80u
-/* Frame flag bits 16..20 are reserved for timing experiments of the candidate kernels (rsv_pairs.cuh); results of a
- * frame launched with any of them are undefined. Hosts must leave them clear. */
 int32_t rsv_static_invalidate(rsv_space* s);
 /* Registrations held by the cached static grid and number of shapes re-registered per frame (0 / n_shapes while no
  * cache exists). */

@@ -81,11 +81,6 @@ struct rsv_space {
     int narrow_blocks = 148 * 4;
     int narrow_blocks1 = 148 * 4;
     int pairs_blocks[2] = {148 * 8, 148 * 8};  // k_pairs<false> (no tag filters), k_pairs<true>
-    int pairs_blocks_own[2] = {148 * 8, 148 * 8};  // k_pairs_own<0>, k_pairs_own<1> (RSV_FRAME_OWN_RECT)
-    uint4* ent_pref = nullptr;                 // [cap_entries + 1] prefix counts of the entry flags (RSV_FRAME_OWN_RECT)
-    uint4* pref_tiles = nullptr;
-    uint32_t n_pref_tiles = 0;
-    bool own_default = false;                  // RSV_PAIRS_OWN=1: unfiltered frames take the own-rect path without the flag
     // peer-memory halo transport (rsv_halo_abi.inl)
     void* mailbox = nullptr;            // this device's mailbox
     uint32_t mailbox_cap = 0;
@@ -180,12 +175,6 @@ static int32_t alloc_outputs(rsv_space* s, uint32_t cap_entries, uint32_t cap_pa
         CU(s, cudaMalloc(&d.entries, (size_t)cap_entries * 4));
         CU(s, cudaMalloc(&d.ent_box, (size_t)cap_entries * sizeof(float4)));
         CU(s, cudaMalloc(&d.ent_home, (size_t)cap_entries * sizeof(uint2)));
-        if (s->ent_pref) cudaFree(s->ent_pref);
-        if (s->pref_tiles) cudaFree(s->pref_tiles);
-        s->ent_pref = nullptr; s->pref_tiles = nullptr;
-        s->n_pref_tiles = (uint32_t)(((size_t)cap_entries + 1 + kPrefTile - 1) / kPrefTile);
-        CU(s, cudaMalloc(&s->ent_pref, ((size_t)cap_entries + 1) * sizeof(uint4)));
-        CU(s, cudaMalloc(&s->pref_tiles, (size_t)s->n_pref_tiles * sizeof(uint4)));
         d.cap_entries = cap_entries;
     }
     if (cap_pairs > d.cap_pairs) {
@@ -301,7 +290,6 @@ int32_t rsv_create(const rsv_config* cfg, rsv_space** out) {
     CUC(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&s->side_stream, cudaStreamNonBlocking));
     if (const char* e = getenv("RSV_NO_GRAPH")) s->graphs = !(e[0] && e[0] != '0');
-    if (const char* e = getenv("RSV_PAIRS_OWN")) s->own_default = e[0] && e[0] != '0';
     CUC(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
     CUC(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
     for (auto& sl : s->slot) {
@@ -323,10 +311,6 @@ int32_t rsv_create(const rsv_config* cfg, rsv_space** out) {
         s->pairs_blocks[0] = s->sm_count * occ;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pairs<true>, kPairsBlock, 0) == cudaSuccess && occ > 0)
         s->pairs_blocks[1] = s->sm_count * occ;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pairs_own<0>, kPairsBlock, 0) == cudaSuccess && occ > 0)
-        s->pairs_blocks_own[0] = s->sm_count * occ;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pairs_own<1>, kPairsBlock, 0) == cudaSuccess && occ > 0)
-        s->pairs_blocks_own[1] = s->sm_count * occ;
     CUC(cudaStreamSynchronize(s->stream));
 #undef CUC
     *out = s;
@@ -359,8 +343,6 @@ int32_t rsv_destroy(rsv_space* s) {
         void* sv[] = {s->sg.cell, s->sg.count, s->sg.entries, s->sg.ent_box, s->sg.ent_home, s->sg.ent_tags, s->sg.cell_of, d.dyn_list, d.n_dyn_dev};
         for (void* p : sv) if (p) cudaFree(p);
     }
-    if (s->ent_pref) cudaFree(s->ent_pref);
-    if (s->pref_tiles) cudaFree(s->pref_tiles);
     if (s->mailbox) cudaFree(s->mailbox);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->side_stream) cudaStreamDestroy(s->side_stream);
@@ -513,19 +495,8 @@ static int32_t enqueue_frame(rsv_space* s, const DevView& d, int32_t margin, uin
     }
     mark(RSV_K_PAIRS);
     const bool grid_only = (flags & RSV_FRAME_GRID_ONLY) != 0;
-    const bool own = (flags & RSV_FRAME_OWN_RECT) && (flags & RSV_FRAME_NO_TAG_FILTERS) && !(flags & RSV_FRAME_ALL_CANDIDATES) &&
-                     s->ent_pref && s->pref_tiles;
     if (d.n_shapes && !grid_only) {
-        if (own) {
-            // prefix counts of the entry flags (three small passes), then the own-rect walk with closed-form ranks
-            k_pref_tiles<<<s->n_pref_tiles, kPrefBlock, 0, st>>>(d, s->pref_tiles);
-            k_pref_scan_tiles<<<1, 1024, 0, st>>>(s->pref_tiles, s->n_pref_tiles);
-            k_pref_write<<<s->n_pref_tiles, kPrefBlock, 0, st>>>(d, s->pref_tiles, s->ent_pref);
-            // (0x10000: experiment switch, first form of the batch)
-            if (flags & 0x80000u) k_pairs<false><<<s->pairs_blocks[0], kPairsBlock, 0, st>>>(d, margin, flags);   // (timing: prefix passes + regular walk)
-            else if (flags & 0x10000u) k_pairs_own<0><<<s->pairs_blocks_own[0], kPairsBlock, 0, st>>>(d, s->ent_pref, margin, flags);
-            else k_pairs_own<1><<<s->pairs_blocks_own[1], kPairsBlock, 0, st>>>(d, s->ent_pref, margin, flags);
-        } else if (flags & RSV_FRAME_NO_TAG_FILTERS) k_pairs<false><<<s->pairs_blocks[0], kPairsBlock, 0, st>>>(d, margin, flags);
+        if (flags & RSV_FRAME_NO_TAG_FILTERS) k_pairs<false><<<s->pairs_blocks[0], kPairsBlock, 0, st>>>(d, margin, flags);
         else k_pairs<true><<<s->pairs_blocks[1], kPairsBlock, 0, st>>>(d, margin, flags);
     }
     mark(RSV_K_NARROW);
@@ -554,7 +525,7 @@ static int32_t frame_via_graph(rsv_space* s, const DevView& d, int32_t margin, u
                                rsv_space::FrameGraph& g, cudaStream_t st) {
     rsv_space::FrameGraph::Key key{};
     key.margin = margin; key.flags = flags; key.stream = st; key.n_tiles = s->n_tiles;
-    key.blocks[0] = s->pairs_blocks[0] ^ (s->pairs_blocks[1] << 16) ^ (s->pairs_blocks_own[0] << 8) ^ (s->pairs_blocks_own[1] << 4); key.blocks[1] = s->narrow_blocks; key.blocks[2] = s->narrow_blocks1;
+    key.blocks[0] = s->pairs_blocks[0] ^ (s->pairs_blocks[1] << 16); key.blocks[1] = s->narrow_blocks; key.blocks[2] = s->narrow_blocks1;
     const bool same = g.seen && memcmp(&key, &g.key, sizeof key) == 0 && memcmp(&d, &g.view, sizeof d) == 0;
     if (!same) {
         drop_graph(g);
@@ -663,7 +634,6 @@ int32_t rsv_frame_launch(rsv_space* s, int32_t margin, uint32_t flags) {
     if (margin < 0 || margin > (1 << 20)) return fail(s, RSV_ERR_BAD_ARG, "rsv_frame: margin %d out of range", margin);
     CU(s, cudaSetDevice(s->device));
     // Incremental frames: single-device Spaces only (strip frames rebuild fully: their ghost set changes every frame).
-    if (s->own_default && (flags & RSV_FRAME_NO_TAG_FILTERS)) flags |= RSV_FRAME_OWN_RECT;
     bool inc = (flags & RSV_FRAME_INCREMENTAL) && !s->strip_mode && !s->d.n_ghosts && s->d.n_shapes;
     if (inc && !s->static_valid) {
         const int32_t rc = build_static(s);

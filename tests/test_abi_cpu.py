@@ -60,7 +60,7 @@ def test_flag_constants_match_the_header():
     src = open(os.path.join(ROOT, "include", "resolv_b200.h")).read()
     defs = {m.group(1): int(m.group(2), 16) for m in re.finditer(r"#define\s+(RSV_[A-Z_0-9]+)\s+0x([0-9a-fA-F]+)u", src)}
     for name, val in (("RSV_META_STATIC", _abi.META_STATIC), ("RSV_META_ABSENT", _abi.META_ABSENT), ("RSV_META_TESTER", _abi.META_TESTER),
-                      ("RSV_FRAME_INCREMENTAL", _abi.FRAME_INCREMENTAL), ("RSV_FRAME_OWN_RECT", _abi.FRAME_OWN_RECT), ("RSV_FRAME_GRID_ONLY", _abi.FRAME_GRID_ONLY),
+                      ("RSV_FRAME_INCREMENTAL", _abi.FRAME_INCREMENTAL), ("RSV_FRAME_GRID_ONLY", _abi.FRAME_GRID_ONLY),
                       ("RSV_FRAME_NO_TAG_FILTERS", _abi.FRAME_NO_TAG_FILTERS), ("RSV_FRAME_TESTER_TABLE", _abi.FRAME_TESTER_TABLE),
                       ("RSV_LINE_DDA", _abi.LINE_DDA), ("RSV_LINE_HOME_ONLY", _abi.LINE_HOME_ONLY)):
         assert defs[name] == val, name
