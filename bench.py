@@ -6,9 +6,16 @@ Bounds gate + SAT narrowphase -> compacted IntersectionSet buffer. `value` times
 events on the library's stream (inputs resident); `e2e` times the same frame through the C ABI with HOST buffers:
 H2D of that step's positions from pinned staging + the frame + D2H of the compacted hits/contacts.
 
-N = 1 workload: BASELINE.json configs[1] — 1M axis-aligned 8-32 px rectangles in a 65536x65536 Space with 32x32
-cells. N > 1 (torchrun, one rank per GPU): the world grows with N (N x 1M shapes in a 65536 x N*65536 Space,
-same density), strip-partitioned by cell rows with a per-frame halo exchange (weak scaling).
+Default workload: BASELINE.json configs[2], the configuration the north-star target is quoted on — 1M mixed shapes
+(circles + convex 3-8-gons, tag-filtered, moving every frame: the timed frames cycle through four position sets
+resident in HBM) in a 65536x65536 Space with 32x32 cells. --workload cfg1 (Bouncer), cfg2 (1M rectangles), cfg4
+(4096 platformer Spaces) and cfg5 (16M shapes in a 262144^2 Space + 10M rays) select the other configs. N > 1
+(torchrun, one rank per GPU): cfg2/cfg3 grow the world with N (N x 1M shapes in a 65536 x N*65536 Space, same
+density: weak scaling), cfg5 splits ONE 16M-shape world (strong scaling); both strip-partition by cell rows with a
+per-frame halo exchange.
+
+Before the N = 1 line is printed the frame's counters (testers, R, P, H, K) and the MTV checksum are compared with
+the CPU oracle on the SAME full-size world (`parity_counts_ok`).
 
 --impl reference times the reference's own CPU algorithm (the oracle port: no Go toolchain exists in this image,
 so the real reference cannot run) on the box's host cores over the same workload.
@@ -38,12 +45,17 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--spaces", type=int, default=4096, help="cfg4: independent platformer Spaces in total (split over the GPUs)")
-    ap.add_argument("--shapes", type=int, default=1_000_000, help="shapes per GPU")
+    ap.add_argument("--shapes", type=int, default=0, help="shapes per GPU (cfg2/cfg3; default 1M) or in total (cfg5; default 16M)")
+    ap.add_argument("--rays", type=int, default=10_000_000, help="cfg5: rays of the LineTest sweep")
+    ap.add_argument("--no-parity", action="store_true", help="skip the full-size oracle check of the counters")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-threads", type=int, default=0)
-    return ap.parse_args()
+    a = ap.parse_args()
+    if not a.shapes:
+        a.shapes = {"cfg5": 16_000_000, "cfg1": 294}.get(a.workload, 1_000_000)
+    return a
 
 
 def make_world(args, n_gpus=1):
@@ -51,8 +63,12 @@ def make_world(args, n_gpus=1):
     n = args.shapes * n_gpus
     if n_gpus > 1:
         raise NotImplementedError
+    if args.workload == "cfg1":
+        return worlds.make_bouncer(n)
     if args.workload == "cfg2":
         return worlds.make_rects(n)
+    if args.workload == "cfg5":
+        return worlds.make_cfg5(n)
     return worlds.make_mixed(n)
 
 
@@ -61,9 +77,15 @@ def workload_name(args, n_gpus):
         return (f"configs[3]: {args.spaces} independent platformer Spaces (640x360, 16x16 cells, ~500 static tiles + 32 dynamic bodies each; "
                 "IntersectionTest with SelectTouchingCells(4).ByTags(SolidWall) per body + 4 LineTest probes per body against ByTags(Platform)), "
                 f"{args.spaces // max(n_gpus, 1)} Spaces per GPU, no communication")
+    if args.workload == "cfg1":
+        return (f"configs[0]: Bouncer-style world, 640x480 Space, 16x16 cells, 6 walls + {args.shapes} bouncers (circles r=8 / 16x16 rectangles), "
+                "one IntersectionTest(SelectTouchingCells(1).FilterShapes()) per bouncer per frame")
+    if args.workload == "cfg5":
+        return (f"configs[4]: {args.shapes} mixed shapes (as configs[2]) in ONE 262144x262144 Space, 32x32 cells, margin 1, "
+                f"strips of {8192 // max(n_gpus, 1)} cell rows per GPU, moving every frame; + LineTest sweep of {args.rays} rays (16-512 px)")
     base = {"cfg2": "configs[1]: axis-aligned 8-32 px rectangles, 65536x65536 Space, 32x32 cells, margin 1, no filter",
-            "cfg3": "configs[2]: mixed circles + convex 3-8-gons, tag-filtered, 65536x65536 Space, 32x32 cells, margin 1"}[args.workload]
-    return f"{args.shapes * n_gpus} shapes, {base}"
+            "cfg3": "configs[2]: mixed circles + convex 3-8-gons, tag-filtered (ByTags), 65536x65536 Space, 32x32 cells, margin 1"}[args.workload]
+    return f"{args.shapes * n_gpus} shapes, {base}, moving every frame (pos += vel, reflected at the borders)"
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -129,7 +151,7 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def kernel_algorithmic_bytes(c, w, n_cells):
+def kernel_algorithmic_bytes(c, w, n_cells, filters=False):
     """Algorithmic bytes each kernel must move per launch: every datum counted once per kernel
     (caches assumed perfect within a kernel), gathers counted at the size of the datum, atomics as 8 B (RMW)."""
     N, R, G, K = c.n_shapes, c.n_entries, c.n_gated, c.n_contacts
@@ -140,10 +162,11 @@ def kernel_algorithmic_bytes(c, w, n_cells):
         "bounds": N * (16 + 32 + 4) + N * (32 + 16 + 4) + 8 * R,   # pos, local AABB, meta -> AABB, cell rect, table reset; one RED per entry
         "scan": 8 * C1,                                    # counters in, offsets out
         "scatter": N * (16 + 4) + 8 * R + 4 * R,           # cell rect, meta; cursor RMW per entry; entry word out
-        "cellsort": 4 * C1 + 8 * R + (4 * R + 32 * N + 16 * R),    # offsets, entries in/out; k_entboxes: entries, each AABB once, float boxes out
-        "pairs": 4 * R + N * (4 + 16 + 4 + 16) + 4 * C1 + (4 + 16) * R + 64 * G + 16 * G,
-        # entry scan; per tester home entry + float box, meta, cell rect; every cell offset once; every entry + float box once;
-        # exact fp64 gate on the survivors (two AABBs); record out
+        "cellsort": 4 * C1 + 8 * R + (4 * R + 32 * N + 16 * R) + (16 * R if filters else 0) + 8 * N,
+        # offsets, entries in/out; k_entboxes: entries, each AABB once, float boxes out (+ tags in, per-entry tags out), home records
+        "pairs": 4 * C1 + (4 + 16) * R + (8 * R + 16 * N if filters else 0) + 8 * N + 16 * G,
+        # every cell offset once; every entry word + float box once (+ per-entry tags and per-tester masks in filtered
+        # frames); home record per tester; record out
         "narrow": G * (16 + 2 * (16 + 4 + 4 + 32)) + G * 2 * vb + 32 * G + 32 * K,
         # record in; pos, meta, vertex offset / radius, AABB of both; vertices of both; hit record out; contacts out
     }
@@ -177,6 +200,46 @@ def bind_to_gpu_cpus(index):
         return None
 
 
+N_POS_PAGES = 4   # position sets resident in HBM that the timed frames cycle through (per-frame motion)
+
+
+def oracle_space(w):
+    """The CPU oracle's Space holding world `w` (test infrastructure: only the checker / baseline legs call this)."""
+    from oracle import oracle as orc
+    sp = orc.OracleSpace(w.space_w, w.space_h, w.cell_w, w.cell_h)
+    sp.add_bulk(w.kind, w.pos0, w.pos, w.radius, w.vert_off, w.nv, w.verts, w.closed, w.tags)
+    return sp
+
+
+def parity_counts(sp, w, pos, dev):
+    """Full-size check of one frame against the oracle on the same world and positions: testers, registrations R,
+    candidates P, hits H, contacts K must be EQUAL; the sum of all MTVs (a checksum of the narrowphase output, summed
+    in different orders on the two sides) must agree to 1e-9 per hit. `dev` = (counts, mtv_sum) of the device frame."""
+    from oracle import oracle as orc
+    sp.set_positions(pos)
+    fc, _, _ = sp.frame(w.margin, tester=w.tester, use_any=w.use_any, any_mask=w.any_mask, none_mask=w.none_mask, record=False,
+                        threads=orc.hardware_threads() or 1)
+    n_cells = sp.width_cells * sp.height_cells
+    import ctypes as C
+    cnt = np.zeros(n_cells, dtype=np.uint32)
+    R = int(sp.L.orc_cells_dump(sp.h, cnt.ctypes.data_as(C.POINTER(C.c_uint32)), None, 0))
+    c, msum = dev
+    want = {"n_testers": int(fc.testers), "n_entries": R, "n_candidates": int(fc.candidates), "n_hits": int(fc.hits), "n_contacts": int(fc.contacts)}
+    got = {k: int(getattr(c, k)) for k in want}
+    tol = 1e-9 * max(int(fc.hits), 1)
+    ok = got == want and abs(msum[0] - fc.mtv_sum_x) <= tol and abs(msum[1] - fc.mtv_sum_y) <= tol
+    return ok, {"device": got, "oracle": want, "mtv_sum_device": [float(msum[0]), float(msum[1])],
+                "mtv_sum_oracle": [float(fc.mtv_sum_x), float(fc.mtv_sum_y)]}
+
+
+def device_frame_with_checksum(ds, margin, flags):
+    from resolv_b200 import _abi
+    c = ds.frame(margin, flags | _abi.FRAME_DOWNLOAD, grow=True)
+    hits, _ = ds.results()
+    live = (hits["count_rank"] & 0x7f) > 0
+    return c, hits["mtv"][live].sum(axis=0) if live.any() else np.zeros(2)
+
+
 def run_b200(args):
     import torch
     rank = int(os.environ.get("RANK", "0"))
@@ -191,6 +254,8 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         if args.workload == "cfg4":
             return run_cfg4(args, rank, world_size, local_rank)
+        if args.workload == "cfg1":
+            raise SystemExit("cfg1 is a 300-shape world: it does not shard (replicas only); run it with --gpus 1")
         from resolv_b200 import strips
         return strips.run_bench(args, rank, world_size, local_rank)
     if args.workload == "cfg4":
@@ -200,12 +265,13 @@ def run_b200(args):
     K, W = args.steps, max(args.warmup, 3)
     w = make_world(args)
     N = w.n
-    ds = space_for_world(w, device=local_rank)
+    n_rays = args.rays if args.workload == "cfg5" else 0
+    ds = space_for_world(w, device=local_rank, max_rays=min(n_rays, 2_000_000))
     margin = w.margin
     base_flags = 0 if (w.use_any.any() or w.none_mask.any()) else _abi.FRAME_NO_TAG_FILTERS
     # positions for every step (per-frame motion), precomputed outside the timed regions
-    frames = []
-    for f in range(min(K + W, 8)):
+    frames = [w.pos.copy()]
+    for f in range(7):
         worlds.advance(w, f + 1)
         frames.append(w.pos.copy())
     # ---- warm-up (also sizes the output buffers)
@@ -214,31 +280,50 @@ def run_b200(args):
         ds.set_positions(frames[i % len(frames)])
         c = ds.frame(margin, _abi.FRAME_DOWNLOAD | base_flags, grow=True)
     n_cells = ds.grid_w * ds.rows * ds.n_spaces
-    # warm the exact call pattern of the timed loop too (same flags: the launch sequence is captured into a CUDA graph
-    # per result slot on the second identical call and replayed from the third)
-    for i in range(max(W, 6)):
+    # ---- parity at full size: the frames of position sets 0 and 1 against the oracle on the same world
+    ds.device_pos_pages(frames[:N_POS_PAGES])
+    parity = None
+    if not args.no_parity:
+        sp = oracle_space(w)
+        checks = []
+        for pg in (0, 1):
+            ds.select_pos_page(pg)
+            checks.append(parity_counts(sp, w, frames[pg], device_frame_with_checksum(ds, margin, base_flags)))
+        parity = {"ok": all(ok for ok, _ in checks), "frames": [d for _, d in checks]}
+        del sp
+    # warm the exact call pattern of the timed loop too (same flags and position pages: the launch sequence is captured
+    # into a CUDA graph per (result slot, position page) on the second identical call and replayed from the third)
+    for i in range(3 * N_POS_PAGES):
+        ds.select_pos_page(i % N_POS_PAGES)
         ds.frame_launch(margin, base_flags)
     ds.frame_finish()
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    # ---- value: K frames back to back, inputs resident in HBM, CUDA events on the library's stream
+    # ---- value: K frames back to back, inputs resident in HBM (frame i reads position set i % 4: every frame sees
+    # moved shapes), CUDA events on the library's stream
     ds.sync()
     torch.cuda.synchronize()
     ds.timer_start()
     for i in range(K):
+        ds.select_pos_page(i % N_POS_PAGES)
         ds.frame_launch(margin, base_flags)
     ms = ds.timer_stop()
     c = ds.frame_finish()
     torch.cuda.synchronize()
     ms_per_step = ms / K
-    # ---- per-kernel durations over another K frames (events between kernels)
+    # ---- per-kernel durations over another K frames (events between kernels), same position cycle
     acc = {k: 0.0 for k in _abi.KERNEL_NAMES}
+    cs = {k: 0.0 for k in ("n_entries", "n_candidates", "n_gated", "n_hits", "n_contacts")}
     for i in range(K):
-        ds.frame(margin, _abi.FRAME_TIMING | base_flags)
+        ds.select_pos_page(i % N_POS_PAGES)
+        ck = ds.frame(margin, _abi.FRAME_TIMING | base_flags)
         t = ds.timing()
         for k in acc:
             acc[k] += t[k] / K
+        for k in cs:
+            cs[k] += int(getattr(ck, k)) / K
+    ds.select_pos_page(0)
     # ---- e2e: host buffers, H2D of the step's positions + frame + D2H of hits/contacts, every step.
     # (a) sequential: commit -> frame -> download, one step at a time (latency of a frame through the API)
     e2e_seq = 0.0
@@ -268,49 +353,80 @@ def run_b200(args):
     ce = ds.frame_finish()
     e2e_t = time.perf_counter() - t0
     clocks = sampler.stop()
+    rays = ray_sweep(args, ds, w) if n_rays else None
 
     peak, peak_src = measured_peaks()
-    algo = kernel_algorithmic_bytes(c, w, n_cells)
+
+    class Avg:   # mean counters of the timed frames (the position cycle changes them slightly from frame to frame)
+        n_shapes = N
+        n_entries, n_candidates, n_gated, n_hits, n_contacts = (cs[k] for k in ("n_entries", "n_candidates", "n_gated", "n_hits", "n_contacts"))
+    algo = kernel_algorithmic_bytes(Avg, w, n_cells, filters=not (base_flags & _abi.FRAME_NO_TAG_FILTERS))
     dom = max(acc, key=lambda k: acc[k])
-    traffic = None   # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    traffic, traffic_src = None, None   # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_kernel_traffic.json")))
-        if args.workload == "cfg2" and args.shapes == 1_000_000:
-            traffic = tj["dram_bytes_per_launch"].get(dom)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_kernel_traffic.json")))
+        if args.workload in tj and args.shapes == 1_000_000:
+            traffic = tj[args.workload]["dram_bytes_per_launch"].get(dom)
+            traffic_src = tj[args.workload].get("source")
     except Exception:
         pass
     achieved = algo[dom] / (acc[dom] * 1e-6) / 1e9 if acc[dom] > 0 else 0.0
     frame_bytes = sum(algo.values())
+    sfb = survey_frame_bytes(Avg, w, n_cells)
     out = {
         "metric": METRIC, "value": N / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": workload_name(args, 1), "l2": "inputs + per-frame intermediates (~0.3 GB) exceed the 126 MB L2",
-                   "margin": margin},
-        "pair_tests_per_sec": int(c.n_candidates) / (ms_per_step * 1e-3),
+                   "margin": margin, "motion": f"timed frames cycle through {N_POS_PAGES} position sets resident in HBM"},
+        "pair_tests_per_sec": cs["n_candidates"] / (ms_per_step * 1e-3),
         "counts": c.as_dict(),
+        "parity_counts_ok": None if parity is None else parity["ok"],
+        "parity": parity,
         "clocks": clocks,
         "e2e": {"value": N * K / e2e_t, "unit": UNIT, "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K,
                 "ms_per_step": 1e3 * e2e_t / K, "mode": "pipelined: two frames in flight, D2H of step i-1 overlaps H2D + kernels of step i",
                 "sequential_ms_per_step": 1e3 * e2e_seq / K, "sequential_value": N * K / e2e_seq},
-        # kernels of this library launched inside the timed `value` region: 11 per frame (k_clear, k_bounds, k_scan,
-        # k_scatter, k_cellsort, k_entboxes, k_pairs, k_bin, k_bin_scatter, k_narrow<0>, k_narrow<1>), replayed as one
-        # CUDA graph per frame once the launch parameters repeat
-        "gpu_launches": K * 11,
+        # kernels of this library launched inside the timed `value` region, per frame: k_clear, k_bounds, k_scan, k_scatter,
+        # k_cellsort, k_entboxes, k_pairs_tile, k_pairs (leftover list), k_bin, k_bin_scatter, k_narrow<0>, k_narrow<1>;
+        # replayed as one CUDA graph per frame once the launch parameters repeat
+        "gpu_launches": K * 12,
         "kernels_us": {k: round(v, 2) for k, v in acc.items()},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": int(algo[dom]), "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                     "algorithmic_bytes": int(algo[dom]), "peak_source": peak_src,
+                     "kernel_fracs": {k: round(algo[k] / (acc[k] * 1e-6) / 1e9 / peak, 4) for k in acc if acc[k] > 0},
                      "frame_algorithmic_bytes": int(frame_bytes),
                      "frame_frac": frame_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
-                     "survey_frame_bytes": int(survey_frame_bytes(c, w, n_cells)),
-                     "survey_frame_frac": survey_frame_bytes(c, w, n_cells) / (ms_per_step * 1e-3) / 1e9 / peak},
+                     "survey_frame_bytes": int(sfb),
+                     "survey_frame_frac": sfb / (ms_per_step * 1e-3) / 1e9 / peak},
     }
+    if rays:
+        out["rays"] = rays
     if old_affinity:
         os.sched_setaffinity(0, old_affinity)   # the CPU baseline may use every core of the box
+    ds.close()
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, budget_s=20.0)
-    ds.close()
     return out
+
+
+def ray_sweep(args, ds, w, batch=2_000_000):
+    """cfg5's LineTest sweep on the grid of the last frame: args.rays segments (start uniform, direction uniform,
+    16-512 px), in batches, DDA iterator; device time of the line kernel (CUDA events on the library's stream)."""
+    from resolv_b200 import _abi, worlds
+    tot_us, hits, cands, done = 0.0, 0, 0, 0
+    ds.frame(w.margin, _abi.FRAME_GRID_ONLY)
+    while done < args.rays:
+        n = min(batch, args.rays - done)
+        rays = worlds.make_rays(n, 20265 + done, w.space_w, w.space_h)
+        rc = ds.linetest(rays, flags=_abi.LINE_DDA)
+        tot_us += rc.kernel_us
+        hits += int(rc.n_hits)
+        cands += int(rc.n_candidates)
+        done += n
+    return {"n_rays": done, "iterator": "DDA", "kernel_ms": tot_us / 1e3, "rays_per_sec": done / (tot_us * 1e-6),
+            "n_candidates": cands, "n_hits": hits}
 
 
 def run_cfg4(args, rank, world, local_rank):
@@ -424,46 +540,78 @@ def run_cfg4(args, rank, world, local_rank):
 
 # ----------------------------------------------------------------------------------------------------------------
 def cpu_baseline(args, budget_s=20.0, steps=None, warmup=1):
-    """The reference's algorithm (oracle port) on the host cores: a step = SetPosition on every shape (grid
-    maintenance, shape.go:239-242) single-threaded as in the reference + every tester's IntersectionTest on
-    `threads` threads with thread-local scratch."""
+    """The reference's algorithm (oracle port; the Go reference itself cannot run here: no Go toolchain) on the host
+    cores. A step = SetPosition on every shape (grid maintenance, shape.go:239-242; single-threaded as in the
+    reference) + every tester's IntersectionTest, (i) on ONE thread and (ii) on all hardware threads with
+    thread-local scratch. `value` is (ii); (i) is `single_thread_value`."""
     from oracle import oracle as orc
     from resolv_b200 import worlds
     threads = args.cpu_threads or orc.hardware_threads() or 1
-    # bounded sample: the same world generator at a shape count whose frame takes ~1 s on one core
-    n = min(args.shapes, 250_000 if steps is None else args.shapes)
-    a2 = argparse.Namespace(**vars(args))
-    a2.shapes = n
-    w = make_world(a2)
-    if n != args.shapes:   # keep the density of the full workload: shrink the Space with sqrt(n / N)
-        side = int(round(65536 * (n / args.shapes) ** 0.5 / 32)) * 32
-        w = (worlds.make_rects(n, space=side) if args.workload == "cfg2" else worlds.make_mixed(n, space=side))
-    sp = orc.OracleSpace(w.space_w, w.space_h, w.cell_w, w.cell_h)
-    sp.add_bulk(w.kind, w.pos0, w.pos, w.radius, w.vert_off, w.nv, w.verts, w.closed, w.tags)
-    kw = dict(tester=w.tester, use_any=w.use_any, any_mask=w.any_mask, none_mask=w.none_mask, record=False, threads=threads)
-    t_total, done, cands = 0.0, 0, 0
-    t_begin = time.perf_counter()
+    if args.workload == "cfg1":
+        return cpu_baseline_cfg1(args, frames=1000 if steps is None else max(steps, 1) * 50)
+    # bounded sample: the full world up to 1M shapes; larger worlds (cfg5) are sampled at 1M shapes of the same density
+    n = min(args.shapes, 1_000_000)
+    if n == args.shapes:
+        w = make_world(args)
+    else:
+        side = int(round((262144 if args.workload == "cfg5" else 65536) * (n / args.shapes) ** 0.5 / 32)) * 32
+        w = worlds.make_rects(n, space=side) if args.workload == "cfg2" else worlds.make_mixed(n, space=side)
+    sp = oracle_space(w)
+    kw = dict(tester=w.tester, use_any=w.use_any, any_mask=w.any_mask, none_mask=w.none_mask, record=False)
+    res = {}
     f = 0
-    while True:
-        worlds.advance(w, f + 1)
-        t0 = time.perf_counter()
-        sp.set_positions(w.pos)
-        fc, _, _ = sp.frame(w.margin, **kw)
-        dt = time.perf_counter() - t0
-        f += 1
-        if f > warmup:
+    for label, th, max_frames, share in (("nt", threads, 10 if steps is None else steps, 0.6), ("1t", 1, 2, 0.4)):
+        t_total, done, cands, t_set = 0.0, 0, 0, 0.0
+        t_begin = time.perf_counter()
+        wu = warmup if label == "nt" else 0
+        while True:
+            worlds.advance(w, f + 1)
+            t0 = time.perf_counter()
+            sp.set_positions(w.pos)
+            t1 = time.perf_counter()
+            fc, _, _ = sp.frame(w.margin, threads=th, **kw)
+            dt = time.perf_counter() - t0
+            f += 1
+            if wu > 0:
+                wu -= 1
+                continue
             t_total += dt
+            t_set += t1 - t0
             done += 1
             cands += fc.candidates
-        if steps is not None and done >= steps:
-            break
-        if steps is None and (time.perf_counter() - t_begin > budget_s or done >= 10):
-            break
-    return {"value": n * done / t_total, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{done} full frames (SetPosition on every shape, 1 thread, + all IntersectionTests, {threads} threads) "
-                      f"of the same generator at {n} shapes and the workload's density; oracle port of the Go reference "
-                      f"(no Go toolchain in this image)",
-            "pair_tests_per_sec": cands / t_total, "ms_per_step": 1e3 * t_total / done}
+            if done >= max_frames or (steps is None and time.perf_counter() - t_begin > budget_s * share):
+                break
+        res[label] = dict(value=n * done / t_total, ms=1e3 * t_total / done, frames=done, pts=cands / t_total, set_ms=1e3 * t_set / done)
+    nt, st = res["nt"], res["1t"]
+    return {"value": nt["value"], "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{nt['frames']} full frames of the workload's own generator at {n} shapes"
+                      + ("" if n == args.shapes else f" (a {n}-shape world of the same density stands in for the {args.shapes}-shape one)")
+                      + f": SetPosition on every shape (1 thread, {nt['set_ms']:.0f} ms) + all IntersectionTests on {threads} threads; "
+                      f"single thread: {st['frames']} frames; oracle port of the Go reference (no Go toolchain in this image)",
+            "pair_tests_per_sec": nt["pts"], "ms_per_step": nt["ms"],
+            "single_thread_value": st["value"], "single_thread_ms_per_step": st["ms"], "single_thread_cores": 1}
+
+
+def cpu_baseline_cfg1(args, frames=1000):
+    """configs[0], the reference's own CPU-runnable case: the Bouncer demo's update loop (examples/worldBouncer.go:139-174)
+    headless on ONE thread (the reference is single-goroutine) — reference-sequential (what the demo does) and the
+    two-phase / frozen form a batched frame computes."""
+    w = make_world(args)
+    dyn = np.nonzero(w.tester)[0]
+    out = {}
+    for label, seq in (("sequential", True), ("two_phase", False)):
+        sp = oracle_space(w)
+        vel = np.ascontiguousarray(w.vel[dyn].copy())
+        sp.bouncer_run(dyn, vel, 50, seq)   # warm-up
+        fc = sp.bouncer_run(dyn, vel, frames, seq)
+        out[label] = dict(value=w.n * frames / fc.seconds, ms=1e3 * fc.seconds / frames, pts=fc.candidates / fc.seconds)
+    return {"value": out["two_phase"]["value"], "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{frames} frames of the Bouncer update loop (gravity, clamp, move, IntersectionTest, reflect, move by the summed MTV) over "
+                      f"{len(dyn)} bouncers + 6 walls, one thread; `value` is the two-phase / frozen form, `sequential_value` the demo's "
+                      "shape-by-shape form; oracle port of the Go reference (no Go toolchain in this image)",
+            "pair_tests_per_sec": out["two_phase"]["pts"], "ms_per_step": out["two_phase"]["ms"],
+            "sequential_value": out["sequential"]["value"], "sequential_ms_per_step": out["sequential"]["ms"],
+            "single_thread_value": out["two_phase"]["value"], "single_thread_ms_per_step": out["two_phase"]["ms"], "single_thread_cores": 1}
 
 
 _CFG4 = {}
@@ -548,11 +696,12 @@ def run_reference(args):
                                                 "note": "throughput is measured on the bounded sample described in cpu_baseline.sample"},
                 "pair_tests_per_sec": cb["pair_tests_per_sec"], "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    # bounded: at most ~250k shapes per step so that K+W steps end within a few minutes on any host
+    # bounded: at most 1M shapes per step so that K+W steps end within a few minutes on any host
     cb = cpu_baseline(args, steps=K, warmup=W)
     n_gpus = args.gpus
     return {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
-            "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "strong" if args.workload == "cfg5" else "weak",
+            "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": {"workload": workload_name(args, max(n_gpus, 1)), "margin": 1,
                                             "note": "throughput per frame is measured on the bounded sample described in cpu_baseline.sample"},
             "pair_tests_per_sec": cb["pair_tests_per_sec"], "cpu_baseline": cb,

@@ -175,6 +175,15 @@ int32_t rsv_commit(rsv_space* s, uint32_t which_mask, uint32_t lo, uint32_t hi);
  * rsv_commit_pos_page) still reads the other. Only RSV_BUF_POS has pages. */
 void* rsv_staging_page(rsv_space* s, int32_t which, int32_t page, size_t* bytes);
 int32_t rsv_commit_pos_page(rsv_space* s, int32_t page, uint32_t lo, uint32_t hi);
+/* Device-resident position pages. A host that already holds several position sets in HBM (frames prepared ahead, or a
+ * device-side integrator writing the next positions while the current frame runs) switches between them without a
+ * copy: rsv_pos_pages allocates pages 1..n_pages-1 (page 0 is RSV_BUF_POS's device buffer; new pages start as copies
+ * of it), rsv_pos_page_upload fills device page `device_page` from pinned staging page 0 / 1, rsv_pos_page_select
+ * makes every later frame, halo pack and line test read positions from that page. The write side of
+ * ShapeBase.update (shape.go:239-242) for hosts that move shapes in bulk. */
+int32_t rsv_pos_pages(rsv_space* s, int32_t n_pages);
+int32_t rsv_pos_page_upload(rsv_space* s, int32_t device_page, int32_t staging_page, uint32_t lo, uint32_t hi);
+int32_t rsv_pos_page_select(rsv_space* s, int32_t device_page);
 /* Device address of buffer `which` (for device-side producers such as the multi-GPU halo unpack). */
 void* rsv_device_buffer(rsv_space* s, int32_t which);
 
@@ -290,7 +299,8 @@ int32_t rsv_ray_results_view(rsv_space* s, rsv_ray_results* out);
  * shapes that reach into each other's stored rows (NCCL send/recv of the buffers filled by rsv_halo_pack), then
  * every device runs rsv_frame: a shape is a tester only on the device whose home rows contain its first cell row,
  * so each ordered pair is tested exactly once and results land where the tester lives. */
-#define RSV_OVF_GHOSTS 0x20u
+#define RSV_OVF_GHOSTS 0x20u /* more halo records than the ghost list or a mailbox buffer holds: results are incomplete;
+                                grow max_ghosts / the mailbox capacity (rsv_strip_setup, rsv_halo_mailbox) and run the frame again */
 /* Launch every kernel of this space on an externally owned CUDA stream (e.g. the stream the host framework
  * issues its NCCL calls on) so that pack -> exchange -> apply -> frame need no host synchronisation. NULL
  * restores the library's own stream. */
@@ -331,6 +341,17 @@ int32_t rsv_halo_connect(rsv_space* s, void* up_mailbox, void* dn_mailbox);
 #define RSV_HALO_RECV 2u
 int32_t rsv_halo_exchange(rsv_space* s, int32_t up_row_max, int32_t dn_row_min, int32_t slot_off_up, int32_t slot_off_dn,
                           uint32_t phases);
+
+/* The frame of a strip-partitioned space with the halo exchange folded into it (peer-memory transport; the space must
+ * be connected with rsv_halo_connect). Replaces rsv_halo_exchange + rsv_frame_launch on every device of the chain:
+ * the owned shapes are registered and, in the same pass, the ones reaching a neighbour's stored rows are stored
+ * straight into that neighbour's mailbox (RSV_HALO_SEND half); the device then waits — on the device, epochs and flags
+ * never touch the host — for both neighbours' batches, applies them, registers the ghosts and runs the rest of the
+ * frame (RSV_HALO_RECV half). One fixed launch sequence per frame, replayed as one CUDA graph; finish with
+ * rsv_frame_finish as usual. phases as for rsv_halo_exchange (a process driving several spaces on ONE device enqueues
+ * all SEND halves before any RECV half). After rsv_halo_connect a space uses either this call or rsv_halo_exchange. */
+int32_t rsv_strip_frame_launch(rsv_space* s, int32_t margin, uint32_t flags, int32_t up_row_max, int32_t dn_row_min,
+                               int32_t slot_off_up, int32_t slot_off_dn, uint32_t phases);
 
 /* ---- parity / debug dumps --------------------------------------------------------------------------------- */
 /* Cell membership after the last frame: cell_end[c] (exclusive end offset of cell c in `entries`, cells row-major,

@@ -90,6 +90,7 @@ def lib():
         getattr(L, n).restype = P(f64)
         getattr(L, n).argtypes = [vp]
     L.orc_go_sort_f64.argtypes = [P(f64), i32, P(i32)]
+    L.orc_bouncer_run.argtypes = [vp, P(i32), i32, P(f64), i32, i32, P(FrameCounts)]
     L.orc_hardware_threads.restype = i32
     _lib = L
     return L
@@ -252,6 +253,15 @@ class OracleSpace:
         cands = dict(a=_arr(L.orc_cand_a(h), P, np.uint32), b=_arr(L.orc_cand_b(h), P, np.uint32),
                      rank=_arr(L.orc_cand_rank(h), P, np.uint32), dist=_arr(L.orc_cand_dist(h), P, np.float64))
         return fc, cands, self._hits()
+
+    def bouncer_run(self, dyn, vel, frames, sequential=True):
+        """Config 1: the Bouncer demo's update loop (examples/worldBouncer.go:139-174) for `frames` frames over the shapes
+        `dyn` with velocities `vel` (updated in place). sequential=False: the two-phase / frozen form."""
+        dyn = np.ascontiguousarray(dyn, dtype=np.int32)
+        assert vel.dtype == np.float64 and vel.flags.c_contiguous and vel.size == 2 * len(dyn)
+        fc = FrameCounts()
+        self.L.orc_bouncer_run(self.h, _ptr(dyn, C.c_int), len(dyn), _ptr(vel, C.c_double), frames, int(sequential), C.byref(fc))
+        return fc
 
     def linetest(self, rays, use_any=None, any_mask=None, none_mask=None, record=True, threads=1, mode="all",
                  candidates=None):

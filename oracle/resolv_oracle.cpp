@@ -1052,6 +1052,64 @@ void orc_frame(void* p, int margin, const uint8_t* tester, const uint8_t* use_an
     if (out) *out = tot;
 }
 
+// Config 1: the Bouncer demo's update loop headless (examples/worldBouncer.go:139-174), for
+// `frames` frames over the dynamic shapes dyn[0..n_dyn) with velocities vel[2*i] (in/out):
+//   Movement.Y += 0.25; Movement = Movement.ClampMagnitude(8); MoveVec(Movement);
+//   IntersectionTest{SelectTouchingCells(1).FilterShapes(), OnIntersect: Movement = Movement.Reflect(normal0).Scale(0.9);
+//                    totalMTV += MTV; return true};  MoveVec(totalMTV)
+// sequential != 0: shape by shape, each seeing the moves of the ones before it (what the demo does).
+// sequential == 0: the two-phase / frozen form (all moves, all tests against the frozen world, all MTV moves) — the
+// form a batched frame (rsv_frame) computes.
+void orc_bouncer_run(void* p, const int* dyn, int n_dyn, double* vel, int frames, int sequential, OrcFrameCounts* out) {
+    OrcWorld* w = (OrcWorld*)p;
+    Scratch sc;
+    OrcFrameCounts c{};
+    std::vector<Vec> total((size_t)n_dyn);
+    auto t0 = std::chrono::steady_clock::now();
+    auto pre = [&](int k) {
+        Vec m{vel[2 * k], vel[2 * k + 1]};
+        m.y += 0.25;
+        if (vmag(m) > 8) m = vscale(vunit(m), 8);                  // vector.go:122-127
+        vel[2 * k] = m.x; vel[2 * k + 1] = m.y;
+        w->all[dyn[k]]->move(m.x, m.y);
+    };
+    auto test = [&](int k) {
+        Shape& self = *w->all[dyn[k]];
+        Vec tot{0, 0};
+        c.testers++;
+        intersection_test(
+            self, select_touching_cells(self, 1), TagFilter{}, sc,
+            [&](const IntersectionSet& set, double) {
+                Vec m{vel[2 * k], vel[2 * k + 1]};
+                Vec nn = vunit(set.intersections[0].normal);        // vector.go:197-200
+                m = vscale(vsub(m, vscale(nn, 2 * vdot(nn, m))), 0.9);
+                vel[2 * k] = m.x; vel[2 * k + 1] = m.y;
+                tot = vadd(tot, set.mtv);
+                c.hits++;
+                c.contacts += (long long)set.intersections.size();
+                c.mtv_sum_x += set.mtv.x; c.mtv_sum_y += set.mtv.y;
+                return true;
+            },
+            [&](const std::vector<Scratch::Possible>& poss) { c.candidates += (long long)poss.size(); });
+        return tot;
+    };
+    for (int f = 0; f < frames; f++) {
+        if (sequential) {
+            for (int k = 0; k < n_dyn; k++) {
+                pre(k);
+                Vec t = test(k);
+                w->all[dyn[k]]->move(t.x, t.y);
+            }
+        } else {
+            for (int k = 0; k < n_dyn; k++) pre(k);
+            for (int k = 0; k < n_dyn; k++) total[(size_t)k] = test(k);
+            for (int k = 0; k < n_dyn; k++) w->all[dyn[k]]->move(total[(size_t)k].x, total[(size_t)k].y);
+        }
+    }
+    c.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (out) *out = c;
+}
+
 long long orc_num_candidates(void* p) { return (long long)((OrcWorld*)p)->candA.size(); }
 long long orc_num_hits(void* p) { return (long long)((OrcWorld*)p)->hitA.size(); }
 long long orc_num_contacts(void* p) { return (long long)((OrcWorld*)p)->contacts.size() / 4; }

@@ -34,7 +34,8 @@ ABI_SYMBOLS = [
     "rsv_linetest_finish", "rsv_ray_staging", "rsv_ray_reserve", "rsv_ray_results_view", "rsv_tester_table",
     "rsv_set_stream", "rsv_strip_setup", "rsv_halo_pack", "rsv_halo_apply", "rsv_staging_page", "rsv_commit_pos_page",
     "rsv_halo_mailbox", "rsv_ipc_export", "rsv_ipc_open", "rsv_ipc_close", "rsv_halo_connect", "rsv_halo_exchange",
-    "rsv_static_invalidate", "rsv_static_info",
+    "rsv_static_invalidate", "rsv_static_info", "rsv_pos_pages", "rsv_pos_page_upload", "rsv_pos_page_select",
+    "rsv_strip_frame_launch",
 ]
 
 
@@ -144,6 +145,14 @@ def load():
     L.rsv_staging_page.argtypes = [vp, i32, i32, C.POINTER(C.c_size_t)]
     L.rsv_commit_pos_page.restype = i32
     L.rsv_commit_pos_page.argtypes = [vp, i32, u32, u32]
+    L.rsv_pos_pages.restype = i32
+    L.rsv_pos_pages.argtypes = [vp, i32]
+    L.rsv_pos_page_upload.restype = i32
+    L.rsv_pos_page_upload.argtypes = [vp, i32, i32, u32, u32]
+    L.rsv_pos_page_select.restype = i32
+    L.rsv_pos_page_select.argtypes = [vp, i32]
+    L.rsv_strip_frame_launch.restype = i32
+    L.rsv_strip_frame_launch.argtypes = [vp, i32, u32, i32, i32, i32, i32, u32]
     L.rsv_tester_table.restype = i32
     L.rsv_tester_table.argtypes = [vp, vp, vp, u64]
     L.rsv_debug_cells.restype = i32
@@ -255,6 +264,18 @@ class DeviceSpace:
     def commit_pos_page(self, page, lo=0, hi=None):
         self._check(self.L.rsv_commit_pos_page(self.h, page, lo, self.n_shapes if hi is None else hi))
 
+    def device_pos_pages(self, positions):
+        """Uploads every (N,2) array of `positions` into its own device position page (at most 4); frames then pick
+        one with select_pos_page(i) — per-frame motion with all inputs resident in HBM."""
+        self._check(self.L.rsv_pos_pages(self.h, len(positions)))
+        for i, p in enumerate(positions):
+            self.buf[BUF_POS][:2 * self.n_shapes] = np.asarray(p, dtype=np.float64).reshape(-1)
+            self._check(self.L.rsv_pos_page_upload(self.h, i, 0, 0, self.n_shapes))
+            self.sync()
+
+    def select_pos_page(self, page):
+        self._check(self.L.rsv_pos_page_select(self.h, page))
+
     def sync(self):
         self._check(self.L.rsv_sync(self.h))
 
@@ -298,8 +319,13 @@ class DeviceSpace:
 
     def frame_finish(self):
         c = Counts()
-        self._check(self.L.rsv_frame_finish(self.h, C.byref(c)))
+        rc = self.L.rsv_frame_finish(self.h, C.byref(c))
+        self._last_counts = c      # (filled even when the frame overflowed: the counters say what to reserve)
+        self._check(rc)
         return c
+
+    def last_counts(self):
+        return self._last_counts
 
     def results(self):
         """(hits, contacts) structured numpy views of the pinned mirrors (valid until the next frame)."""

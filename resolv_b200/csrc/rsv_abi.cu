@@ -60,12 +60,14 @@ struct rsv_space {
     // captured launch sequence of a frame, one per result slot (frame_via_graph)
     struct FrameGraph {
         struct Key {
-            int32_t margin; uint32_t flags; cudaStream_t stream; uint32_t n_tiles; int blocks[3];
+            int32_t margin; uint32_t flags; cudaStream_t stream; uint32_t n_tiles; int blocks[3]; HaloArgs halo;
         } key{};
         DevView view{};
         cudaGraphExec_t exec = nullptr;
         int seen = 0;
-    } graph[2];
+    } graph[2][4];   // per result slot and device position page
+    void* pos_page[4] = {};   // device position pages (rsv_pos_pages); page 0 is dev_buf[RSV_BUF_POS]
+    int n_pos_pages = 1, cur_pos_page = 0;
     bool graphs = true;  // RSV_NO_GRAPH=1 in the environment turns graph replay off
     cudaStream_t copy_stream = nullptr;
     cudaStream_t side_stream = nullptr;  // second narrowphase kernel
@@ -167,14 +169,14 @@ static int32_t alloc_outputs(rsv_space* s, uint32_t cap_entries, uint32_t cap_pa
         if (d.ent_home) cudaFree(d.ent_home);
         if (d.ent_tags) cudaFree(d.ent_tags);
         d.entries = nullptr; d.ent_box = nullptr; d.ent_home = nullptr; d.ent_tags = nullptr; d.cap_entries = 0;
-        CU(s, cudaMalloc(&d.ent_tags, (size_t)cap_entries * 8));
+        CU(s, cudaMalloc(&d.ent_tags, ((size_t)cap_entries + 8) * 8));
         if (d.multi) cudaFree(d.multi);
         d.multi = nullptr;
         d.cap_multi = cap_entries + 1;  // (incremental frames list every cell that received a dynamic registration)
         CU(s, cudaMalloc(&d.multi, (size_t)d.cap_multi * 4));
-        CU(s, cudaMalloc(&d.entries, (size_t)cap_entries * 4));
-        CU(s, cudaMalloc(&d.ent_box, (size_t)cap_entries * sizeof(float4)));
-        CU(s, cudaMalloc(&d.ent_home, (size_t)cap_entries * sizeof(uint2)));
+        CU(s, cudaMalloc(&d.entries, ((size_t)cap_entries + 8) * 4));
+        CU(s, cudaMalloc(&d.ent_box, ((size_t)cap_entries + 8) * sizeof(float4)));
+        CU(s, cudaMalloc(&d.ent_home, ((size_t)cap_entries + 8) * sizeof(uint2)));
         d.cap_entries = cap_entries;
     }
     if (cap_pairs > d.cap_pairs) {
@@ -279,7 +281,7 @@ int32_t rsv_create(const rsv_config* cfg, rsv_space** out) {
     CUC(cudaMalloc(&d.aabb, (size_t)N * sizeof(Box)));
     CUC(cudaMalloc(&d.crect, (size_t)N * sizeof(int4)));
     s->n_tiles = (uint32_t)((n_cells + 1 + kScanTile - 1) / kScanTile);
-    CUC(cudaMalloc(&d.cell, ((size_t)s->n_tiles * kScanTile) * 4));
+    CUC(cudaMalloc(&d.cell, ((size_t)s->n_tiles * kScanTile + 16) * 4));   // (+16: 16-byte-aligned row windows of the tile kernel)
     CUC(cudaMemsetAsync(d.cell, 0, ((size_t)s->n_tiles * kScanTile) * 4, s->stream));
     CUC(cudaMalloc(&d.tile_state, (size_t)s->n_tiles * 8));
     CUC(cudaMalloc(&d.tester_start, (size_t)N * 4));
@@ -307,6 +309,7 @@ int32_t rsv_create(const rsv_config* cfg, rsv_space** out) {
         s->narrow_blocks = s->sm_count * occ;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_narrow<1>, kNarrowBlock, 0) == cudaSuccess && occ > 0)
         s->narrow_blocks1 = s->sm_count * occ;
+
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pairs<false>, kPairsBlock, 0) == cudaSuccess && occ > 0)
         s->pairs_blocks[0] = s->sm_count * occ;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pairs<true>, kPairsBlock, 0) == cudaSuccess && occ > 0)
@@ -338,11 +341,12 @@ int32_t rsv_destroy(rsv_space* s) {
         if (sl.h_contacts) cudaFreeHost(sl.h_contacts);
         if (sl.ev_done) cudaEventDestroy(sl.ev_done);
     }
-    for (auto& g : s->graph) drop_graph(g);
+    for (auto& gs : s->graph) for (auto& g : gs) drop_graph(g);
     {
         void* sv[] = {s->sg.cell, s->sg.count, s->sg.entries, s->sg.ent_box, s->sg.ent_home, s->sg.ent_tags, s->sg.cell_of, d.dyn_list, d.n_dyn_dev};
         for (void* p : sv) if (p) cudaFree(p);
     }
+    for (int p = 1; p < 4; p++) if (s->pos_page[p]) cudaFree(s->pos_page[p]);
     if (s->mailbox) cudaFree(s->mailbox);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->side_stream) cudaStreamDestroy(s->side_stream);
@@ -406,6 +410,40 @@ int32_t rsv_commit_pos_page(rsv_space* s, int32_t page, uint32_t lo, uint32_t hi
     return RSV_OK;
 }
 
+// Device-resident position pages: a host (or a device-side integrator) that keeps several position sets in HBM selects
+// which one the next frames read, without any copy. Page 0 is RSV_BUF_POS's device buffer.
+int32_t rsv_pos_pages(rsv_space* s, int32_t n_pages) {
+    if (!s || n_pages < 1 || n_pages > 4) return RSV_ERR_BAD_ARG;
+    CU(s, cudaSetDevice(s->device));
+    s->pos_page[0] = s->dev_buf[RSV_BUF_POS];
+    for (int p = 1; p < n_pages; p++)
+        if (!s->pos_page[p]) {
+            CU(s, cudaMalloc(&s->pos_page[p], s->buf_bytes[RSV_BUF_POS]));
+            CU(s, cudaMemcpyAsync(s->pos_page[p], s->dev_buf[RSV_BUF_POS], s->buf_bytes[RSV_BUF_POS], cudaMemcpyDeviceToDevice, s->stream));
+        }
+    if (n_pages > s->n_pos_pages) s->n_pos_pages = n_pages;
+    return RSV_OK;
+}
+
+int32_t rsv_pos_page_upload(rsv_space* s, int32_t device_page, int32_t staging_page, uint32_t lo, uint32_t hi) {
+    if (!s || device_page < 0 || device_page >= s->n_pos_pages || staging_page < 0 || staging_page > 1) return RSV_ERR_BAD_ARG;
+    if (staging_page == 1 && !s->host_pos_page1) return fail(s, RSV_ERR_BAD_ARG, "rsv_pos_page_upload: staging page 1 was never requested");
+    if (hi > s->n_shapes) hi = s->n_shapes;
+    if (lo >= hi) return RSV_OK;
+    CU(s, cudaSetDevice(s->device));
+    void* dst = device_page ? s->pos_page[device_page] : s->dev_buf[RSV_BUF_POS];
+    const char* src = (const char*)(staging_page ? s->host_pos_page1 : s->host_buf[RSV_BUF_POS]);
+    CU(s, cudaMemcpyAsync((char*)dst + (size_t)lo * 16, src + (size_t)lo * 16, (size_t)(hi - lo) * 16, cudaMemcpyHostToDevice, s->stream));
+    return RSV_OK;
+}
+
+int32_t rsv_pos_page_select(rsv_space* s, int32_t device_page) {
+    if (!s || device_page < 0 || device_page >= s->n_pos_pages) return RSV_ERR_BAD_ARG;
+    s->cur_pos_page = device_page;
+    s->d.pos = (const double2*)(device_page ? s->pos_page[device_page] : s->dev_buf[RSV_BUF_POS]);
+    return RSV_OK;
+}
+
 void* rsv_device_buffer(rsv_space* s, int32_t which) {
     if (!s || which < 0 || which >= RSV_BUF_COUNT) return nullptr;
     return s->dev_buf[which];
@@ -460,23 +498,38 @@ static inline int blocks_for(uint32_t n, int block, int cap) {
 }
 
 // The kernels of one frame plus the counter read-back, enqueued on `st` (directly, or into a stream capture).
+// halo != nullptr: the frame of a strip-partitioned space with the halo exchange folded in (rsv_strip_frame_launch);
+// phases selects the part before the wait on the neighbours (RSV_HALO_SEND) and / or the part after it (RSV_HALO_RECV).
 static int32_t enqueue_frame(rsv_space* s, const DevView& d, int32_t margin, uint32_t flags, rsv_space::FrameSlot& sl,
-                             cudaStream_t st, bool timing) {
+                             cudaStream_t st, bool timing, const HaloArgs* halo = nullptr, uint32_t phases = 3u) {
     auto mark = [&](int k) { if (timing) cudaEventRecord(s->ev[k], st); };
-    mark(RSV_K_CLEAR);
-    {
-        // the cell array is allocated in whole scan tiles, so it can be cleared 16 B at a time past n_cells + 1
-        const uint32_t n4 = (uint32_t)(((size_t)d.n_cells + 1 + 3) / 4);
-        k_clear<<<blocks_for(n4, kGridBlock, s->sm_count * 8), kGridBlock, 0, st>>>(
-            reinterpret_cast<uint4*>(d.cell), n4, d.tile_state, s->n_tiles, reinterpret_cast<uint32_t*>(d.ctr),
-            (uint32_t)(offsetof(Counters, ray_hit_cursor) / 4));
-    }
-    mark(RSV_K_BOUNDS);
     const int gcap = s->sm_count * 8;
     const bool inc = d.subset == kSubsetDynamic;   // incremental frame: only dyn_list is re-registered
-    const uint32_t max_items = inc ? d.n_dyn : (d.own_hi - d.own_lo) + (d.n_ghosts ? d.cap_ghosts : 0u);
-    // (an incremental frame launches k_bounds even without dynamic shapes: it carries the static counts over)
-    if (d.n_shapes) k_bounds<<<blocks_for(max_items, kGridBlock, gcap), kGridBlock, 0, st>>>(d, margin);
+    const uint32_t max_items = inc ? d.n_dyn : (d.own_hi - d.own_lo) + ((d.n_ghosts && !halo) ? d.cap_ghosts : 0u);
+    if (phases & RSV_HALO_SEND) {
+        mark(RSV_K_CLEAR);
+        {
+            // the cell array is allocated in whole scan tiles, so it can be cleared 16 B at a time past n_cells + 1
+            const uint32_t n4 = (uint32_t)(((size_t)d.n_cells + 1 + 3) / 4);
+            k_clear<<<blocks_for(n4, kGridBlock, s->sm_count * 8), kGridBlock, 0, st>>>(
+                reinterpret_cast<uint4*>(d.cell), n4, d.tile_state, s->n_tiles, reinterpret_cast<uint32_t*>(d.ctr),
+                (uint32_t)(offsetof(Counters, ray_hit_cursor) / 4));
+        }
+        mark(RSV_K_BOUNDS);
+        // (an incremental frame launches k_bounds even without dynamic shapes: it carries the static counts over)
+        if (halo) {
+            DevView v = d;
+            v.part = kPartOwned;
+            k_bounds<true><<<blocks_for(std::max<uint32_t>(max_items, 1u), kGridBlock, gcap), kGridBlock, 0, st>>>(v, margin, *halo);
+        } else if (d.n_shapes) {
+            k_bounds<false><<<blocks_for(max_items, kGridBlock, gcap), kGridBlock, 0, st>>>(d, margin, HaloArgs{});
+        }
+    }
+    if (!(phases & RSV_HALO_RECV)) {
+        CU(s, cudaGetLastError());
+        return RSV_OK;
+    }
+    if (halo) k_halo_apply_bounds<<<dim3(blocks_for(halo->cap, kGridBlock, s->sm_count), 2), kGridBlock, 0, st>>>(d, margin, *halo);
     mark(RSV_K_SCAN);
     const int scan_blocks = (d.n_cells + 1 + kScanTile - 1) / kScanTile;
     if (inc) k_scan<true><<<scan_blocks, kScanBlock, 0, st>>>(d.cell, d.n_cells + 1, d.tile_state, &d.ctr->scan_ticket, d.multi,
@@ -485,7 +538,8 @@ static int32_t enqueue_frame(rsv_space* s, const DevView& d, int32_t margin, uin
                                                            &d.ctr->n_multi, d.cap_multi, nullptr);
     mark(RSV_K_SCATTER);
     if (inc && d.static_entries) k_static_place<<<blocks_for(d.static_entries, kGridBlock, gcap), kGridBlock, 0, st>>>(d, s->sg, flags);
-    if (d.n_shapes && max_items) k_scatter<<<blocks_for(max_items, kGridBlock, gcap), kGridBlock, 0, st>>>(d);
+    const uint32_t scatter_items = max_items + (halo ? d.cap_ghosts : 0u);   // (k_scatter walks own + ghosts)
+    if (d.n_shapes && scatter_items) k_scatter<<<blocks_for(scatter_items, kGridBlock, gcap), kGridBlock, 0, st>>>(d);
     mark(RSV_K_CELLSORT);
     if (inc) {
         k_cellfix<<<blocks_for(std::min<uint32_t>(d.n_cells, 4u * std::max<uint32_t>(d.n_dyn, 1u)), kGridBlock, gcap), kGridBlock, 0, st>>>(d, flags);
@@ -522,10 +576,11 @@ static int32_t enqueue_frame(rsv_space* s, const DevView& d, int32_t margin, uin
 // reference's own examples are a few hundred shapes) are bound by launch overhead, not by the kernels.
 // Returns 1 if the frame was submitted as a graph, 0 if the caller has to launch directly, < 0 on error.
 static int32_t frame_via_graph(rsv_space* s, const DevView& d, int32_t margin, uint32_t flags, rsv_space::FrameSlot& sl,
-                               rsv_space::FrameGraph& g, cudaStream_t st) {
+                               rsv_space::FrameGraph& g, cudaStream_t st, const HaloArgs* halo = nullptr) {
     rsv_space::FrameGraph::Key key{};
     key.margin = margin; key.flags = flags; key.stream = st; key.n_tiles = s->n_tiles;
-    key.blocks[0] = s->pairs_blocks[0] ^ (s->pairs_blocks[1] << 16); key.blocks[1] = s->narrow_blocks; key.blocks[2] = s->narrow_blocks1;
+    if (halo) key.halo = *halo;   // (flags carries bit 31 for fused strip frames)
+    key.blocks[0] = s->pairs_blocks[0] ^ (s->pairs_blocks[1] << 16);
     const bool same = g.seen && memcmp(&key, &g.key, sizeof key) == 0 && memcmp(&d, &g.view, sizeof d) == 0;
     if (!same) {
         drop_graph(g);
@@ -541,7 +596,7 @@ static int32_t frame_via_graph(rsv_space* s, const DevView& d, int32_t margin, u
             s->graphs = false;
             return 0;
         }
-        const int32_t rc = enqueue_frame(s, d, margin, flags, sl, st, false);
+        const int32_t rc = enqueue_frame(s, d, margin, flags & 0x7fffffffu, sl, st, false, halo, 3u);
         const cudaError_t e = cudaStreamEndCapture(st, &graph);
         if (rc != RSV_OK || e != cudaSuccess || !graph || cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) {
             cudaGetLastError();
@@ -568,7 +623,7 @@ static int32_t build_static(rsv_space* s) {
     CU(s, cudaMemsetAsync(sg.count, 0, cell_bytes, st));
     if (!d.dyn_list) CU(s, cudaMalloc(&d.dyn_list, (size_t)s->cfg.max_shapes * 4));
     if (!d.n_dyn_dev) CU(s, cudaMalloc(&d.n_dyn_dev, 4));
-    for (auto& g : s->graph) drop_graph(g);
+    for (auto& gs : s->graph) for (auto& g : gs) drop_graph(g);
     DevView v = d;
     v.subset = kSubsetStaticBuild;
     v.cell = sg.cell;
@@ -579,7 +634,7 @@ static int32_t build_static(rsv_space* s) {
                                                                      (uint32_t)(offsetof(Counters, ray_hit_cursor) / 4));
     CU(s, cudaMemsetAsync(d.n_dyn_dev, 0, 4, st));
     const uint32_t items = d.own_hi - d.own_lo;
-    if (items) k_bounds<<<blocks_for(items, kGridBlock, gcap), kGridBlock, 0, st>>>(v, 0);
+    if (items) k_bounds<false><<<blocks_for(items, kGridBlock, gcap), kGridBlock, 0, st>>>(v, 0, HaloArgs{});
     Counters hc_local{};   // (pageable on purpose: the pinned mirrors may belong to a frame / ray batch in flight)
     Counters* hc = &hc_local;
     uint32_t n_dyn = 0;
@@ -654,7 +709,7 @@ int32_t rsv_frame_launch(rsv_space* s, int32_t margin, uint32_t flags) {
     int32_t submitted = 0;
     // (timed frames record events between the kernels; the ghost count of strip frames is read on the device)
     if (s->graphs && !timing) {
-        submitted = frame_via_graph(s, d, margin, flags, sl, s->graph[s->launch_slot], st);
+        submitted = frame_via_graph(s, d, margin, flags, sl, s->graph[s->launch_slot][s->cur_pos_page], st);
         if (submitted < 0) return submitted;
     }
     if (!submitted) {

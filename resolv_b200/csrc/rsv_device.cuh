@@ -71,6 +71,7 @@ struct DevView {
     int32_t home_lo, home_hi;        // rows whose shapes run IntersectionTest here (default [0, H))
     // ---- incremental grid (rsv_grid.cuh, RSV_FRAME_INCREMENTAL): which shapes the grid kernels of this launch visit
     uint32_t subset;                 // kSubsetAll, kSubsetStaticBuild or kSubsetDynamic
+    uint32_t part;                   // kPartAll, or kPartOwned for the k_bounds launch of a frame with a fused halo exchange
     uint32_t* dyn_list;              // slots that are re-registered every frame (not RSV_META_STATIC, or static orphan testers)
     uint32_t* n_dyn_dev;             // device-side length of dyn_list (written by the static build)
     uint32_t n_dyn;                  // its value on the host (valid in kSubsetDynamic frames)
@@ -116,6 +117,7 @@ __device__ __forceinline__ float4 float_box(const Box& b) {
 }
 
 constexpr uint32_t kSubsetAll = 0u, kSubsetStaticBuild = 1u, kSubsetDynamic = 2u;
+constexpr uint32_t kPartAll = 0u, kPartOwned = 1u;
 
 constexpr int kClampCell = 1 << 30;
 

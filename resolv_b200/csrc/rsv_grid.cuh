@@ -29,6 +29,7 @@ __device__ __forceinline__ bool clamp_rect(const DevView& d, int4 r, int& x0, in
 // In the per-frame part of an incremental frame (kSubsetDynamic) they are the slots of dyn_list instead.
 __device__ __forceinline__ uint32_t n_items(const DevView& d) {
     if (d.subset == kSubsetDynamic) return d.n_dyn;
+    if (d.part == kPartOwned) return d.own_hi - d.own_lo;   // (the ghosts are registered by k_halo_apply_bounds)
     uint32_t ng = d.n_ghosts ? min(*d.n_ghosts, d.cap_ghosts) : 0u;
     return (d.own_hi - d.own_lo) + ng;
 }
@@ -68,27 +69,39 @@ __device__ __forceinline__ void warp_big_rects(bool big, int x0, int y0, int x1,
     }
 }
 
+// Halo exchange folded into the grid kernels (strip partitioning over peer memory, rsv_halo.cuh): k_bounds<true> packs
+// the owned shapes that reach a neighbour's stored rows straight into that neighbour's mailbox while it registers
+// them, its last block publishes the counts and raises the neighbours' `ready` flags; k_halo_apply_bounds then waits
+// for this device's own flags, applies the received positions and registers the ghosts. Epochs live on the device, so
+// a strip frame is one fixed launch sequence (one CUDA graph).
+struct HaloRec;
+struct HaloMailboxHeader;
+struct HaloArgs {
+    HaloMailboxHeader* mine;
+    HaloRec* dst[2][2];          // [side: 0 upper, 1 lower neighbour][epoch parity]: where our records go (peer memory)
+    uint32_t* peer_ready[2][2];  // the neighbours' `ready` words for data from our side
+    uint32_t* peer_done[2][2];   // the neighbours' `done` words for our side
+    const HaloRec* recv[2][2];   // our own receive buffers
+    int32_t up_row_max, dn_row_min;
+    int32_t slot_off[2];
+    uint32_t cap;
+};
+
 // Bounds() -> toCellSpace() per shape, and the per-cell registration counts.
 //   Circle.Bounds                circle.go:33-39      (pos +- r  ==  pos + (-r, +r), exact in IEEE)
 //   ConvexPolygon.Bounds         convexPolygon.go:158-161 (cached local bounds + position)
 //   Bounds.toCellSpace           utils.go:90-98
 //   addToTouchingCells           shape.go:191-214     (cells outside the grid are skipped)
-__global__ void __launch_bounds__(kGridBlock) k_bounds(DevView d, int margin) {
-    unsigned long long my_entries = 0, my_testers = 0;
-    const uint32_t n = n_items(d);
-    if (blockIdx.x == 0 && threadIdx.x == 0 && d.n_ghosts && *d.n_ghosts > d.cap_ghosts)
-        atomicOr(&d.ctr->overflow, RSV_OVF_GHOSTS);
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t j0 = blockIdx.x * blockDim.x; j0 < n; j0 += stride) {  // (warp-uniform trip count)
-        const uint32_t j = j0 + threadIdx.x;
-        bool big = false, listed = false;
-        int x0 = 0, y0 = 0, x1 = -1, y1 = -1;
-        uint32_t base = 0, islot = 0;
-        if (j < n) {
-        const uint32_t i = item_slot(d, j);
-        islot = i;
+// One shape per lane; the whole warp must call this together (shapes covering many cells are registered cooperatively).
+// Returns the shape's cell rect in `r_out` (for the halo pack).
+__device__ __forceinline__ void bounds_item(const DevView& d, int margin, bool valid, uint32_t i, double2 p, unsigned long long& my_entries,
+                                            unsigned long long& my_testers, int4& r_out, uint32_t& meta_out) {
+    bool big = false, listed = false;
+    int x0 = 0, y0 = 0, x1 = -1, y1 = -1;
+    uint32_t base = 0;
+    if (valid) {
         uint32_t meta = __ldg(d.meta + i);
-        double2 p = __ldg(d.pos + i);
+        meta_out = meta;
         Box lb = load_box(d.laabb + i);
         Box b{dadd(lb.minx, p.x), dadd(lb.miny, p.y), dadd(lb.maxx, p.x), dadd(lb.maxy, p.y)};
         int4 r;
@@ -97,6 +110,7 @@ __global__ void __launch_bounds__(kGridBlock) k_bounds(DevView d, int margin) {
         r.z = cell_of(b.maxx, d.cell_w);
         r.w = cell_of(b.maxy, d.cell_h);
         if (meta & RSV_META_ABSENT) r = make_int4(kClampCell, kClampCell, -kClampCell, -kClampCell);
+        r_out = r;
         store_box(d.aabb + i, b);
         d.crect[i] = r;
         d.tester_count[i] = 0;
@@ -129,19 +143,21 @@ __global__ void __launch_bounds__(kGridBlock) k_bounds(DevView d, int margin) {
                     for (int x = x0; x <= x1; x++) atomicAdd(d.cell + row + x + 1, 1u);
                 }
         }
-        }
-        warp_big_rects(big, x0, y0, x1, y1, 0u, base, [&](int x, int y, int, int, int, int, uint32_t, uint32_t bb) {
-            atomicAdd(d.cell + bb + (uint32_t)(y - d.row_lo) * (uint32_t)d.W + x + 1, 1u);
-        });
-        if (d.subset == kSubsetStaticBuild) {   // warp-aggregated append keeps dyn_list nearly in slot order
-            const uint32_t lm = __ballot_sync(0xffffffffu, listed);
-            uint32_t b0 = 0;
-            if ((threadIdx.x & 31) == 0 && lm) b0 = atomicAdd(d.n_dyn_dev, (uint32_t)__popc(lm));
-            b0 = __shfl_sync(0xffffffffu, b0, 0);
-            if (listed) d.dyn_list[b0 + __popc(lm & ((1u << (threadIdx.x & 31)) - 1u))] = islot;
-        }
     }
-    // block reduction of the two statistics -> one atomic each per block
+    warp_big_rects(big, x0, y0, x1, y1, 0u, base, [&](int x, int y, int, int, int, int, uint32_t, uint32_t bb) {
+        atomicAdd(d.cell + bb + (uint32_t)(y - d.row_lo) * (uint32_t)d.W + x + 1, 1u);
+    });
+    if (d.subset == kSubsetStaticBuild) {   // warp-aggregated append keeps dyn_list nearly in slot order
+        const uint32_t lm = __ballot_sync(0xffffffffu, listed);
+        uint32_t b0 = 0;
+        if ((threadIdx.x & 31) == 0 && lm) b0 = atomicAdd(d.n_dyn_dev, (uint32_t)__popc(lm));
+        b0 = __shfl_sync(0xffffffffu, b0, 0);
+        if (listed) d.dyn_list[b0 + __popc(lm & ((1u << (threadIdx.x & 31)) - 1u))] = i;
+    }
+}
+
+// Block reduction of the two statistics -> one atomic each per block.
+__device__ __forceinline__ void bounds_stats(const DevView& d, unsigned long long my_entries, unsigned long long my_testers, bool add_static) {
     for (int o = 16; o > 0; o >>= 1) {
         my_entries += __shfl_down_sync(0xffffffffu, my_entries, o);
         my_testers += __shfl_down_sync(0xffffffffu, my_testers, o);
@@ -153,13 +169,19 @@ __global__ void __launch_bounds__(kGridBlock) k_bounds(DevView d, int margin) {
     if (threadIdx.x == 0) {
         unsigned long long e = 0, t = 0;
         for (int w = 0; w < kGridBlock / 32; w++) { e += s_e[w]; t += s_t[w]; }
-        if (d.subset == kSubsetDynamic && blockIdx.x == 0) { e += d.static_entries; t += d.static_testers; }
+        if (add_static) { e += d.static_entries; t += d.static_testers; }
         if (e) atomicAdd(&d.ctr->n_entries, e);
         if (t) atomicAdd(&d.ctr->n_testers, t);
     }
 }
 
-// Zeroes everything a frame accumulates into: per-cell counters, scan tile states, frame counters. One launch.
+__device__ __forceinline__ uint32_t ld_vol_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+__device__ __forceinline__ void st_vol_u32(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
+
+template <bool HALO>
+__global__ void __launch_bounds__(kGridBlock) k_bounds(DevView d, int margin, HaloArgs h);
+
+// Zeroes everything a frame accumulates into:// Zeroes everything a frame accumulates into: per-cell counters, scan tile states, frame counters. One launch.
 __global__ void __launch_bounds__(kGridBlock) k_clear(uint4* __restrict__ cell4, uint32_t n4, unsigned long long* __restrict__ state,
                                                       uint32_t n_tiles, uint32_t* __restrict__ ctr_words, uint32_t n_ctr_words) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;

@@ -47,6 +47,8 @@ __global__ void __launch_bounds__(kGridBlock) k_halo_pack(DevView d, int up_row_
 // Writes received positions into the resident position buffer and appends the slots to this frame's ghost list.
 __global__ void __launch_bounds__(kGridBlock) k_halo_apply(DevView d, const HaloRec* recv, int slot_off, uint32_t cap) {
     const uint32_t n = min(recv[0].slot, cap);
+    // (n_ghosts[1]: sticky "a batch exceeded its buffer" word, turned into RSV_OVF_GHOSTS by the next frame's k_bounds)
+    if (recv[0].slot > cap && blockIdx.x == 0 && threadIdx.x == 0) d.n_ghosts[1] = recv[0].slot;
     double2* pos = const_cast<double2*>(d.pos);
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const HaloRec r = recv[1 + k];
@@ -69,7 +71,11 @@ struct HaloMailboxHeader {
     uint32_t done[2][2];   // [side][parity]: last epoch the neighbour on `side` has finished applying out of ITS [.][parity] buffer
     uint32_t cap;
     uint32_t cnt[2];       // append counters of the running pack (records go straight into the neighbours' mailboxes)
-    uint32_t pad[5];
+    uint32_t epoch;        // fused path (k_bounds<true>): exchanges this device has published, kept on the device
+    uint32_t pack_done;    // blocks of the running k_bounds<true> that have finished
+    uint32_t apply_done;   // blocks of the running k_halo_apply_bounds that have finished
+    uint32_t sticky_ovf;   // a received batch exceeded the mailbox capacity (reported by the next frame: RSV_OVF_GHOSTS)
+    uint32_t pad[1];
 };
 static_assert(sizeof(HaloMailboxHeader) == 64, "mailbox header layout");
 
@@ -95,11 +101,14 @@ __global__ void k_halo_publish(uint32_t* cnt, HaloRec* peer_up, HaloRec* peer_dn
 
 // k_halo_apply for both sides in one launch (blockIdx.y = side).
 __global__ void __launch_bounds__(kGridBlock) k_halo_apply2(DevView d, const HaloRec* recv_up, int off_up, const HaloRec* recv_dn,
-                                                            int off_dn, uint32_t cap) {
+                                                            int off_dn, uint32_t cap, uint32_t* sticky_ovf) {
     const HaloRec* recv = blockIdx.y ? recv_dn : recv_up;
     const int slot_off = blockIdx.y ? off_dn : off_up;
     if (!recv) return;
-    const uint32_t n = min(*reinterpret_cast<const volatile uint32_t*>(&recv[0].slot), cap);
+    const uint32_t n_pub = *reinterpret_cast<const volatile uint32_t*>(&recv[0].slot);
+    const uint32_t n = min(n_pub, cap);
+    // the sender dropped the records past the capacity: the frame that follows must not pass for complete
+    if (n_pub > cap && blockIdx.x == 0 && threadIdx.x == 0 && sticky_ovf) *sticky_ovf = n_pub;
     double2* pos = const_cast<double2*>(d.pos);
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const HaloRec r = recv[1 + k];
@@ -117,6 +126,125 @@ __global__ void k_halo_signal(uint32_t* flag_a, uint32_t* flag_b, uint32_t value
     if (flag_a) *reinterpret_cast<volatile uint32_t*>(flag_a) = value;
     if (flag_b) *reinterpret_cast<volatile uint32_t*>(flag_b) = value;
     __threadfence_system();
+}
+
+// ---- fused path: pack inside k_bounds, apply + ghost registration in one kernel, epochs and waits on the device -----
+// k_bounds over the frame's shapes. HALO: the launch covers the OWNED shapes only (DevView::part == kPartOwned) and
+// appends every owned shape whose cell rows reach a neighbour's stored rows (first row <= up_row_max / last row >=
+// dn_row_min) to that neighbour's mailbox; the last block to finish publishes counts + `ready` flags and advances the
+// device-side epoch.
+template <bool HALO>
+__global__ void __launch_bounds__(kGridBlock) k_bounds(DevView d, int margin, HaloArgs h) {
+    unsigned long long my_entries = 0, my_testers = 0;
+    const uint32_t n = n_items(d);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && d.n_ghosts) {
+        if (!HALO && d.part == kPartAll && *d.n_ghosts > d.cap_ghosts) atomicOr(&d.ctr->overflow, RSV_OVF_GHOSTS);
+        if (d.n_ghosts[1]) { atomicOr(&d.ctr->overflow, RSV_OVF_GHOSTS); d.n_ghosts[1] = 0u; }
+    }
+    uint32_t e = 0;
+    int par = 0;
+    if (HALO) {
+        e = ld_vol_u32(&h.mine->epoch) + 1u;
+        par = (int)(e & 1u);
+        // the neighbours must have applied what we stored into this parity two epochs ago
+        if (threadIdx.x == 0 && e > 2u)
+            for (int side = 0; side < 2; side++)
+                if (h.dst[side][par])
+                    while (ld_vol_u32(&h.mine->done[side][par]) < e - 2u) {}
+        __syncthreads();
+    }
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t j0 = blockIdx.x * blockDim.x; j0 < n; j0 += stride) {  // (warp-uniform trip count)
+        const uint32_t j = j0 + threadIdx.x;
+        const bool valid = j < n;
+        const uint32_t i = valid ? item_slot(d, j) : 0u;
+        double2 p = make_double2(0.0, 0.0);
+        if (valid) p = __ldg(d.pos + i);
+        int4 r = make_int4(0, 0, -1, -1);
+        uint32_t meta = RSV_META_ABSENT;
+        bounds_item(d, margin, valid, i, p, my_entries, my_testers, r, meta);
+        if (HALO && valid && !(meta & RSV_META_ABSENT)) {
+            if (h.dst[0][par] && r.y <= h.up_row_max) {
+                const uint32_t k = atomicAdd(&h.mine->cnt[0], 1u);
+                if (k < h.cap) h.dst[0][par][1 + k] = HaloRec{i, 0u, p.x, p.y};
+            }
+            if (h.dst[1][par] && r.w >= h.dn_row_min) {
+                const uint32_t k = atomicAdd(&h.mine->cnt[1], 1u);
+                if (k < h.cap) h.dst[1][par][1 + k] = HaloRec{i, 0u, p.x, p.y};
+            }
+        }
+    }
+    bounds_stats(d, my_entries, my_testers, d.subset == kSubsetDynamic && blockIdx.x == 0);
+    if (HALO) {
+        __threadfence_system();   // this block's records are in the neighbours' memory before it counts as finished
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(&h.mine->pack_done, 1u) == gridDim.x - 1u) {
+            __threadfence_system();
+            const uint32_t c0 = atomicAdd(&h.mine->cnt[0], 0u), c1 = atomicAdd(&h.mine->cnt[1], 0u);
+            if (h.dst[0][par]) st_vol_u32(&h.dst[0][par][0].slot, c0);
+            if (h.dst[1][par]) st_vol_u32(&h.dst[1][par][0].slot, c1);
+            __threadfence_system();
+            if (h.peer_ready[0][par]) st_vol_u32(h.peer_ready[0][par], e);
+            if (h.peer_ready[1][par]) st_vol_u32(h.peer_ready[1][par], e);
+            h.mine->cnt[0] = 0u; h.mine->cnt[1] = 0u; h.mine->pack_done = 0u;
+            *d.n_ghosts = 0u;
+            st_vol_u32(&h.mine->epoch, e);
+            __threadfence();
+        }
+    }
+}
+
+// Waits (on the device) for both neighbours' batches of the current epoch, writes the received positions, appends the
+// slots to this frame's ghost list and registers the ghosts exactly as k_bounds registers owned shapes. The last block
+// tells the neighbours that their buffers of this parity are free again. blockIdx.y = side.
+__global__ void __launch_bounds__(kGridBlock) k_halo_apply_bounds(DevView d, int margin, HaloArgs h) {
+    unsigned long long my_entries = 0, my_testers = 0;
+    const uint32_t e = ld_vol_u32(&h.mine->epoch);
+    const int par = (int)(e & 1u), side = (int)blockIdx.y;
+    const HaloRec* recv = h.recv[side][par];
+    uint32_t n = 0;
+    if (h.dst[side][par]) {   // a neighbour exists on this side
+        if (threadIdx.x == 0)
+            while (ld_vol_u32(&h.mine->ready[side][par]) < e) {}
+        __syncthreads();
+        const uint32_t n_pub = ld_vol_u32(&recv[0].slot);
+        n = min(n_pub, h.cap);
+        if (n_pub > h.cap && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&d.ctr->overflow, RSV_OVF_GHOSTS);
+    }
+    double2* pos = const_cast<double2*>(d.pos);
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t k0 = blockIdx.x * blockDim.x; k0 < n; k0 += stride) {   // (warp-uniform trip count)
+        const uint32_t k = k0 + threadIdx.x;
+        bool valid = k < n;
+        uint32_t slot = 0;
+        double2 p = make_double2(0.0, 0.0);
+        if (valid) {
+            const HaloRec r = recv[1 + k];
+            const long long sl = (long long)r.slot + h.slot_off[side];
+            valid = sl >= 0 && sl < (long long)d.n_shapes;
+            slot = (uint32_t)sl;
+            p = make_double2(r.x, r.y);
+            if (valid) {
+                pos[slot] = p;
+                const uint32_t g = atomicAdd(d.n_ghosts, 1u);
+                if (g < d.cap_ghosts) d.ghosts[g] = slot;
+                else { atomicOr(&d.ctr->overflow, RSV_OVF_GHOSTS); valid = false; }   // (not listed: must not be registered either)
+            }
+        }
+        int4 r = make_int4(0, 0, -1, -1);
+        uint32_t meta = 0;
+        bounds_item(d, margin, valid, slot, p, my_entries, my_testers, r, meta);
+    }
+    bounds_stats(d, my_entries, my_testers, false);
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(&h.mine->apply_done, 1u) == gridDim.x * gridDim.y - 1u) {
+        __threadfence_system();
+        if (h.peer_done[0][par]) st_vol_u32(h.peer_done[0][par], e);
+        if (h.peer_done[1][par]) st_vol_u32(h.peer_done[1][par], e);
+        h.mine->apply_done = 0u;
+        __threadfence_system();
+    }
 }
 
 }  // namespace rsv

@@ -28,8 +28,8 @@ int32_t rsv_strip_setup(rsv_space* s, uint32_t own_lo, uint32_t own_hi, int32_t 
         d.cap_ghosts = max_ghosts;
     }
     if (!d.n_ghosts) {
-        CU(s, cudaMalloc(&d.n_ghosts, 4));
-        CU(s, cudaMemset(d.n_ghosts, 0, 4));
+        CU(s, cudaMalloc(&d.n_ghosts, 8));   // [0] ghosts of the current frame, [1] sticky "a halo batch was truncated" word
+        CU(s, cudaMemset(d.n_ghosts, 0, 8));
     }
     d.own_lo = own_lo; d.own_hi = own_hi;
     d.home_lo = home_lo; d.home_hi = home_hi;
@@ -148,7 +148,7 @@ int32_t rsv_halo_connect(rsv_space* s, void* up_mailbox, void* dn_mailbox) {
     }
     // epochs restart at 1: clear our flag words (callers synchronise all devices between connect and the first exchange)
     CU(s, cudaMemset(s->mailbox, 0, offsetof(HaloMailboxHeader, cap)));
-    CU(s, cudaMemset((char*)s->mailbox + offsetof(HaloMailboxHeader, cnt), 0, sizeof(uint32_t) * 2));
+    CU(s, cudaMemset((char*)s->mailbox + offsetof(HaloMailboxHeader, cnt), 0, sizeof(uint32_t) * 6));   // cnt, epoch, block counters
     s->halo_epoch = 0;
     return RSV_OK;
 }
@@ -195,9 +195,71 @@ int32_t rsv_halo_exchange(rsv_space* s, int32_t up_row_max, int32_t dn_row_min, 
             return fail(s, RSV_ERR_CUDA, "cuStreamWaitValue32 failed");
     k_halo_apply2<<<dim3(blocks_for(cap, kGridBlock, s->sm_count), 2), kGridBlock, 0, st>>>(
         s->d, peer[0] ? halo_mailbox_recv(mine, cap, 0, par) : nullptr, slot_off_up,
-        peer[1] ? halo_mailbox_recv(mine, cap, 1, par) : nullptr, slot_off_dn, cap);
+        peer[1] ? halo_mailbox_recv(mine, cap, 1, par) : nullptr, slot_off_dn, cap, s->d.n_ghosts + 1);
     k_halo_signal<<<1, 1, 0, st>>>(peer[0] ? &peer[0]->done[1][par] : nullptr, peer[1] ? &peer[1]->done[0][par] : nullptr, e);
     CU(s, cudaGetLastError());
+    return RSV_OK;
+}
+
+// The frame of a strip-partitioned space with the halo exchange folded into it (peer-memory transport; call
+// rsv_halo_mailbox / rsv_halo_connect first). Replaces rsv_halo_exchange + rsv_frame_launch:
+//   k_clear -> k_bounds over the owned shapes, which also packs the boundary shapes straight into the neighbours'
+//   mailboxes; its last block publishes counts + `ready` flags                                   [RSV_HALO_SEND]
+//   k_halo_apply_bounds waits ON THE DEVICE for both neighbours' batches, applies them and registers the ghosts ->
+//   scan, scatter, ... narrowphase as in rsv_frame_launch                                           [RSV_HALO_RECV]
+// Epochs are kept on the device, so the sequence is the same every frame and is replayed as one CUDA graph. While a
+// device waits for its neighbours it has already done its own registration work; the exchange costs one small kernel.
+// A space must use either this call or rsv_halo_exchange after rsv_halo_connect, not both.
+int32_t rsv_strip_frame_launch(rsv_space* s, int32_t margin, uint32_t flags, int32_t up_row_max, int32_t dn_row_min,
+                               int32_t slot_off_up, int32_t slot_off_dn, uint32_t phases) {
+    if (!s) return RSV_ERR_BAD_ARG;
+    if (!s->mailbox || !s->strip_mode) return fail(s, RSV_ERR_BAD_ARG, "rsv_strip_frame_launch: call rsv_strip_setup / rsv_halo_mailbox / rsv_halo_connect first");
+    if (!(phases & (RSV_HALO_SEND | RSV_HALO_RECV))) return fail(s, RSV_ERR_BAD_ARG, "rsv_strip_frame_launch: no phase selected");
+    if (margin < 0 || margin > (1 << 20)) return fail(s, RSV_ERR_BAD_ARG, "rsv_frame: margin %d out of range", margin);
+    CU(s, cudaSetDevice(s->device));
+    const uint32_t cap = s->mailbox_cap;
+    HaloArgs h{};
+    h.mine = (HaloMailboxHeader*)s->mailbox;
+    for (int side = 0; side < 2; side++) {
+        HaloMailboxHeader* peer = (HaloMailboxHeader*)s->peer_mailbox[side];
+        for (int par = 0; par < 2; par++) {
+            h.recv[side][par] = halo_mailbox_recv(s->mailbox, cap, side, par);
+            if (!peer) continue;
+            h.dst[side][par] = halo_mailbox_recv(peer, cap, 1 - side, par);
+            h.peer_ready[side][par] = &peer->ready[1 - side][par];
+            h.peer_done[side][par] = &peer->done[1 - side][par];
+        }
+    }
+    h.up_row_max = up_row_max; h.dn_row_min = dn_row_min;
+    h.slot_off[0] = slot_off_up; h.slot_off[1] = slot_off_dn;
+    h.cap = cap;
+    s->d.subset = kSubsetAll;
+    DevView& d = s->d;
+    cudaStream_t st = s->stream;
+    const bool timing = (flags & RSV_FRAME_TIMING) != 0;
+    if (phases & RSV_HALO_SEND) {
+        rsv_space::FrameSlot& sl0 = s->slot[s->launch_slot];
+        if (sl0.pending) {  // both slots busy: the oldest frame was never finished -> its results are dropped
+            sl0.pending = false;
+            if (s->finish_slot == s->launch_slot) s->finish_slot ^= 1;
+        }
+    }
+    rsv_space::FrameSlot& sl = s->slot[s->launch_slot];
+    d.hits = sl.hits; d.contacts = sl.contacts; d.kind_queue = sl.kind_queue;
+    int32_t submitted = 0;
+    if (s->graphs && !timing && phases == (RSV_HALO_SEND | RSV_HALO_RECV)) {
+        submitted = frame_via_graph(s, d, margin, flags | 0x80000000u, sl, s->graph[s->launch_slot][s->cur_pos_page], st, &h);
+        if (submitted < 0) return submitted;
+    }
+    if (!submitted) {
+        const int32_t rc = enqueue_frame(s, d, margin, flags, sl, st, timing, &h, phases);
+        if (rc != RSV_OK) return rc;
+    }
+    if (!(phases & RSV_HALO_RECV)) return RSV_OK;
+    CU(s, cudaEventRecord(sl.ev_done, st));
+    sl.flags = flags;
+    sl.pending = true;
+    s->launch_slot ^= 1;
     return RSV_OK;
 }
 

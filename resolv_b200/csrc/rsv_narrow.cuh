@@ -211,7 +211,7 @@ template <class Poly, class F>
 __device__ __forceinline__ void visit_poly_poly(const Poly& A, const Poly& B, F f) {
     for (int j = 0; j < B.nl; j++) {
         V2 os = B.get(j), oe = B.line_end(j);
-        for (int i = 0; i < A.nl; i++) {
+            for (int i = 0; i < A.nl; i++) {
             V2 pt;
             if (line_x_line(A.get(i), A.line_end(i), os, oe, pt)) f(pt, j, i);
         }
@@ -481,8 +481,13 @@ __device__ __forceinline__ void narrow_one(const DevView& d, double2* sva, doubl
     }
 }
 
-// GROUP 0: the convex-convex bins with staged vertices (the heavy ones; compiled on their own so that the other pair
-// tests do not inflate this kernel's registers and code). GROUP 1: every other bin.
+// One thread per pair. GROUP 0: the convex-convex bins with staged vertices (compiled on their own so that the other
+// pair tests do not inflate this kernel's registers and code). GROUP 1: every other bin.
+// (Tried in round 2 and removed: eight lanes per pair — vertices, edge normals, edge pairs and SAT axes dealt over the
+// lanes, `smallest` folded in axis order. Bit-identical, but the sequential tail of a pair (contact sort, fold, sign
+// flips) runs on one lane of eight: 380 warp instructions per pair against 144, and slower on every config —
+// 385 / 158 / 41 us against 125 / 110 / 34 us on configs 2 / 3 / 4; profiles/r2_narrow_coop_unroll_variants.log.
+// Partial unrolling of the vertex / edge loops for more independent fp64 chains: 127 / 114 us at x2, worse at x4.)
 template <int GROUP>
 // (the convex-convex instantiation fits 96 registers without spilling: five blocks per SM; the mixed one does not)
 __global__ void __launch_bounds__(kNarrowBlock, GROUP == 0 ? RSV_NARROW_MIN_BLOCKS + 1 : RSV_NARROW_MIN_BLOCKS) k_narrow(DevView d) {

@@ -77,14 +77,33 @@ def exchange(send_up, send_dn, recv_up, recv_dn, rank, world):
             r.wait()
 
 
-def tile_world(kind: str, n: int, tile: int, seed: int = 20265, size: int = 65536):
-    """Tile `tile` of the weak-scaling world: the single-GPU workload generator shifted down by tile * size."""
+def tile_world(kind: str, n: int, tile: int, seed: int = 20265, size: int = 65536, world: int = 1):
+    """Tile `tile` (= the shapes owned by rank `tile`) of a strip-partitioned world.
+    cfg2 / cfg3 (weak scaling): the single-GPU workload generator shifted down by tile * size.
+    cfg5 (strong scaling): bands [tile * 8 / world, (tile + 1) * 8 / world) of the ONE 16M-shape config-5 world
+    (worlds.make_cfg5_band), n = shapes per rank."""
     from . import worlds
+    if kind == "cfg5":
+        per = worlds.CFG5_BANDS // world
+        ws = [worlds.make_cfg5_band(b, n * world, seed) for b in range(tile * per, (tile + 1) * per)]
+        return ws[0] if len(ws) == 1 else worlds.concat(ws, name=f"cfg5_tile{tile}")
     w = (worlds.make_rects(n, seed=seed + 101 * tile, space=size) if kind == "cfg2"
          else worlds.make_mixed(n, seed=seed + 101 * tile, space=size))
     w.pos[:, 1] += tile * float(size)
     w.pos0 = w.pos.copy()
     return w.finalize()
+
+
+def whole_world(kind: str, n: int, world: int, seed: int = 20265, size: int = 65536):
+    """The same world as ONE Space (slot = tile * n + k): what the union of all ranks must reproduce."""
+    from . import worlds
+    ws = [tile_world(kind, n, t, seed, size, world) for t in range(world)]
+    return worlds.concat(ws, space_h=space_height(kind, world, size), name=f"{kind}_whole")
+
+
+def space_height(kind: str, world: int, size: int = 65536) -> int:
+    from . import worlds
+    return worlds.CFG5_SPACE if kind == "cfg5" else size * world
 
 
 def concat_worlds(ws, space_h):
@@ -120,14 +139,14 @@ class StripRank:
         self.torch = torch
         tiles = []
         for t in (rank - 1, rank, rank + 1):
-            w = tile_world(kind, n, min(max(t, 0), world - 1), seed, size)
+            w = tile_world(kind, n, min(max(t, 0), world - 1), seed, size, world)
             if t < 0 or t >= world:
                 w.tester[:] = 0
                 absent = True
             else:
                 absent = False
             tiles.append((w, absent))
-        space_h = size * world
+        space_h = space_height(kind, world, size)
         self.w = concat_worlds([t[0] for t in tiles], space_h)
         self.absent = np.concatenate([np.full(n, a) for _, a in tiles])
         cell_h = self.w.cell_h
@@ -163,6 +182,7 @@ class StripRank:
         L.rsv_halo_exchange.restype = C.c_int32
         L.rsv_halo_exchange.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint32]
         self.peer_mode = False
+        self.fused = os.environ.get("RSV_HALO_FUSED", "1") != "0"   # (0: the separate rsv_halo_exchange chain of round 1)
         self._opened = []
         self.device = device
         self.ds._check(L.rsv_strip_setup(self.ds.h, n, 2 * n, self.plan.home_lo, self.plan.home_hi, 2 * cap_halo))
@@ -246,9 +266,19 @@ class StripRank:
             self.exchange()
             self.apply()
 
-    def step_launch(self, extra_flags=0):
-        self.halo_step()
-        self.ds.frame_launch(self.margin, self.flags | extra_flags)
+    def step_launch(self, extra_flags=0, phases=3):
+        """One frame of this rank. Peer transport: the fused form (rsv_strip_frame_launch — pack inside k_bounds, waits
+        on the device, one CUDA graph per frame); phases 1 / 2 split it for processes that drive several ranks on one
+        device. NCCL transport: pack -> send/recv -> apply -> frame."""
+        if self.peer_mode and self.fused:
+            p = self.plan
+            self.ds._check(self.ds.L.rsv_strip_frame_launch(self.ds.h, self.margin, self.flags | extra_flags, p.up_row_max,
+                                                            p.dn_row_min, -self.n, self.n, phases))
+            return
+        if phases & 1:
+            self.halo_step()
+        if phases & 2:
+            self.ds.frame_launch(self.margin, self.flags | extra_flags)
 
     def linetest(self, rays, flags=0, **kw):
         """LineTest of a batch of rays against the shapes HOMED on this rank (RSV_LINE_HOME_ONLY): every rank is given
@@ -273,26 +303,78 @@ class StripRank:
         self.ds.close()
 
 
+def _summed_counts(c, dev, dist):
+    import torch
+    t = torch.tensor([int(c.n_testers), int(c.n_candidates), int(c.n_hits), int(c.n_contacts), int(c.n_gated)], device=dev, dtype=torch.int64)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return dict(zip(("n_testers", "n_candidates", "n_hits", "n_contacts", "n_gated"), (int(v) for v in t.tolist())))
+
+
 def run_bench(args, rank, world, local_rank):
-    """bench.py leg for N > 1 GPUs: weak scaling, args.shapes shapes per GPU."""
+    """bench.py leg for N > 1 GPUs. cfg2 / cfg3: weak scaling, args.shapes shapes per GPU in a Space that grows with N.
+    cfg5: strong scaling, ONE world of args.shapes shapes in a 262144^2 Space cut into N strips (+ the ray sweep).
+    Rank 0 additionally runs the SAME world as one Space on its own GPU and the summed counters of all ranks must equal
+    that frame's (`strip_counts_ok`)."""
     import torch
     import torch.distributed as dist
-    from . import _abi, worlds
-    from bench import ClockSampler, METRIC, UNIT, workload_name, measured_peaks
+    from . import _abi, worlds, space_for_world
+    from bench import ClockSampler, METRIC, UNIT, workload_name, measured_peaks, N_POS_PAGES
 
     K, W = args.steps, max(args.warmup, 3)
-    n = args.shapes
-    sr = StripRank(args.workload, n, rank, world, local_rank, margin=1, span_rows=1)
+    kind = args.workload
+    strong = kind == "cfg5"
+    n = args.shapes // world if strong else args.shapes
+    n_rays = args.rays if strong else 0
+    sr = StripRank(kind, n, rank, world, local_rank, margin=1, span_rows=1, max_rays=min(n_rays, 2_000_000))
     ds = sr.ds
     dev = torch.device("cuda", local_rank)
     transport = "NCCL send/recv"
     if os.environ.get("RSV_HALO_TRANSPORT", "peer") == "peer" and sr.connect_ipc(dist):
-        transport = "peer-memory mailboxes over NVLink (CUDA IPC, stream-ordered waits; no NCCL call per step)"
+        transport = ("peer-memory mailboxes over NVLink (CUDA IPC), exchange folded into the frame: pack inside k_bounds, device-side "
+                     "flag waits, one CUDA graph per frame" if sr.fused else
+                     "peer-memory mailboxes over NVLink (CUDA IPC, stream-ordered waits; no NCCL call per step)")
+    # position sets of the owned shapes resident in HBM: the timed frames cycle through them (per-frame motion)
+    own0 = sr.w.pos[n:2 * n].copy()
+    vel = sr.w.vel[n:2 * n].copy() if sr.w.vel is not None else np.zeros_like(own0)
+    sets = [sr.w.pos.copy() for _ in range(N_POS_PAGES)]
+    for k in range(N_POS_PAGES):
+        sets[k][n:2 * n] = own0 + k * vel
     # warm-up (also sizes the output buffers: grow on capacity errors)
     for i in range(W):
-        sr.halo_step()
-        c = ds.frame(sr.margin, sr.flags | _abi.FRAME_DOWNLOAD, grow=True)
-    for i in range(max(W, 6)):      # the timed loop's exact call pattern (its flags select its own CUDA graphs)
+        if sr.peer_mode and sr.fused:
+            sr.step_launch(_abi.FRAME_DOWNLOAD)
+            try:
+                c = ds.frame_finish()
+            except _abi.RsvError as e:      # (every rank has done its exchange: epochs stay in step across ranks)
+                if e.code != _abi.RSV_ERR_CAPACITY:
+                    raise
+                lc = ds.last_counts()
+                ds.reserve(int(lc.n_entries * 1.3) + 1024, int(lc.n_gated * 1.3) + 1024, int(lc.n_contacts * 1.3) + 1024)
+        else:
+            sr.halo_step()
+            c = ds.frame(sr.margin, sr.flags | _abi.FRAME_DOWNLOAD, grow=True)
+    ds.device_pos_pages(sets)
+    # ---- the same world as ONE Space on rank 0's GPU: the summed counters of the ranks must equal it (frame of set 0)
+    ds.select_pos_page(0)
+    sr.step_launch(_abi.FRAME_DOWNLOAD)
+    c0 = ds.frame_finish()
+    got = _summed_counts(c0, dev, dist)
+    check = None
+    if not getattr(args, "no_parity", False):
+        ok = torch.zeros(1, device=dev, dtype=torch.int64)
+        if rank == 0:
+            whole = whole_world(kind, n, world)
+            one = space_for_world(whole, device=local_rank)
+            cw = one.frame(1, sr.flags, grow=True)
+            one.close()
+            want = {k: int(getattr(cw, k)) for k in ("n_testers", "n_candidates", "n_hits", "n_contacts")}
+            check = {"ok": all(got[k] == want[k] for k in want), "ranks_summed": got, "single_space": want}
+            ok[0] = int(check["ok"])
+            del whole
+        dist.broadcast(ok, 0)
+        dist.barrier()
+    for i in range(3 * N_POS_PAGES):      # the timed loop's exact call pattern (its flags and pages select its own CUDA graphs)
+        ds.select_pos_page(i % N_POS_PAGES)
         sr.step_launch()
     ds.frame_finish()
     sampler = ClockSampler(local_rank)
@@ -302,6 +384,7 @@ def run_bench(args, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(sr.stream)
     for i in range(K):
+        ds.select_pos_page(i % N_POS_PAGES)
         sr.step_launch()
     e1.record(sr.stream)
     torch.cuda.synchronize()
@@ -309,26 +392,22 @@ def run_bench(args, rank, world, local_rank):
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     dist.barrier()
+    ds.select_pos_page(0)
     # e2e, pipelined like the N = 1 leg: every step each rank uploads the positions of its owned range from a pinned
     # page, exchanges halos, runs the frame and downloads its results; the download of step i-1 (copy stream)
     # overlaps the upload + exchange + kernels of step i. Two position sets alternate (pages 0 / 1).
-    own_pos = sr.w.pos[n:2 * n].copy()
-    vel = sr.w.vel[n:2 * n].copy() if sr.w.vel is not None else np.zeros_like(own_pos)
     pages = [ds.pos_page(0), ds.pos_page(1)]
-    pages[0][2 * n:4 * n] = own_pos.reshape(-1)
-    pages[1][2 * n:4 * n] = (own_pos + vel).reshape(-1)
-    # one sequential warm pass sizes the buffers for both position sets
-    for pg in (0, 1):
-        ds.commit_pos_page(pg, n, 2 * n)
-        sr.halo_step()
-        ds.frame(sr.margin, sr.flags | _abi.FRAME_DOWNLOAD, grow=True)
+    pages[0][2 * n:4 * n] = own0.reshape(-1)
+    pages[1][2 * n:4 * n] = (own0 + vel).reshape(-1)
     h2d = d2h = 0
 
     def launch(i):
         ds.commit_pos_page(i % 2, n, 2 * n)
-        sr.halo_step()
-        ds.frame_launch(sr.margin, sr.flags | _abi.FRAME_DOWNLOAD)
+        sr.step_launch(_abi.FRAME_DOWNLOAD)
 
+    for i in range(2):    # warm this call pattern (graphs of the DOWNLOAD flag set)
+        launch(i)
+        ds.frame_finish()
     torch.cuda.synchronize()
     dist.barrier()
     t0 = time.perf_counter()
@@ -347,7 +426,29 @@ def run_bench(args, rank, world, local_rank):
     tot = torch.tensor([int(c.n_candidates), int(c.n_hits), int(c.n_contacts), int(c.n_entries), h2d // K, d2h // K], device=dev, dtype=torch.int64)
     dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     clocks = sampler.stop()
-    sr_peer = sr.peer_mode
+    # ---- cfg5: the ray sweep across strips. Every rank tests all rays against the shapes HOMED on it (RSV_LINE_HOME_ONLY):
+    # the union over ranks is the sweep on the whole Space; time = max over ranks of the summed kernel times.
+    rays = None
+    if n_rays:
+        batch = 2_000_000
+        t_us, hits, done = 0.0, 0, 0
+        ds.select_pos_page(0)
+        sr.step_launch()
+        ds.frame_finish()
+        while done < n_rays:
+            m = min(batch, n_rays - done)
+            seg = worlds.make_rays(m, 20265 + done, sr.w.space_w, sr.w.space_h)
+            rc = ds.linetest(seg, flags=_abi.LINE_DDA | _abi.LINE_HOME_ONLY)
+            t_us += rc.kernel_us
+            hits += int(rc.n_hits)
+            done += m
+        rt = torch.tensor([t_us], device=dev, dtype=torch.float64)
+        dist.all_reduce(rt, op=dist.ReduceOp.MAX)
+        rh = torch.tensor([hits], device=dev, dtype=torch.int64)
+        dist.all_reduce(rh, op=dist.ReduceOp.SUM)
+        rays = {"n_rays": n_rays, "iterator": "DDA, every rank tests all rays against the shapes homed on it (union = whole Space)",
+                "kernel_ms": float(rt.item()) / 1e3, "rays_per_sec": n_rays / (float(rt.item()) * 1e-6), "n_hits": int(rh.item())}
+    sr_peer, sr_fused = sr.peer_mode, sr.fused
     dist.barrier()      # (a rank must not unmap a neighbour's mailbox while that neighbour is still running)
     sr.close()
     if rank != 0:
@@ -355,24 +456,29 @@ def run_bench(args, rank, world, local_rank):
     ms_per_step = float(ms.item()) / K
     N = n * world
     peak, peak_src = measured_peaks()
-    return {
+    out = {
         "metric": METRIC, "value": N / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": workload_name(args, world) + f"; Space grown to 65536 x {65536 * world}, strip-partitioned by cell rows, "
-                   "halo exchange of (slot, position) records with both neighbours every step: " + transport,
-                   "l2": "inputs + per-frame intermediates (~0.3 GB per GPU) exceed the 126 MB L2", "margin": 1},
+        "config": {"workload": workload_name(args, world) + ("" if strong else f"; Space grown to 65536 x {65536 * world}") +
+                   ", strip-partitioned by cell rows, halo exchange of (slot, position) records with both neighbours every step: " + transport,
+                   "l2": "inputs + per-frame intermediates (~0.3 GB per GPU) exceed the 126 MB L2", "margin": 1,
+                   "motion": f"timed frames cycle through {N_POS_PAGES} position sets resident in HBM"},
         "pair_tests_per_sec": int(tot[0].item()) / (ms_per_step * 1e-3),
         "counts": {"n_shapes": N, "n_candidates": int(tot[0].item()), "n_hits": int(tot[1].item()), "n_contacts": int(tot[2].item()),
                    "n_entries": int(tot[3].item())},
+        "strip_counts_ok": None if check is None else check["ok"], "strip_check": check,
         "clocks": clocks,
         "e2e": {"value": N * K / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int(tot[4].item()),
                 "d2h_bytes_per_step": int(tot[5].item()), "ms_per_step": 1e3 * float(te.item()) / K},
-        # per rank and step: 11 frame kernels + the halo exchange (4 kernels on the peer transport; pack + 2 applies on NCCL)
-        "gpu_launches": K * (11 + (4 if sr_peer else 3)) * world,
+        # per rank and step: 11 frame kernels + the exchange (fused: 1 extra kernel; separate peer chain: 4; NCCL: pack + 2 applies)
+        "gpu_launches": K * (11 + (1 if (sr_peer and sr_fused) else (4 if sr_peer else 3))) * world,
         "roofline": {"bound": "hbm", "kernel": "frame", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
                      "traffic": None, "peak_source": peak_src, "note": "per-kernel roofline is reported by the N=1 run"},
     }
+    if rays:
+        out["rays"] = rays
+    return out
 
 
 HALO_DTYPE = np.dtype([("slot", np.uint32), ("pad", np.uint32), ("x", np.float64), ("y", np.float64)])

@@ -168,6 +168,49 @@ def make_mixed(n: int, seed: int = 20263, space: int = 65536, cell: int = 32, fi
     return w.finalize()
 
 
+CFG5_SPACE = 262144
+CFG5_BANDS = 8
+
+
+def make_cfg5_band(band: int, n_total: int = 16_000_000, seed: int = 20265) -> World:
+    """Config 5 is ONE world of n_total mixed shapes (as config 3) in a 262144^2 Space, defined as 8 horizontal bands of
+    n_total/8 shapes each (band b covers y in [b, b+1) * 32768) so that any strip partition into 1/2/4/8 ranks sees the
+    SAME world: rank g of G holds bands [g*8/G, (g+1)*8/G). Slot order = band order."""
+    n = n_total // CFG5_BANDS
+    bh = CFG5_SPACE // CFG5_BANDS
+    w = make_mixed(n, seed=seed + 101 * band, space=CFG5_SPACE)
+    w.pos[:, 1] = rand_u01(seed + 101 * band, 2, n) * bh + band * float(bh)
+    w.pos0 = w.pos.copy()
+    w.name = f"cfg5_band{band}"
+    return w.finalize()
+
+
+def concat(ws, space_h=None, name="concat") -> World:
+    """Concatenate Worlds of one Space (slot order = list order)."""
+    w0 = ws[0]
+    cat = np.concatenate
+    voff, acc = [], 0
+    for w in ws:
+        voff.append(w.vert_off.astype(np.int64) + acc)
+        acc += len(w.verts)
+    out = World(space_w=w0.space_w, space_h=space_h or w0.space_h, cell_w=w0.cell_w, cell_h=w0.cell_h,
+                kind=cat([w.kind for w in ws]), pos=cat([w.pos for w in ws]), pos0=cat([w.pos0 for w in ws]),
+                radius=cat([w.radius for w in ws]), tags=cat([w.tags for w in ws]), nv=cat([w.nv for w in ws]),
+                vert_off=cat(voff).astype(np.uint32), verts=cat([w.verts for w in ws]),
+                closed=cat([w.closed for w in ws]), tester=cat([w.tester for w in ws]),
+                use_any=cat([w.use_any for w in ws]), any_mask=cat([w.any_mask for w in ws]),
+                none_mask=cat([w.none_mask for w in ws]), space_idx=cat([w.space_idx for w in ws]),
+                n_spaces=1, margin=w0.margin, name=name,
+                vel=cat([w.vel for w in ws]) if w0.vel is not None else None)
+    out.local_aabb = cat([w.local_aabb for w in ws])
+    return out
+
+
+def make_cfg5(n_total: int = 16_000_000, seed: int = 20265) -> World:
+    """The whole config-5 world (single-GPU run / oracle checks at reduced n_total)."""
+    return concat([make_cfg5_band(b, n_total, seed) for b in range(CFG5_BANDS)], name=f"cfg5_{n_total}")
+
+
 def _append_top_left_rects(rows, x, y, ww, hh, tags):
     """NewRectangleFromTopLeft (convexPolygon.go:638-643): built at (x,y), then Move(w/2, h/2)."""
     rows.append(dict(kind=1, pos0=(x, y), pos=(x + ww / 2, y + hh / 2), radius=0.0, verts=rect_verts(ww, hh), tags=tags))

@@ -20,12 +20,12 @@ def _hits_table(hits, con, to_global):
     return a, b, n, rank, h["mtv"].copy(), cons
 
 
-@pytest.mark.parametrize("kind,transport", [("cfg2", "copy"), ("cfg3", "copy"), ("cfg3", "peer")])
+@pytest.mark.parametrize("kind,transport", [("cfg2", "copy"), ("cfg3", "copy"), ("cfg3", "peer"), ("cfg3", "fused"), ("cfg2", "fused")])
 def test_two_strips_equal_one_space(kind, transport):
     import torch
     n, size, world = 20000, 9280, 2
     ranks = [strips.StripRank(kind, n, r, world, 0, size=size, cap_halo=8192) for r in range(world)]
-    if transport == "peer":
+    if transport in ("peer", "fused"):
         # the peer-memory transport with both "devices" in one process: mailboxes are connected by pointer (processes
         # on different GPUs map them through CUDA IPC instead); pushes, flag waits and applies are all stream-ordered
         boxes = [sr.mailbox()[0] for sr in ranks]
@@ -41,7 +41,14 @@ def test_two_strips_equal_one_space(kind, transport):
                 for r, sr in enumerate(ranks):
                     sr.ds.buf[_abi.BUF_POS][2 * n:4 * n] = ref_world.pos[r * n:(r + 1) * n].reshape(-1)
                     sr.ds.commit(1 << _abi.BUF_POS, n, 2 * n)
-            if transport == "peer":
+            if transport == "fused":
+                # rsv_strip_frame_launch: the exchange is part of the frame (pack inside k_bounds, device-side waits);
+                # send halves of both ranks first, as above
+                for sr in ranks:
+                    sr.step_launch(_abi.FRAME_DOWNLOAD, phases=1)
+                for sr in ranks:
+                    sr.step_launch(_abi.FRAME_DOWNLOAD, phases=2)
+            elif transport == "peer":
                 for sr in ranks:            # all send halves first: both ranks' streams may share a hardware queue
                     sr.exchange_peer(1)
                 for sr in ranks:
@@ -55,9 +62,9 @@ def test_two_strips_equal_one_space(kind, transport):
                 torch.cuda.synchronize()
             tables, P = [], 0
             for sr in ranks:
-                if transport != "peer":
+                if transport == "copy":
                     sr.apply()
-                c = sr.ds.frame(1, sr.flags | _abi.FRAME_DOWNLOAD, grow=True)
+                c = sr.ds.frame_finish() if transport == "fused" else sr.ds.frame(1, sr.flags | _abi.FRAME_DOWNLOAD, grow=True)
                 P += c.n_candidates
                 hits, con = sr.ds.results()
                 tables.append(_hits_table(hits, con, sr.global_slot))
@@ -76,7 +83,8 @@ def test_two_strips_equal_one_space(kind, transport):
             assert np.array_equal(bits(dc), bits(rcc))
             assert len(a) > 1000
             # the halo really is a small boundary layer
-            assert int(ranks[0].send_dn[0].item() & 0xffffffff) < n // 20
+            if transport == "copy":
+                assert int(ranks[0].send_dn[0].item() & 0xffffffff) < n // 20
     finally:
         for sr in ranks:
             sr.close()
@@ -187,3 +195,41 @@ def test_rays_across_two_strips(dda):
         for sr in ranks:
             sr.close()
         ref.close()
+
+
+@pytest.mark.parametrize("transport", ["copy", "fused"])
+def test_a_halo_batch_larger_than_its_buffer_fails_the_frame(transport):
+    """A boundary population beyond the halo capacity must not pass silently (records past the capacity are dropped by
+    the sender): the frame that uses the truncated batch reports RSV_OVF_GHOSTS / RSV_ERR_CAPACITY."""
+    import torch
+    n, size, world = 20000, 9280, 2
+    ranks = [strips.StripRank("cfg2", n, r, world, 0, size=size, cap_halo=64) for r in range(world)]
+    try:
+        if transport == "fused":
+            boxes = [sr.mailbox()[0] for sr in ranks]
+            ranks[0].connect(None, boxes[1])
+            ranks[1].connect(boxes[0], None)
+            for sr in ranks:
+                sr.step_launch(0, phases=1)
+            for sr in ranks:
+                sr.step_launch(0, phases=2)
+            for sr in ranks:
+                with pytest.raises(_abi.RsvError) as ei:
+                    sr.ds.frame_finish()
+                assert ei.value.code == _abi.RSV_ERR_CAPACITY
+        else:
+            for sr in ranks:
+                sr.pack()
+            torch.cuda.synchronize()
+            assert int(ranks[0].send_dn[0].item() & 0xffffffff) > 64          # more boundary shapes than the buffer holds
+            ranks[1].recv_up.copy_(ranks[0].send_dn)
+            ranks[0].recv_dn.copy_(ranks[1].send_up)
+            torch.cuda.synchronize()
+            for sr in ranks:
+                sr.apply()
+                with pytest.raises(_abi.RsvError) as ei:
+                    sr.ds.frame(1, sr.flags)
+                assert ei.value.code == _abi.RSV_ERR_CAPACITY
+    finally:
+        for sr in ranks:
+            sr.close()
