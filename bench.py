@@ -296,7 +296,7 @@ def run_b200(args):
     for i in range(3 * N_POS_PAGES):
         ds.select_pos_page(i % N_POS_PAGES)
         ds.frame_launch(margin, base_flags)
-    ds.frame_finish()
+    ds.drain()
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -310,6 +310,7 @@ def run_b200(args):
         ds.frame_launch(margin, base_flags)
     ms = ds.timer_stop()
     c = ds.frame_finish()
+    ds.drain()
     torch.cuda.synchronize()
     ms_per_step = ms / K
     # ---- per-kernel durations over another K frames (events between kernels), same position cycle
@@ -336,22 +337,31 @@ def run_b200(args):
         e2e_seq += time.perf_counter() - t0
         h2d += 16 * N
         d2h += 32 * int(ce.n_gated) + 32 * int(ce.n_contacts) + 128
-    # (b) pipelined (the throughput mode of the API: two frames in flight, double-buffered position staging):
-    # step i uploads ITS positions from pinned page i%2, runs the frame and downloads ITS results; the download of
-    # step i-1 overlaps the upload + kernels of step i. Every step still moves all of its bytes both ways.
+    # (b) pipelined (the throughput mode of the API: two frames in flight, positions double-buffered on the host AND on the
+    # device): step i uploads ITS positions from pinned page i%2 into device page i%2 on the upload stream, runs the
+    # frame on that page and downloads ITS results; the upload of step i and the download of step i-1 overlap the
+    # kernels in flight. Every step still moves all of its bytes both ways.
     pages = [ds.pos_page(0), ds.pos_page(1)]
     pages[0][:2 * N] = frames[0].reshape(-1)
     pages[1][:2 * N] = frames[1 % len(frames)].reshape(-1)
+
+    def launch(i):
+        ds.pos_page_upload(i % 2, i % 2)
+        ds.select_pos_page(i % 2)
+        ds.frame_launch(margin, _abi.FRAME_DOWNLOAD | base_flags)
+
+    for i in range(4):   # warm this call pattern (its CUDA graphs)
+        launch(i)
+        ds.frame_finish()
     ds.sync()
     t0 = time.perf_counter()
-    ds.commit_pos_page(0)
-    ds.frame_launch(margin, _abi.FRAME_DOWNLOAD | base_flags)
+    launch(0)
     for i in range(1, K):
-        ds.commit_pos_page(i % 2)
-        ds.frame_launch(margin, _abi.FRAME_DOWNLOAD | base_flags)
+        launch(i)
         ds.frame_finish()
     ce = ds.frame_finish()
     e2e_t = time.perf_counter() - t0
+    ds.select_pos_page(0)
     clocks = sampler.stop()
     rays = ray_sweep(args, ds, w) if n_rays else None
 
@@ -385,7 +395,7 @@ def run_b200(args):
         "parity": parity,
         "clocks": clocks,
         "e2e": {"value": N * K / e2e_t, "unit": UNIT, "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K,
-                "ms_per_step": 1e3 * e2e_t / K, "mode": "pipelined: two frames in flight, D2H of step i-1 overlaps H2D + kernels of step i",
+                "ms_per_step": 1e3 * e2e_t / K, "mode": "pipelined: two frames in flight; H2D of step i (upload stream) and D2H of step i-1 (copy stream) overlap the kernels",
                 "sequential_ms_per_step": 1e3 * e2e_seq / K, "sequential_value": N * K / e2e_seq},
         # kernels of this library launched inside the timed `value` region, per frame: k_clear, k_bounds, k_scan, k_scatter,
         # k_cellsort, k_entboxes, k_pairs_tile, k_pairs (leftover list), k_bin, k_bin_scatter, k_narrow<0>, k_narrow<1>;
@@ -494,14 +504,17 @@ def run_cfg4(args, rank, world, local_rank):
     # e2e: per step the positions of this GPU's shapes go up from pinned memory, the rays go up, hits / contacts / ray sets come down
     h2d = d2h = 0
     e2e_t = 0.0
+    bodies = np.nonzero(w.tester != 0)[0].astype(np.uint32)        # only the bodies move: only their positions go up
+    list_slots, list_xy = ds.pos_list()
+    list_slots[:len(bodies)] = bodies
     for i in range(K):
-        ds.buf[_abi.BUF_POS][:2 * w.n] = frames[i % len(frames)].reshape(-1)   # the game moving its bodies and aiming its probes (untimed)
+        list_xy[:2 * len(bodies)] = frames[i % len(frames)][bodies].reshape(-1)   # the game moving its bodies and aiming its probes (untimed)
         stage_rays(i)
         t0 = time.perf_counter()
-        ds.commit(1 << _abi.BUF_POS)
+        ds.commit_pos_list(len(bodies))
         ce, re_ = step(i, True, False)
         e2e_t += time.perf_counter() - t0
-        h2d += 16 * w.n + 56 * n_rays
+        h2d += 20 * len(bodies) + 56 * n_rays
         d2h += 32 * int(ce.n_gated) + 32 * int(ce.n_contacts) + 64 * int(re_.n_hits) + 32 * int(re_.n_contacts) + 8 * n_rays + 256
     clocks = sampler.stop()
     tot = torch.tensor([ms, e2e_t], device=torch.device("cuda", local_rank), dtype=torch.float64)
@@ -530,7 +543,8 @@ def run_cfg4(args, rank, world, local_rank):
                    "n_rays": int(cnt[4].item()), "n_ray_hits": int(cnt[5].item())},
         "clocks": clocks,
         "e2e": {"value": N * K / float(tot[1].item()), "unit": UNIT, "h2d_bytes_per_step": int(cnt[6].item()), "d2h_bytes_per_step": int(cnt[7].item()),
-                "ms_per_step": 1e3 * float(tot[1].item()) / K, "mode": "sequential: commit -> frame + probes -> download"},
+                "ms_per_step": 1e3 * float(tot[1].item()) / K,
+                "mode": "sequential: sparse position update of the bodies (rsv_commit_pos_list) -> frame + probes -> download"},
         # per GPU and step: k_clear, k_bounds, k_scan<true>, k_static_place, k_scatter, k_cellfix, k_pairs, k_bin, k_bin_scatter, k_narrow x2, k_linetest
         "gpu_launches": K * 12 * world,
         "roofline": {"bound": "hbm", "kernel": "frame", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,

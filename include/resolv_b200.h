@@ -179,11 +179,20 @@ int32_t rsv_commit_pos_page(rsv_space* s, int32_t page, uint32_t lo, uint32_t hi
  * device-side integrator writing the next positions while the current frame runs) switches between them without a
  * copy: rsv_pos_pages allocates pages 1..n_pages-1 (page 0 is RSV_BUF_POS's device buffer; new pages start as copies
  * of it), rsv_pos_page_upload fills device page `device_page` from pinned staging page 0 / 1, rsv_pos_page_select
- * makes every later frame, halo pack and line test read positions from that page. The write side of
+ * makes every later frame, halo pack and line test read positions from that page. Uploads run on their own stream:
+ * the upload of the NEXT frame's positions overlaps the kernels of the frame in flight (the library orders an upload
+ * after the frames that still read the page and a frame after the upload of the page it selects). The write side of
  * ShapeBase.update (shape.go:239-242) for hosts that move shapes in bulk. */
 int32_t rsv_pos_pages(rsv_space* s, int32_t n_pages);
 int32_t rsv_pos_page_upload(rsv_space* s, int32_t device_page, int32_t staging_page, uint32_t lo, uint32_t hi);
 int32_t rsv_pos_page_select(rsv_space* s, int32_t device_page);
+/* Sparse position updates: rsv_pos_list_staging(which = 0) is a pinned u32[max_shapes] list of moved slots,
+ * (which = 1) the matching f64[2 * max_shapes] new positions; rsv_commit_pos_list(count) uploads the first `count`
+ * entries of both (20 bytes per moved shape instead of the whole position buffer) and scatters them into the position
+ * page the next frame reads. The write side of ShapeBase.update (shape.go:239-242) when few shapes move; the host's
+ * own copy in RSV_BUF_POS staging is not touched (keep it current if rsv_commit(RSV_BUF_POS) is used as well). */
+void* rsv_pos_list_staging(rsv_space* s, int32_t which, size_t* bytes);
+int32_t rsv_commit_pos_list(rsv_space* s, uint32_t count);
 /* Device address of buffer `which` (for device-side producers such as the multi-GPU halo unpack). */
 void* rsv_device_buffer(rsv_space* s, int32_t which);
 
@@ -204,6 +213,15 @@ int32_t rsv_frame(rsv_space* s, int32_t margin, uint32_t flags, rsv_counts* out)
 int32_t rsv_frame_launch(rsv_space* s, int32_t margin, uint32_t flags);
 int32_t rsv_frame_finish(rsv_space* s, rsv_counts* out);
 int32_t rsv_results_view(rsv_space* s, rsv_results* out);
+/* Explicit pair tests: A.Intersection(B) (circle.go:69-82, convexPolygon.go:288-300 -> shape.go:318-479) for a list of
+ * ordered pairs, against the positions committed so far. rsv_pair_staging returns a pinned u32[2 * max_pairs] list the
+ * host fills with (tester slot, other slot); rsv_test_pairs(n) runs Bounds + the exact Bounds gate + the narrowphase
+ * for the first n pairs and downloads one rsv_hit per pair IN LIST ORDER (rank = list index; RSV_HIT_NOT_GATED / no
+ * contacts = empty set) into the result mirrors (rsv_results_view). The grid of the last frame is not touched. This is
+ * what the host layer uses when OnIntersect moved a shape in the middle of an IntersectionTest: the reference tests
+ * candidate after candidate against the CURRENT positions (shape.go:296-312). */
+void* rsv_pair_staging(rsv_space* s, uint32_t max_pairs, size_t* bytes);
+int32_t rsv_test_pairs(rsv_space* s, uint32_t n_pairs, rsv_counts* out);
 /* Per tester slot: first record and number of records in the hit buffer of the last frame run with
  * RSV_FRAME_TESTER_TABLE (random access for a single Shape.IntersectionTest call); non-testers have count 0. */
 int32_t rsv_tester_table(rsv_space* s, uint32_t* first, uint32_t* count, uint64_t n_shapes);

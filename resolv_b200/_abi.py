@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
     "rsv_set_stream", "rsv_strip_setup", "rsv_halo_pack", "rsv_halo_apply", "rsv_staging_page", "rsv_commit_pos_page",
     "rsv_halo_mailbox", "rsv_ipc_export", "rsv_ipc_open", "rsv_ipc_close", "rsv_halo_connect", "rsv_halo_exchange",
     "rsv_static_invalidate", "rsv_static_info", "rsv_pos_pages", "rsv_pos_page_upload", "rsv_pos_page_select",
-    "rsv_strip_frame_launch",
+    "rsv_strip_frame_launch", "rsv_pos_list_staging", "rsv_commit_pos_list", "rsv_pair_staging", "rsv_test_pairs",
 ]
 
 
@@ -151,6 +151,14 @@ def load():
     L.rsv_pos_page_upload.argtypes = [vp, i32, i32, u32, u32]
     L.rsv_pos_page_select.restype = i32
     L.rsv_pos_page_select.argtypes = [vp, i32]
+    L.rsv_pair_staging.restype = vp
+    L.rsv_pair_staging.argtypes = [vp, u32, C.POINTER(C.c_size_t)]
+    L.rsv_test_pairs.restype = i32
+    L.rsv_test_pairs.argtypes = [vp, u32, C.POINTER(Counts)]
+    L.rsv_pos_list_staging.restype = vp
+    L.rsv_pos_list_staging.argtypes = [vp, i32, C.POINTER(C.c_size_t)]
+    L.rsv_commit_pos_list.restype = i32
+    L.rsv_commit_pos_list.argtypes = [vp, u32]
     L.rsv_strip_frame_launch.restype = i32
     L.rsv_strip_frame_launch.argtypes = [vp, i32, u32, i32, i32, i32, i32, u32]
     L.rsv_tester_table.restype = i32
@@ -273,6 +281,38 @@ class DeviceSpace:
             self._check(self.L.rsv_pos_page_upload(self.h, i, 0, 0, self.n_shapes))
             self.sync()
 
+    def test_pairs(self, pairs):
+        """A.Intersection(B) for explicit ordered pairs [(a, b), ...] against the committed positions: returns
+        (counts, hits, contacts), one hit record per pair in list order."""
+        pairs = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+        nb = C.c_size_t()
+        p = self.L.rsv_pair_staging(self.h, max(len(pairs), 1), C.byref(nb))
+        if not p:
+            raise RsvError(RSV_ERR_OOM, "rsv_pair_staging failed")
+        _view(p, nb.value, np.uint32)[:2 * len(pairs)] = pairs.reshape(-1)
+        c = Counts()
+        self._check(self.L.rsv_test_pairs(self.h, len(pairs), C.byref(c)))
+        hits, con = self.results()
+        return c, hits, con
+
+    def pos_list(self):
+        """(slots u32[max_shapes], xy f64[2 * max_shapes]) pinned staging of the sparse position update."""
+        nb = C.c_size_t()
+        ps = self.L.rsv_pos_list_staging(self.h, 0, C.byref(nb))
+        if not ps:
+            raise RsvError(RSV_ERR_OOM, "rsv_pos_list_staging failed")
+        slots = _view(ps, nb.value, np.uint32)
+        px = self.L.rsv_pos_list_staging(self.h, 1, C.byref(nb))
+        return slots, _view(px, nb.value, np.float64)
+
+    def commit_pos_list(self, count):
+        self._check(self.L.rsv_commit_pos_list(self.h, count))
+
+    def pos_page_upload(self, device_page, staging_page, lo=0, hi=None):
+        """Queues the upload of pinned staging page 0 / 1 into device position page `device_page` on the upload stream
+        (overlaps the kernels of the frame in flight)."""
+        self._check(self.L.rsv_pos_page_upload(self.h, device_page, staging_page, lo, self.n_shapes if hi is None else hi))
+
     def select_pos_page(self, page):
         self._check(self.L.rsv_pos_page_select(self.h, page))
 
@@ -326,6 +366,13 @@ class DeviceSpace:
 
     def last_counts(self):
         return self._last_counts
+
+    def drain(self):
+        """Finishes whatever frames are still in flight (at most two) and drops their results."""
+        c = Counts()
+        for _ in range(2):
+            if self.L.rsv_frame_finish(self.h, C.byref(c)) == RSV_ERR_BAD_ARG:
+                break
 
     def results(self):
         """(hits, contacts) structured numpy views of the pinned mirrors (valid until the next frame)."""

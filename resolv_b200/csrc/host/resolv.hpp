@@ -18,10 +18,16 @@
 // Semantics of the frame: a Space caches the results of one device frame (all shapes as testers, no device-side tag
 // filter, margin of the last request). Any mutation marks it stale; the next IntersectionTest re-runs the frame.
 // Filters are predicates on the other shape, so applying them to the compacted hit records on the host is
-// equivalent to the reference applying them before the pair test. Callbacks run nearest-first with ties in
-// candidate generation order (shape.go:291-293; sort.Slice is an insertion sort for n <= 12).
+// equivalent to the reference applying them before the pair test. Callbacks run in the order Go's sort.Slice leaves
+// the candidate list in (shape.go:291-293): detail::GoSortSlice below is pdqsort_func as shipped in the Go standard
+// library (insertion sort up to 12 elements, pattern-defeating quicksort beyond), so exact distance ties among more
+// than 12 candidates come out as the reference's do. Frames record EVERY candidate (RSV_FRAME_ALL_CANDIDATES): the
+// sort needs the whole list, and when a callback moves a shape the remaining candidates are re-tested against the
+// current positions (rsv_test_pairs), exactly as the reference evaluates Intersection() candidate by candidate.
 #pragma once
 #include <algorithm>
+#include <any>
+#include <typeinfo>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -52,6 +58,141 @@ struct Vector {  // vector.go:24-27
     }
     Vector Rotate(double a) const { return {X * std::cos(a) - Y * std::sin(a), X * std::sin(a) + Y * std::cos(a)}; }  // vector.go:246-252
 };
+
+namespace detail {
+// sort.Slice of the Go standard library (sort/zsortfunc.go, pdqsort_func) over an index range with caller-supplied
+// less(i, j) / swap(i, j): same comparisons and swaps in the same order, hence the same permutation — including for
+// equal keys, where the algorithm is not stable beyond 12 elements.
+template <class Less, class Swap>
+struct GoSorter {
+    Less less;
+    Swap swap;
+    enum Hint { kUnknown, kIncreasing, kDecreasing };
+    void insertionSort(int a, int b) {
+        for (int i = a + 1; i < b; i++)
+            for (int j = i; j > a && less(j, j - 1); j--) swap(j, j - 1);
+    }
+    void siftDown(int lo, int hi, int first) {
+        int root = lo;
+        for (;;) {
+            int child = 2 * root + 1;
+            if (child >= hi) return;
+            if (child + 1 < hi && less(first + child, first + child + 1)) child++;
+            if (!less(first + root, first + child)) return;
+            swap(first + root, first + child);
+            root = child;
+        }
+    }
+    void heapSort(int a, int b) {
+        const int first = a, lo = 0, hi = b - a;
+        for (int i = (hi - 1) / 2; i >= 0; i--) siftDown(i, hi, first);
+        for (int i = hi - 1; i >= 0; i--) { swap(first, first + i); siftDown(lo, i, first); }
+    }
+    static int bitsLen(unsigned v) { int n = 0; while (v) { n++; v >>= 1; } return n; }
+    void breakPatterns(int a, int b) {
+        const int length = b - a;
+        if (length >= 8) {
+            uint64_t r = (uint64_t)length;                      // xorshift seeded with the length
+            const unsigned modulus = 1u << bitsLen((unsigned)length);
+            const int idx = a + (length / 4) * 2 - 1;
+            for (int i = 0; i < 3; i++) {
+                r ^= r << 13; r ^= r >> 7; r ^= r << 17;
+                int other = (int)((unsigned)r & (modulus - 1));
+                if (other >= length) other -= length;
+                swap(idx - 1 + i, a + other);
+            }
+        }
+    }
+    void order2(int& a, int& b, int& swaps) { if (less(b, a)) { swaps++; std::swap(a, b); } }
+    int median(int a, int b, int c, int& swaps) { order2(a, b, swaps); order2(b, c, swaps); order2(a, b, swaps); return b; }
+    int medianAdjacent(int a, int& swaps) { return median(a - 1, a, a + 1, swaps); }
+    int choosePivot(int a, int b, Hint& hint) {
+        const int shortestNinther = 50, maxSwaps = 4 * 3;
+        const int l = b - a;
+        int swaps = 0, i = a + l / 4 * 1, j = a + l / 4 * 2, k = a + l / 4 * 3;
+        if (l >= 8) {
+            if (l >= shortestNinther) { i = medianAdjacent(i, swaps); j = medianAdjacent(j, swaps); k = medianAdjacent(k, swaps); }
+            j = median(i, j, k, swaps);
+        }
+        hint = swaps == 0 ? kIncreasing : (swaps == maxSwaps ? kDecreasing : kUnknown);
+        return j;
+    }
+    void reverseRange(int a, int b) { for (int i = a, j = b - 1; i < j; i++, j--) swap(i, j); }
+    bool partialInsertionSort(int a, int b) {
+        const int maxSteps = 5, shortestShifting = 50;
+        int i = a + 1;
+        for (int step = 0; step < maxSteps; step++) {
+            while (i < b && !less(i, i - 1)) i++;
+            if (i == b) return true;
+            if (b - a < shortestShifting) return false;
+            swap(i, i - 1);
+            if (i - a >= 2)
+                for (int j = i - 1; j >= 1; j--) { if (!less(j, j - 1)) break; swap(j, j - 1); }
+            if (b - i >= 2)
+                for (int j = i + 1; j < b; j++) { if (!less(j, j - 1)) break; swap(j, j - 1); }
+        }
+        return false;
+    }
+    int partitionEqual(int a, int b, int pivot) {
+        swap(a, pivot);
+        int i = a + 1, j = b - 1;
+        for (;;) {
+            while (i <= j && !less(a, i)) i++;
+            while (i <= j && less(a, j)) j--;
+            if (i > j) break;
+            swap(i, j); i++; j--;
+        }
+        return i;
+    }
+    int partition(int a, int b, int pivot, bool& already) {
+        swap(a, pivot);
+        int i = a + 1, j = b - 1;
+        while (i <= j && less(i, a)) i++;
+        while (i <= j && !less(j, a)) j--;
+        if (i > j) { swap(j, a); already = true; return j; }
+        swap(i, j); i++; j--;
+        for (;;) {
+            while (i <= j && less(i, a)) i++;
+            while (i <= j && !less(j, a)) j--;
+            if (i > j) break;
+            swap(i, j); i++; j--;
+        }
+        swap(j, a);
+        already = false;
+        return j;
+    }
+    void pdqsort(int a, int b, int limit) {
+        const int maxInsertion = 12;
+        bool wasBalanced = true, wasPartitioned = true;
+        for (;;) {
+            const int length = b - a;
+            if (length <= maxInsertion) { insertionSort(a, b); return; }
+            if (limit == 0) { heapSort(a, b); return; }
+            if (!wasBalanced) { breakPatterns(a, b); limit--; }
+            Hint hint;
+            int pivot = choosePivot(a, b, hint);
+            if (hint == kDecreasing) { reverseRange(a, b); pivot = (b - 1) - (pivot - a); hint = kIncreasing; }
+            if (wasBalanced && wasPartitioned && hint == kIncreasing && partialInsertionSort(a, b)) return;
+            if (a > 0 && !less(a - 1, pivot)) { a = partitionEqual(a, b, pivot); continue; }
+            bool already = false;
+            const int mid = partition(a, b, pivot, already);
+            wasPartitioned = already;
+            const int leftLen = mid - a, rightLen = b - mid, balanceThreshold = length / 8;
+            if (leftLen < rightLen) { wasBalanced = leftLen >= balanceThreshold; pdqsort(a, mid, limit); a = mid + 1; }
+            else { wasBalanced = rightLen >= balanceThreshold; pdqsort(mid + 1, b, limit); b = mid; }
+        }
+    }
+};
+// sort.Slice(v, func(i, j) bool { return key(v[i]) < key(v[j]) })
+template <class T, class Key>
+void GoSortSlice(std::vector<T>& v, Key key) {
+    auto less = [&](int i, int j) { return key(v[(size_t)i]) < key(v[(size_t)j]); };
+    auto swp = [&](int i, int j) { std::swap(v[(size_t)i], v[(size_t)j]); };
+    GoSorter<decltype(less), decltype(swp)> s{less, swp};
+    const int n = (int)v.size();
+    s.pdqsort(0, n, GoSorter<decltype(less), decltype(swp)>::bitsLen((unsigned)n));
+}
+}  // namespace detail
 
 using Tags = uint64_t;  // tags.go:8; Has == any bit in common (tags.go:29-31)
 inline bool TagsHas(Tags t, Tags v) { return (t & v) > 0; }
@@ -85,6 +226,8 @@ public:
     void Move(double x, double y) { pos_.X += x; pos_.Y += y; updatePosition(); }  // shape.go:98-102
     void MoveVec(Vector v) { Move(v.X, v.Y); }
     Space* GetSpace() const { return space_; }
+    void SetData(std::any d) { data_ = std::move(d); }      // shape.go:121-129
+    const std::any& Data() const { return data_; }
     virtual Bounds GetBounds() const = 0;
     virtual bool IsCircle() const = 0;
     inline ShapeFilter SelectTouchingCells(int margin);                  // + .FilterShapes() folded in (cell.go:73-83)
@@ -98,6 +241,7 @@ protected:
     inline void updatePosition();  // same, when only the position changed: 16 bytes to upload, registrations of others kept
     Vector pos_;
     Tags tags_ = 0;
+    std::any data_;
     uint32_t id_ = 0;
     Space* space_ = nullptr;
     uint32_t slot_ = 0;
@@ -120,6 +264,7 @@ struct ShapeLineTestSettings {  // convexPolygon.go:304-315
     const ShapeFilter* TestAgainst = nullptr;
     std::function<bool(const IntersectionSet&, int, int)> OnIntersect;
     bool IncludeAllPoints = false;
+    std::vector<int> Lines;   // convexPolygon.go:314, 329-340: matched against the INDICES of this slice (reference quirk kept)
 };
 
 class ConvexPolygon : public Shape {  // convexPolygon.go:12-46
@@ -195,6 +340,21 @@ public:
     ShapeFilter NotByTags(Tags t) const { auto f = *this; f.filters_.push_back([t](Shape& s) { return !TagsHas(s.GetTags(), t); }); return f; }
     ShapeFilter ByFunc(std::function<bool(Shape&)> fn) const { auto f = *this; f.filters_.push_back(std::move(fn)); return f; }
     ShapeFilter Not(Shape* x) const { auto f = *this; f.filters_.push_back([x](Shape& s) { return &s != x; }); return f; }
+    // shapefilter.go:66-74: strictly between min and max away from the point
+    ShapeFilter ByDistance(Vector point, double min, double max) const {
+        auto f = *this;
+        f.filters_.push_back([=](Shape& s) { Vector p = s.Position(); double x = p.X - point.X, y = p.Y - point.Y; double d = std::sqrt(x * x + y * y); return d > min && d < max; });
+        return f;
+    }
+    // shapefilter.go:84-96: shapes whose Data() is of the given type (Go tests interface implementation by reflection;
+    // the C++ counterpart is the dynamic type held by the std::any). Shapes without data never pass.
+    ShapeFilter ByDataType(const std::type_info& t) const {
+        auto f = *this;
+        const std::type_info* tp = &t;
+        f.filters_.push_back([tp](Shape& s) { return s.Data().has_value() && s.Data().type() == *tp; });
+        return f;
+    }
+    template <class T> ShapeFilter ByDataType() const { return ByDataType(typeid(T)); }
     bool Accepts(Shape& s) const {
         for (auto& f : filters_) if (!f(s)) return false;
         return true;
@@ -263,7 +423,8 @@ public:
     // the device, like shapes whose update() never runs keep theirs in the reference (shape.go:239-242).
     void Step(int margin) {
         prepare();
-        const uint32_t flags = RSV_FRAME_DOWNLOAD | RSV_FRAME_TESTER_TABLE | RSV_FRAME_NO_TAG_FILTERS | RSV_FRAME_INCREMENTAL;
+        // every candidate gets a record (rank = position in possibleIntersections before the sort, shape.go:277-289)
+        const uint32_t flags = RSV_FRAME_DOWNLOAD | RSV_FRAME_TESTER_TABLE | RSV_FRAME_NO_TAG_FILTERS | RSV_FRAME_INCREMENTAL | RSV_FRAME_ALL_CANDIDATES;
         rsv_counts c{};
         int32_t rc = rsv_frame(h_, margin, flags, &c);
         for (int tries = 0; rc == RSV_ERR_CAPACITY && tries < 3; tries++) {
@@ -274,7 +435,7 @@ public:
         first_.resize(shapes_.size()); count_.resize(shapes_.size());
         rsv_tester_table(h_, first_.data(), count_.data(), shapes_.size());
         rsv_results_view(h_, &res_);
-        margin_ = margin; stale_ = false; counts_ = c;
+        margin_ = margin; stale_ = false; counts_ = c; frameEpoch_ = moveEpoch_;
     }
     // (static registrations cached on the device, shapes re-registered per frame) — see rsv_static_info
     std::pair<uint32_t, uint32_t> StaticInfo() { uint32_t a = 0, b = 0; rsv_static_info(h_, &a, &b); return {a, b}; }
@@ -286,14 +447,14 @@ private:
     friend class ConvexPolygon;
     friend bool LineTest(const LineTestSettings&);
     static constexpr uint32_t kStillFrames = 2, kPromoteEvery = 4;
-    void markDirty(Shape* s) { writeRow(s, false); moved_[s->slot_] = 1; stale_ = true; }
+    void markDirty(Shape* s) { writeRow(s, false); moved_[s->slot_] = 1; stale_ = true; moveEpoch_++; }
     void markMoved(Shape* s) {
         const uint32_t i = s->slot_;
         pos_[2 * i] = s->pos_.X; pos_[2 * i + 1] = s->pos_.Y;
         moved_[i] = 1;
         if (meta_[i] & RSV_META_STATIC) { meta_[i] &= ~RSV_META_STATIC; metaDirty_ = true; }   // demotion is immediate
         posLo_ = std::min(posLo_, i); posHi_ = std::max(posHi_, i + 1);
-        stale_ = true;
+        stale_ = true; moveEpoch_++;
     }
     // Static / dynamic classification + upload of what changed; runs before every device frame.
     void prepare() {
@@ -314,6 +475,11 @@ private:
             metaDirty_ = true;
         }
         frameNo_++;
+        upload(tagsDirty);
+    }
+    // Uploads what changed since the last upload (whole rows after Add / shape edits, otherwise the dirty position range).
+    void upload(bool tagsDirty = false) {
+        const uint32_t n = (uint32_t)shapes_.size();
         if (fullCommit_) {
             rsv_commit(h_, (1u << RSV_BUF_COUNT) - 1, 0, n);
         } else {
@@ -323,6 +489,39 @@ private:
         }
         fullCommit_ = false; metaDirty_ = false;
         posLo_ = 0xffffffffu; posHi_ = 0;
+    }
+    // A.Intersection(B) for explicit pairs against the CURRENT positions (rsv_test_pairs); one set per pair, in order.
+    std::vector<IntersectionSet> testPairs(const std::vector<std::pair<Shape*, Shape*>>& pairs) {
+        std::vector<IntersectionSet> out(pairs.size());
+        if (pairs.empty()) return out;
+        upload();
+        size_t nb = 0;
+        uint32_t* list = (uint32_t*)rsv_pair_staging(h_, (uint32_t)pairs.size(), &nb);
+        if (!list) throw std::runtime_error("resolv: rsv_pair_staging failed");
+        for (size_t k = 0; k < pairs.size(); k++) { list[2 * k] = pairs[k].first->slot_; list[2 * k + 1] = pairs[k].second->slot_; }
+        rsv_counts c{};
+        int32_t rc = rsv_test_pairs(h_, (uint32_t)pairs.size(), &c);
+        for (int tries = 0; rc == RSV_ERR_CAPACITY && tries < 3; tries++) {
+            rsv_reserve(h_, 0, (uint32_t)std::max<uint64_t>(c.n_gated, pairs.size()) * 5 / 4 + 1024, (uint32_t)(c.n_contacts * 5 / 4 + 1024));
+            rc = rsv_test_pairs(h_, (uint32_t)pairs.size(), &c);
+        }
+        if (rc != RSV_OK) throw std::runtime_error(std::string("resolv: ") + rsv_last_error(h_));
+        // (the result views now hold the pair records: the frame's views are gone, so is the tester table)
+        stale_ = true;
+        rsv_results r{};
+        rsv_results_view(h_, &r);
+        for (size_t k = 0; k < pairs.size() && k < r.n_hit_records; k++) fillSet(out[k], r.hits[k], r.contacts, pairs[k].second);
+        return out;
+    }
+    static void fillSet(IntersectionSet& set, const rsv_hit& h, const rsv_contact* contacts, Shape* other) {
+        const uint32_t n = h.count_rank & 0x7f;
+        if (n == 0) return;
+        set.OtherShape = other;
+        set.MTV = {h.mtv_x, h.mtv_y};
+        for (uint32_t i = 0; i < n; i++) {
+            const rsv_contact& q = contacts[h.first_contact + i];
+            set.Intersections.push_back({{q.px, q.py}, {q.nx, q.ny}});
+        }
     }
     void writeRow(Shape* s, bool isNew) {
         uint32_t i = s->slot_;
@@ -359,6 +558,7 @@ private:
     std::vector<uint8_t> moved_;     // update() ran since the last device frame
     std::vector<uint32_t> still_;    // device frames since the shape last moved
     uint32_t posLo_ = 0xffffffffu, posHi_ = 0, frameNo_ = 0;
+    uint64_t moveEpoch_ = 0, frameEpoch_ = 0;   // bumped by every shape move / edit; value at the last device frame
     std::vector<uint32_t> first_, count_;
     rsv_results res_{};
     rsv_counts counts_{};
@@ -377,63 +577,55 @@ inline ShapeFilter Shape::SelectTouchingCells(int margin) {
 inline bool Shape::IntersectionTest(const IntersectionTestSettings& st) {
     if (!space_ || !st.TestAgainst || !st.TestAgainst->space) return false;
     Space& sp = *space_;
-    sp.ensureFrame(st.TestAgainst->margin);
-    // copy this tester's sets out of the borrowed result views first: a callback may move shapes, which re-runs the
-    // frame and overwrites the views
-    struct Cand { double d; uint32_t rank; Shape* other; IntersectionSet set; };
+    const ShapeFilter& ta = *st.TestAgainst;
+    // ---- possibleIntersections (shape.go:277-289): every shape the iterator yields except the tester, with its distance
+    struct Cand { double d; Shape* other; bool known; IntersectionSet set; };
     std::vector<Cand> list;
-    const rsv_hit* hits = sp.res_.hits;
-    for (uint32_t k = 0; k < sp.count_[slot_]; k++) {
-        const rsv_hit* h = hits + sp.first_[slot_] + k;
-        const uint32_t n = h->count_rank & 0x7f;
-        if (n == 0) continue;
-        Shape* other = sp.shapes_[h->b];
-        if (!st.TestAgainst->Accepts(*other)) continue;
-        Cand c{other->pos_.DistanceSquared(pos_), h->count_rank >> 8, other, {}};   // shape.go:179-181
-        c.set.OtherShape = other;
-        c.set.MTV = {h->mtv_x, h->mtv_y};
-        for (uint32_t i = 0; i < n; i++) {
-            const rsv_contact& q = sp.res_.contacts[h->first_contact + i];
-            c.set.Intersections.push_back({{q.px, q.py}, {q.nx, q.ny}});
+    uint64_t validEpoch = ~0ull;   // move epoch the `set`s of the list were computed at (~0: none computed yet)
+    if (ta.owner) {
+        sp.ensureFrame(ta.margin);
+        // the iterator is owner.SelectTouchingCells(margin).FilterShapes(): the owner's records, in generation order
+        const uint32_t os = ta.owner->slot_;
+        const bool own = ta.owner == this;
+        for (uint32_t k = 0; k < sp.count_[os]; k++) {
+            const rsv_hit& h = sp.res_.hits[sp.first_[os] + k];
+            Shape* other = sp.shapes_[h.b];
+            if (other == this || !ta.Accepts(*other)) continue;
+            Cand c{other->pos_.DistanceSquared(pos_), other, own, {}};   // shape.go:179-181
+            if (own) Space::fillSet(c.set, h, sp.res_.contacts, other);   // copied out: callbacks may invalidate the views
+            list.push_back(std::move(c));
         }
-        list.push_back(std::move(c));
+        if (own) validEpoch = sp.frameEpoch_;
+    } else {
+        // space.FilterShapes(): every shape of the Space in Add order (space.go:100-110)
+        for (Shape* other : sp.Shapes()) {
+            if (other == this || !ta.Accepts(*other)) continue;
+            list.push_back(Cand{other->pos_.DistanceSquared(pos_), other, false, {}});
+        }
     }
-    std::stable_sort(list.begin(), list.end(), [](const Cand& a, const Cand& b) { return a.d < b.d || (a.d == b.d && a.rank < b.rank); });
+    detail::GoSortSlice(list, [](const Cand& c) { return c.d; });   // shape.go:291-293
     bool collided = false;
-    const Vector before = pos_;
-    for (auto& c : list) {
-        IntersectionSet set;
-        if (pos_.X != before.X || pos_.Y != before.Y) {
-            // a callback moved the tester: later sets must see the new position (shape.go:252-258) -> re-test that pair
-            set = Intersection(*c.other);
-            if (set.IsEmpty()) continue;
-        } else {
-            set = c.set;
+    for (size_t idx = 0; idx < list.size(); idx++) {
+        if (sp.moveEpoch_ != validEpoch || !list[idx].known) {
+            // something moved since the sets were computed (the usual MoveVec(MTV) inside OnIntersect), or they never
+            // were: the reference calls Intersection() on the CURRENT world for every remaining candidate (shape.go:298)
+            std::vector<std::pair<Shape*, Shape*>> pairs;
+            for (size_t k = idx; k < list.size(); k++) pairs.push_back({this, list[k].other});
+            auto sets = sp.testPairs(pairs);
+            for (size_t k = idx; k < list.size(); k++) { list[k].set = std::move(sets[k - idx]); list[k].known = true; }
+            validEpoch = sp.moveEpoch_;
         }
+        if (list[idx].set.IsEmpty()) continue;
         collided = true;
-        if (!st.OnIntersect || !st.OnIntersect(set)) break;
+        if (!st.OnIntersect || !st.OnIntersect(list[idx].set)) break;
     }
     return collided;
 }
 
-// A single ordered pair through the device: the frame cache is refreshed and the record (this, other) looked up.
+// A single ordered pair (circle.go:69-82, convexPolygon.go:288-300) through rsv_test_pairs.
 inline IntersectionSet Shape::Intersection(Shape& other) {
-    IntersectionSet set;
-    if (!space_ || other.space_ != space_) return set;
-    Space& sp = *space_;
-    // margin large enough that `other` is a candidate whenever the Bounds overlap (they then share a cell)
-    sp.ensureFrame(sp.margin_ < 0 ? 1 : sp.margin_);
-    for (uint32_t k = 0; k < sp.count_[slot_]; k++) {
-        const rsv_hit* h = sp.res_.hits + sp.first_[slot_] + k;
-        if (h->b != other.slot_ || (h->count_rank & 0x7f) == 0) continue;
-        set.OtherShape = &other;
-        set.MTV = {h->mtv_x, h->mtv_y};
-        for (uint32_t i = 0; i < (h->count_rank & 0x7f); i++) {
-            const rsv_contact& c = sp.res_.contacts[h->first_contact + i];
-            set.Intersections.push_back({{c.px, c.py}, {c.nx, c.ny}});
-        }
-    }
-    return set;
+    if (!space_ || other.space_ != space_) return {};
+    return space_->testPairs({{this, &other}})[0];
 }
 
 // utils.go:276-370 through rsv_linetest. TestAgainst built from SelectTouchingCells / FilterShapes: the device
@@ -459,7 +651,8 @@ inline bool LineTest(const LineTestSettings& st) {
         if (other == st.TestAgainst->owner || !st.TestAgainst->Accepts(*other)) continue;
         list.push_back({h->key, h->count_rank >> 8, h});
     }
-    std::stable_sort(list.begin(), list.end(), [](const Cand& a, const Cand& b) { return a.key < b.key || (a.key == b.key && a.rank < b.rank); });
+    // records come in candidate generation order; utils.go:355-357 sorts them with sort.Slice
+    detail::GoSortSlice(list, [](const Cand& c) { return c.key; });
     int idx = 0;
     for (auto& c : list) {
         IntersectionSet set;
@@ -488,6 +681,9 @@ inline bool ConvexPolygon::ShapeLineTest(const ShapeLineTestSettings& st) {
     if (!st.IncludeAllPoints) {
         size_t nl = (Closed && Points.size() > 2) ? t.size() : (t.empty() ? 0 : t.size() - 1);
         for (size_t i = 0; i < nl; i++) {
+            // convexPolygon.go:329-340: `for lineIndex := range settings.Lines` ranges over the slice's INDICES, so line i
+            // is cast from iff i < len(Lines) — whatever the slice holds (kept as in the reference)
+            if (!st.Lines.empty() && i >= st.Lines.size()) continue;
             Vector s = t[i], e = t[(i + 1) % t.size()];
             Vector dir = e.Sub(s).Unit();
             Vector nrm = Vector{dir.Y, -dir.X}.Unit();
@@ -520,7 +716,7 @@ inline bool ConvexPolygon::ShapeLineTest(const ShapeLineTestSettings& st) {
         };
         LineTest(lt);
     }
-    std::stable_sort(results.begin(), results.end(), [](const IntersectionSet& a, const IntersectionSet& b) { return a.MTV.MagnitudeSquared() < b.MTV.MagnitudeSquared(); });
+    detail::GoSortSlice(results, [](const IntersectionSet& r) { return r.MTV.MagnitudeSquared(); });   // convexPolygon.go:398-400
     for (size_t i = 0; i < results.size(); i++)
         if (st.OnIntersect && !st.OnIntersect(results[i], (int)i, (int)results.size())) break;
     return !results.empty();

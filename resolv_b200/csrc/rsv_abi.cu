@@ -68,12 +68,21 @@ struct rsv_space {
     } graph[2][4];   // per result slot and device position page
     void* pos_page[4] = {};   // device position pages (rsv_pos_pages); page 0 is dev_buf[RSV_BUF_POS]
     int n_pos_pages = 1, cur_pos_page = 0;
+    // uploads into a position page run on their own stream so that they overlap the kernels of the frame in flight:
+    // ev_page_up[p] = last upload into page p, ev_page_rd[p] = last frame launched on page p
+    cudaStream_t upload_stream = nullptr;
+    cudaEvent_t ev_page_up[4] = {}, ev_page_rd[4] = {};
+    bool page_up_pending[4] = {}, page_rd_valid[4] = {};
     bool graphs = true;  // RSV_NO_GRAPH=1 in the environment turns graph replay off
     cudaStream_t copy_stream = nullptr;
     cudaStream_t side_stream = nullptr;  // second narrowphase kernel
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     Counters* h_ctr = nullptr;       // pinned counters of the line tests
     void* host_pos_page1 = nullptr;  // second pinned staging page for RSV_BUF_POS (rsv_staging_page)
+    // sparse position updates (rsv_commit_pos_list): pinned (slot, x, y) lists and their device copies
+    uint32_t* h_pair_list = nullptr; uint32_t* d_pair_list = nullptr; uint32_t cap_pair_list = 0;   // rsv_test_pairs
+    uint32_t* h_list_slots = nullptr; double* h_list_xy = nullptr;
+    uint32_t* d_list_slots = nullptr; double2* d_list_xy = nullptr;
     uint32_t launched_flags = 0;     // flags of the last finished frame
     rsv_counts last_counts{};
     uint64_t last_records = 0, last_contacts = 0;
@@ -114,6 +123,13 @@ static int32_t fail(rsv_space* s, int32_t code, const char* fmt, ...) {
             return fail((s), e__ == cudaErrorMemoryAllocation ? RSV_ERR_OOM : RSV_ERR_CUDA, "%s: %s", #call, \
                         cudaGetErrorString(e__));                                                     \
     } while (0)
+
+static inline int blocks_for(uint32_t n, int block, int cap) {
+    long long b = ((long long)n + block - 1) / block;
+    if (b < 1) b = 1;
+    if (b > cap) b = cap;
+    return (int)b;
+}
 
 static void drop_graph(rsv_space::FrameGraph& g) {
     if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -333,6 +349,12 @@ int32_t rsv_destroy(rsv_space* s) {
     for (void* p : dev) if (p) cudaFree(p);
     if (s->h_ctr) cudaFreeHost(s->h_ctr);
     if (s->host_pos_page1) cudaFreeHost(s->host_pos_page1);
+    if (s->h_pair_list) cudaFreeHost(s->h_pair_list);
+    if (s->d_pair_list) cudaFree(s->d_pair_list);
+    if (s->h_list_slots) cudaFreeHost(s->h_list_slots);
+    if (s->h_list_xy) cudaFreeHost(s->h_list_xy);
+    if (s->d_list_slots) cudaFree(s->d_list_slots);
+    if (s->d_list_xy) cudaFree(s->d_list_xy);
     for (auto& sl : s->slot) {
         void* dv[] = {sl.hits, sl.contacts, sl.kind_queue};
         for (void* p : dv) if (p) cudaFree(p);
@@ -347,6 +369,11 @@ int32_t rsv_destroy(rsv_space* s) {
         for (void* p : sv) if (p) cudaFree(p);
     }
     for (int p = 1; p < 4; p++) if (s->pos_page[p]) cudaFree(s->pos_page[p]);
+    if (s->upload_stream) { cudaStreamSynchronize(s->upload_stream); cudaStreamDestroy(s->upload_stream); }
+    for (int p = 0; p < 4; p++) {
+        if (s->ev_page_up[p]) cudaEventDestroy(s->ev_page_up[p]);
+        if (s->ev_page_rd[p]) cudaEventDestroy(s->ev_page_rd[p]);
+    }
     if (s->mailbox) cudaFree(s->mailbox);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->side_stream) cudaStreamDestroy(s->side_stream);
@@ -416,31 +443,91 @@ int32_t rsv_pos_pages(rsv_space* s, int32_t n_pages) {
     if (!s || n_pages < 1 || n_pages > 4) return RSV_ERR_BAD_ARG;
     CU(s, cudaSetDevice(s->device));
     s->pos_page[0] = s->dev_buf[RSV_BUF_POS];
+    if (!s->upload_stream) {
+        CU(s, cudaStreamCreateWithFlags(&s->upload_stream, cudaStreamNonBlocking));
+        for (int p = 0; p < 4; p++) {
+            CU(s, cudaEventCreateWithFlags(&s->ev_page_up[p], cudaEventDisableTiming));
+            CU(s, cudaEventCreateWithFlags(&s->ev_page_rd[p], cudaEventDisableTiming));
+        }
+    }
     for (int p = 1; p < n_pages; p++)
         if (!s->pos_page[p]) {
             CU(s, cudaMalloc(&s->pos_page[p], s->buf_bytes[RSV_BUF_POS]));
             CU(s, cudaMemcpyAsync(s->pos_page[p], s->dev_buf[RSV_BUF_POS], s->buf_bytes[RSV_BUF_POS], cudaMemcpyDeviceToDevice, s->stream));
         }
+    CU(s, cudaStreamSynchronize(s->stream));
     if (n_pages > s->n_pos_pages) s->n_pos_pages = n_pages;
     return RSV_OK;
 }
 
 int32_t rsv_pos_page_upload(rsv_space* s, int32_t device_page, int32_t staging_page, uint32_t lo, uint32_t hi) {
     if (!s || device_page < 0 || device_page >= s->n_pos_pages || staging_page < 0 || staging_page > 1) return RSV_ERR_BAD_ARG;
+    if (!s->upload_stream) return fail(s, RSV_ERR_BAD_ARG, "rsv_pos_page_upload: call rsv_pos_pages first");
     if (staging_page == 1 && !s->host_pos_page1) return fail(s, RSV_ERR_BAD_ARG, "rsv_pos_page_upload: staging page 1 was never requested");
     if (hi > s->n_shapes) hi = s->n_shapes;
     if (lo >= hi) return RSV_OK;
     CU(s, cudaSetDevice(s->device));
     void* dst = device_page ? s->pos_page[device_page] : s->dev_buf[RSV_BUF_POS];
     const char* src = (const char*)(staging_page ? s->host_pos_page1 : s->host_buf[RSV_BUF_POS]);
-    CU(s, cudaMemcpyAsync((char*)dst + (size_t)lo * 16, src + (size_t)lo * 16, (size_t)(hi - lo) * 16, cudaMemcpyHostToDevice, s->stream));
+    // the frames already launched on this page must have read it before it is overwritten
+    if (s->page_rd_valid[device_page]) CU(s, cudaStreamWaitEvent(s->upload_stream, s->ev_page_rd[device_page], 0));
+    CU(s, cudaMemcpyAsync((char*)dst + (size_t)lo * 16, src + (size_t)lo * 16, (size_t)(hi - lo) * 16, cudaMemcpyHostToDevice, s->upload_stream));
+    CU(s, cudaEventRecord(s->ev_page_up[device_page], s->upload_stream));
+    s->page_up_pending[device_page] = true;
     return RSV_OK;
 }
 
 int32_t rsv_pos_page_select(rsv_space* s, int32_t device_page) {
     if (!s || device_page < 0 || device_page >= s->n_pos_pages) return RSV_ERR_BAD_ARG;
+    CU(s, cudaSetDevice(s->device));
     s->cur_pos_page = device_page;
     s->d.pos = (const double2*)(device_page ? s->pos_page[device_page] : s->dev_buf[RSV_BUF_POS]);
+    if (s->page_up_pending[device_page]) {   // frames on this page start after its upload has landed
+        CU(s, cudaStreamWaitEvent(s->stream, s->ev_page_up[device_page], 0));
+        s->page_up_pending[device_page] = false;
+    }
+    return RSV_OK;
+}
+
+// Sparse position updates: the host lists the slots that moved and their new positions (two pinned arrays owned by the
+// library) and only those 20 bytes per moved shape cross the bus; a small kernel scatters them into the position page
+// the next frame reads. The write side of ShapeBase.update (shape.go:239-242) for worlds in which few shapes move
+// (config 4: 32 bodies among 500 tiles per Space).
+static __global__ void k_pos_scatter(double2* __restrict__ pos, const uint32_t* __restrict__ slots, const double2* __restrict__ xy,
+                                     uint32_t n, uint32_t n_shapes) {
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const uint32_t i = slots[k];
+        if (i < n_shapes) pos[i] = xy[k];
+    }
+}
+
+void* rsv_pos_list_staging(rsv_space* s, int32_t which, size_t* bytes) {
+    if (!s || which < 0 || which > 1) return nullptr;
+    if (cudaSetDevice(s->device) != cudaSuccess) return nullptr;
+    const size_t N = s->cfg.max_shapes;
+    if (!s->h_list_slots) {
+        if (cudaHostAlloc(&s->h_list_slots, N * 4, cudaHostAllocDefault) != cudaSuccess ||
+            cudaHostAlloc(&s->h_list_xy, N * 16, cudaHostAllocDefault) != cudaSuccess ||
+            cudaMalloc(&s->d_list_slots, N * 4) != cudaSuccess || cudaMalloc(&s->d_list_xy, N * 16) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+    }
+    if (bytes) *bytes = which ? N * 16 : N * 4;
+    return which ? (void*)s->h_list_xy : (void*)s->h_list_slots;
+}
+
+int32_t rsv_commit_pos_list(rsv_space* s, uint32_t count) {
+    if (!s) return RSV_ERR_BAD_ARG;
+    if (!s->h_list_slots) return fail(s, RSV_ERR_BAD_ARG, "rsv_commit_pos_list: call rsv_pos_list_staging first");
+    if (count > s->cfg.max_shapes) return fail(s, RSV_ERR_BAD_ARG, "rsv_commit_pos_list: %u entries > capacity %u", count, s->cfg.max_shapes);
+    if (!count) return RSV_OK;
+    CU(s, cudaSetDevice(s->device));
+    CU(s, cudaMemcpyAsync(s->d_list_slots, s->h_list_slots, (size_t)count * 4, cudaMemcpyHostToDevice, s->stream));
+    CU(s, cudaMemcpyAsync(s->d_list_xy, s->h_list_xy, (size_t)count * 16, cudaMemcpyHostToDevice, s->stream));
+    k_pos_scatter<<<blocks_for(count, 256, s->sm_count * 4), 256, 0, s->stream>>>(const_cast<double2*>(s->d.pos), s->d_list_slots, s->d_list_xy,
+                                                                                 count, s->n_shapes);
+    CU(s, cudaGetLastError());
     return RSV_OK;
 }
 
@@ -486,16 +573,11 @@ int32_t rsv_commit(rsv_space* s, uint32_t which_mask, uint32_t lo, uint32_t hi) 
 int32_t rsv_sync(rsv_space* s) {
     if (!s) return RSV_ERR_BAD_ARG;
     CU(s, cudaSetDevice(s->device));
+    if (s->upload_stream) CU(s, cudaStreamSynchronize(s->upload_stream));
     CU(s, cudaStreamSynchronize(s->stream));
     return RSV_OK;
 }
 
-static inline int blocks_for(uint32_t n, int block, int cap) {
-    long long b = ((long long)n + block - 1) / block;
-    if (b < 1) b = 1;
-    if (b > cap) b = cap;
-    return (int)b;
-}
 
 // The kernels of one frame plus the counter read-back, enqueued on `st` (directly, or into a stream capture).
 // halo != nullptr: the frame of a strip-partitioned space with the halo exchange folded in (rsv_strip_frame_launch);
@@ -717,6 +799,10 @@ int32_t rsv_frame_launch(rsv_space* s, int32_t margin, uint32_t flags) {
         if (rc != RSV_OK) return rc;
     }
     CU(s, cudaEventRecord(sl.ev_done, st));
+    if (s->upload_stream) {
+        CU(s, cudaEventRecord(s->ev_page_rd[s->cur_pos_page], st));
+        s->page_rd_valid[s->cur_pos_page] = true;
+    }
     sl.flags = flags;
     sl.pending = true;
     s->launch_slot ^= 1;
@@ -796,6 +882,78 @@ int32_t rsv_frame(rsv_space* s, int32_t margin, uint32_t flags, rsv_counts* out)
     int32_t rc = rsv_frame_launch(s, margin, flags);
     if (rc != RSV_OK) return rc;
     return rsv_frame_finish(s, out);
+}
+
+// ---- explicit pair tests: Shape.Intersection(other) for a host-supplied list of ordered pairs ----------------------
+// One record per listed pair, in list order: Bounds() of both shapes from the committed positions, the exact Bounds
+// gate, the narrowphase. Used by the host layer when a callback moved a shape in the middle of an IntersectionTest
+// (shape.go:296-312 evaluates s.owner.Intersection(p.Shape) live, candidate by candidate) and for single
+// Shape.Intersection / IsIntersecting calls (circle.go:69-82, convexPolygon.go:288-300). The grid of the last frame is
+// left alone.
+static __global__ void k_pairs_from_list(DevView d, const uint32_t* __restrict__ list, uint32_t n) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) d.ctr->pair_cursor = n;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const uint32_t A = list[2 * k], B = list[2 * k + 1];
+        for (int w = 0; w < 2; w++) {
+            const uint32_t i = w ? B : A;
+            const double2 p = __ldg(d.pos + i);
+            const Box lb = load_box(d.laabb + i);
+            store_box(d.aabb + i, Box{rsv::dadd(lb.minx, p.x), rsv::dadd(lb.miny, p.y), rsv::dadd(lb.maxx, p.x), rsv::dadd(lb.maxy, p.y)});   // (same value from every writer)
+        }
+        *reinterpret_cast<uint4*>(d.hits + k) = make_uint4(A, B, 0u, k << 8);
+    }
+}
+
+void* rsv_pair_staging(rsv_space* s, uint32_t max_pairs, size_t* bytes) {
+    if (!s || !max_pairs) return nullptr;
+    if (cudaSetDevice(s->device) != cudaSuccess) return nullptr;
+    if (max_pairs > s->cap_pair_list) {
+        if (s->h_pair_list) cudaFreeHost(s->h_pair_list);
+        if (s->d_pair_list) cudaFree(s->d_pair_list);
+        s->h_pair_list = nullptr; s->d_pair_list = nullptr; s->cap_pair_list = 0;
+        if (cudaHostAlloc(&s->h_pair_list, (size_t)max_pairs * 8, cudaHostAllocDefault) != cudaSuccess ||
+            cudaMalloc(&s->d_pair_list, (size_t)max_pairs * 8) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        s->cap_pair_list = max_pairs;
+    }
+    if (bytes) *bytes = (size_t)s->cap_pair_list * 8;
+    return s->h_pair_list;
+}
+
+int32_t rsv_test_pairs(rsv_space* s, uint32_t n_pairs, rsv_counts* out) {
+    if (!s) return RSV_ERR_BAD_ARG;
+    if (n_pairs > s->cap_pair_list) return fail(s, RSV_ERR_BAD_ARG, "rsv_test_pairs: %u pairs > staged capacity %u", n_pairs, s->cap_pair_list);
+    if (n_pairs > s->d.cap_pairs) return fail(s, RSV_ERR_CAPACITY, "rsv_test_pairs: %u pairs > pair capacity %u (rsv_reserve)", n_pairs, s->d.cap_pairs);
+    for (uint32_t k = 0; k < 2 * n_pairs; k++)
+        if (s->h_pair_list[k] >= s->n_shapes) return fail(s, RSV_ERR_BAD_ARG, "rsv_test_pairs: slot %u out of range", s->h_pair_list[k]);
+    CU(s, cudaSetDevice(s->device));
+    for (auto& sl : s->slot) sl.pending = false;   // frames launched earlier and never finished are dropped
+    s->finish_slot = s->launch_slot;
+    rsv_space::FrameSlot& sl = s->slot[s->launch_slot];
+    DevView& d = s->d;
+    d.hits = sl.hits; d.contacts = sl.contacts; d.kind_queue = sl.kind_queue;
+    cudaStream_t st = s->stream;
+    k_clear<<<1, kGridBlock, 0, st>>>(reinterpret_cast<uint4*>(d.cell), 0u, d.tile_state, 0u, reinterpret_cast<uint32_t*>(d.ctr),
+                                     (uint32_t)(offsetof(Counters, ray_hit_cursor) / 4));
+    if (n_pairs) {
+        CU(s, cudaMemcpyAsync(s->d_pair_list, s->h_pair_list, (size_t)n_pairs * 8, cudaMemcpyHostToDevice, st));
+        k_pairs_from_list<<<blocks_for(n_pairs, 256, s->sm_count * 4), 256, 0, st>>>(d, s->d_pair_list, n_pairs);
+        k_bin<<<blocks_for(n_pairs, 256, s->sm_count * 8), 256, 0, st>>>(d);
+        k_bin_scatter<<<blocks_for(n_pairs, 256, s->sm_count * 4), 256, 0, st>>>(d);
+        k_narrow<1><<<s->narrow_blocks1, kNarrowBlock, 0, st>>>(d);
+        k_narrow<0><<<s->narrow_blocks, kNarrowBlock, 0, st>>>(d);
+    }
+    CU(s, cudaGetLastError());
+    CU(s, cudaMemcpyAsync(sl.h_ctr, d.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CU(s, cudaEventRecord(sl.ev_done, st));
+    sl.flags = RSV_FRAME_DOWNLOAD;
+    sl.pending = true;
+    s->launch_slot ^= 1;
+    const int32_t rc = rsv_frame_finish(s, out);
+    if (out) { out->n_testers = 0; out->n_entries = 0; out->n_candidates = n_pairs; }
+    return rc;
 }
 
 int32_t rsv_results_view(rsv_space* s, rsv_results* out) {

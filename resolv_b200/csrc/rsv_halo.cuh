@@ -143,7 +143,9 @@ __global__ void __launch_bounds__(kGridBlock) k_bounds(DevView d, int margin, Ha
     }
     uint32_t e = 0;
     int par = 0;
+    __shared__ int s_wrote;   // some thread of this block stored a record into a neighbour's mailbox
     if (HALO) {
+        if (threadIdx.x == 0) s_wrote = 0;
         e = ld_vol_u32(&h.mine->epoch) + 1u;
         par = (int)(e & 1u);
         // the neighbours must have applied what we stored into this parity two epochs ago
@@ -167,17 +169,22 @@ __global__ void __launch_bounds__(kGridBlock) k_bounds(DevView d, int margin, Ha
             if (h.dst[0][par] && r.y <= h.up_row_max) {
                 const uint32_t k = atomicAdd(&h.mine->cnt[0], 1u);
                 if (k < h.cap) h.dst[0][par][1 + k] = HaloRec{i, 0u, p.x, p.y};
+                s_wrote = 1;
             }
             if (h.dst[1][par] && r.w >= h.dn_row_min) {
                 const uint32_t k = atomicAdd(&h.mine->cnt[1], 1u);
                 if (k < h.cap) h.dst[1][par][1 + k] = HaloRec{i, 0u, p.x, p.y};
+                s_wrote = 1;
             }
         }
     }
     bounds_stats(d, my_entries, my_testers, d.subset == kSubsetDynamic && blockIdx.x == 0);
     if (HALO) {
-        __threadfence_system();   // this block's records are in the neighbours' memory before it counts as finished
+        // this block's records must be in the neighbours' memory before it counts as finished: ONE system-scope fence per
+        // block, by the thread that counts (cumulative over the block's stores through the barrier) — a fence in every
+        // thread cost 40 us per frame here
         __syncthreads();
+        if (threadIdx.x == 0 && s_wrote) __threadfence_system();   // (most blocks hold no boundary shape)
         if (threadIdx.x == 0 && atomicAdd(&h.mine->pack_done, 1u) == gridDim.x - 1u) {
             __threadfence_system();
             const uint32_t c0 = atomicAdd(&h.mine->cnt[0], 0u), c1 = atomicAdd(&h.mine->cnt[1], 0u);
@@ -236,8 +243,8 @@ __global__ void __launch_bounds__(kGridBlock) k_halo_apply_bounds(DevView d, int
         bounds_item(d, margin, valid, slot, p, my_entries, my_testers, r, meta);
     }
     bounds_stats(d, my_entries, my_testers, false);
-    __threadfence_system();
     __syncthreads();
+    if (threadIdx.x == 0) __threadfence();
     if (threadIdx.x == 0 && atomicAdd(&h.mine->apply_done, 1u) == gridDim.x * gridDim.y - 1u) {
         __threadfence_system();
         if (h.peer_done[0][par]) st_vol_u32(h.peer_done[0][par], e);

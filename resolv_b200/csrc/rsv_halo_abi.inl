@@ -257,6 +257,10 @@ int32_t rsv_strip_frame_launch(rsv_space* s, int32_t margin, uint32_t flags, int
     }
     if (!(phases & RSV_HALO_RECV)) return RSV_OK;
     CU(s, cudaEventRecord(sl.ev_done, st));
+    if (s->upload_stream) {
+        CU(s, cudaEventRecord(s->ev_page_rd[s->cur_pos_page], st));
+        s->page_rd_valid[s->cur_pos_page] = true;
+    }
     sl.flags = flags;
     sl.pending = true;
     s->launch_slot ^= 1;

@@ -376,7 +376,7 @@ def run_bench(args, rank, world, local_rank):
     for i in range(3 * N_POS_PAGES):      # the timed loop's exact call pattern (its flags and pages select its own CUDA graphs)
         ds.select_pos_page(i % N_POS_PAGES)
         sr.step_launch()
-    ds.frame_finish()
+    ds.drain()
     sampler = ClockSampler(local_rank)
     sampler.start()
     dist.barrier()
@@ -389,9 +389,19 @@ def run_bench(args, rank, world, local_rank):
     e1.record(sr.stream)
     torch.cuda.synchronize()
     c = ds.frame_finish()
+    ds.drain()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     dist.barrier()
+    # per-kernel durations on this rank over another K frames (events between the kernels; the exchange is part of `bounds`)
+    acc = {k: 0.0 for k in _abi.KERNEL_NAMES + ["frame"]}
+    for i in range(K):
+        ds.select_pos_page(i % N_POS_PAGES)
+        sr.step_launch(_abi.FRAME_TIMING)
+        ds.frame_finish()
+        t = ds.timing()
+        for k in acc:
+            acc[k] += t[k] / K
     ds.select_pos_page(0)
     # e2e, pipelined like the N = 1 leg: every step each rank uploads the positions of its owned range from a pinned
     # page, exchanges halos, runs the frame and downloads its results; the download of step i-1 (copy stream)
@@ -402,10 +412,11 @@ def run_bench(args, rank, world, local_rank):
     h2d = d2h = 0
 
     def launch(i):
-        ds.commit_pos_page(i % 2, n, 2 * n)
+        ds.pos_page_upload(i % 2, i % 2, n, 2 * n)      # (upload stream: overlaps the kernels of the frame in flight)
+        ds.select_pos_page(i % 2)
         sr.step_launch(_abi.FRAME_DOWNLOAD)
 
-    for i in range(2):    # warm this call pattern (graphs of the DOWNLOAD flag set)
+    for i in range(4):    # warm this call pattern (graphs of the DOWNLOAD flag set)
         launch(i)
         ds.frame_finish()
     torch.cuda.synchronize()
@@ -469,6 +480,7 @@ def run_bench(args, rank, world, local_rank):
                    "n_entries": int(tot[3].item())},
         "strip_counts_ok": None if check is None else check["ok"], "strip_check": check,
         "clocks": clocks,
+        "kernels_us_rank0": {k: round(v, 2) for k, v in acc.items()},
         "e2e": {"value": N * K / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int(tot[4].item()),
                 "d2h_bytes_per_step": int(tot[5].item()), "ms_per_step": 1e3 * float(te.item()) / K},
         # per rank and step: 11 frame kernels + the exchange (fused: 1 extra kernel; separate peer chain: 4; NCCL: pack + 2 applies)

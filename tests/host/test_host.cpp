@@ -95,5 +95,59 @@ int main() {
         printf("RMR %d\n", (int)player->IntersectionTest(st));
     }
     { auto si = space->StaticInfo(); printf("SI %u %u\n", si.first, si.second); }
+    // 7. the first callback's MoveVec(MTV) pushes the tester INTO a shape it did not touch before the move: the
+    //    reference tests every remaining candidate against the current world, so the wall is reported in the same call
+    Shape* block = add(NewRectangle(600, 66, 16, 8), SolidWall);               // 9
+    Shape* wall = add(NewRectangle(606, 46, 8, 11), SolidWall);                // 10
+    (void)block; (void)wall;
+    player->SetPosition(600, 59);
+    {
+        auto near = player->SelectTouchingCells(2).ByTags(SolidWall);
+        IntersectionTestSettings st;
+        st.TestAgainst = &near;
+        st.OnIntersect = [&](const IntersectionSet& set) { print_set("PW", 0, set); player->MoveVec(set.MTV); return true; };
+        player->IntersectionTest(st);
+        printf("PWP %a %a\n", player->Position().X, player->Position().Y);
+    }
+    // 8. TestAgainst = the whole Space (space.FilterShapes(), every shape in Add order), with ByDistance on top
+    player->SetPosition(100, 196);
+    {
+        auto all = space->FilterShapes().ByTags(SolidWall);
+        IntersectionTestSettings st;
+        st.TestAgainst = &all;
+        st.OnIntersect = [&](const IntersectionSet& set) { print_set("WS", 0, set); return true; };
+        player->IntersectionTest(st);
+        auto ring = space->FilterShapes().ByDistance(Vector{100, 196}, 50, 200);
+        st.TestAgainst = &ring;
+        st.OnIntersect = [&](const IntersectionSet& set) { print_set("BD", 0, set); return true; };
+        player->IntersectionTest(st);
+    }
+    // 9. more than 12 candidates with exactly equal distances: the callback order is whatever Go's pdqsort leaves
+    {
+        Shape* hub = add(NewCircle(300, 100, 5.5), Player);                    // 11
+        const int off[24][2] = {{3, 4}, {-3, 4}, {3, -4}, {-3, -4}, {4, 3}, {-4, 3}, {4, -3}, {-4, -3}, {5, 0}, {-5, 0}, {0, 5}, {0, -5},
+                                {5, 5}, {-5, 5}, {5, -5}, {-5, -5}, {1, 7}, {-1, 7}, {1, -7}, {-1, -7}, {7, 1}, {-7, 1}, {7, -1}, {-7, -1}};
+        for (auto& o : off) add(NewCircle(300 + o[0], 100 + o[1], 2), Platform);  // 12..35
+        auto near = hub->SelectTouchingCells(1).ByTags(Platform);
+        IntersectionTestSettings st;
+        st.TestAgainst = &near;
+        st.OnIntersect = [&](const IntersectionSet& set) { print_set("PQ", 0, set); return true; };
+        hub->IntersectionTest(st);
+    }
+    // 10. ShapeLineTestSettings.Lines is matched against the slice's indices, not its values (convexPolygon.go:329-340)
+    player->SetPosition(416, 190);
+    {
+        auto near = player->SelectTouchingCells(4).ByTags(Platform);
+        for (int variant = 0; variant < 3; variant++) {
+            ShapeLineTestSettings sl;
+            sl.Vec = {0, 12};
+            sl.TestAgainst = &near;
+            if (variant == 0) sl.Lines = {3};            // one element: only line 0 is considered, whatever the value
+            if (variant == 1) sl.Lines = {0};
+            if (variant == 2) sl.Lines = {9, 9, 9, 9};   // four elements: all four lines
+            sl.OnIntersect = [&](const IntersectionSet& set, int i, int n) { print_set("LQ", variant * 10000 + i * 100 + n, set); return true; };
+            printf("LQR %d %d\n", variant, (int)static_cast<ConvexPolygon*>(player)->ShapeLineTest(sl));
+        }
+    }
     return 0;
 }

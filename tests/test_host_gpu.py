@@ -24,7 +24,7 @@ def _build_and_run(tmp_path):
     for ln in out.splitlines():
         f = ln.split()
         if len(f) <= 3:
-            recs.append((f[0], [int(x) for x in f[1:]] if f[0] != "MVP" else [float.fromhex(x) for x in f[1:]]))
+            recs.append((f[0], [int(x) for x in f[1:]] if f[0] not in ("MVP", "PWP") else [float.fromhex(x) for x in f[1:]]))
         else:
             recs.append((f[0], int(f[1]), int(f[2]), int(f[3]), [float.fromhex(x) for x in f[4:]]))
     return recs
@@ -121,3 +121,72 @@ def test_host_layer_transcript_equals_oracle(tmp_path):
     # the frames above were incremental: shapes that stood still were flagged static by the host layer on its own
     si = [r[1] for r in recs if r[0] == "SI"]
     assert len(si) == 2 and si[0][0] > 0 and si[0][1] < n, si
+
+
+def _replay(sp, tester, cand, move):
+    """The reference loop (shape.go:291-312) with oracle primitives: candidates `cand` (generation order) sorted by
+    distance with the oracle's restatement of sort.Slice, Intersection() evaluated live, optional MoveVec(MTV)."""
+    from oracle.oracle import go_sort
+    p = sp.position(tester)
+    d = np.array([float((sp.position(int(b))[0] - p[0]) ** 2 + (sp.position(int(b))[1] - p[1]) ** 2) for b in cand])
+    out = []
+    for k in go_sort(d):
+        b = int(cand[k])
+        mtv, con = sp.intersection(tester, b)
+        if len(con):
+            out.append((b, len(con), mtv.tolist() + [0.0, 0.0] + con.reshape(-1).tolist()))
+            if move:
+                sp.move(tester, mtv[0], mtv[1])
+    return out
+
+
+def test_host_layer_moves_whole_space_filters_and_go_sort(tmp_path):
+    recs = _build_and_run(tmp_path)
+    sp, player, ball = _world()
+    sp.set_position(2, 1e7, 1e7)                      # (scenario 6 removed shape 2)
+    block = sp.add_rectangle(600, 66, 16, 8, SOLID)
+    wall = sp.add_rectangle(606, 46, 8, 11, SOLID)
+    n = sp.num_shapes
+    only = lambda i: np.eye(sp.num_shapes, dtype=np.uint8)[i]
+    # 7. pushed into the wall by the first MTV: the wall is reported in the same call
+    sp.set_position(player, 600, 59)
+    fc, cands, hits = sp.frame(2, tester=only(player), use_any=np.ones(n, np.uint8), any_mask=np.full(n, SOLID, np.uint64))
+    assert not any(int(b) == wall for b in hits.b), "the wall must not touch the player before the move"
+    ora = _replay(sp, player, cands["b"], move=True)
+    assert [o[0] for o in ora] == [block, wall]
+    _same([(r[2], r[3], r[4]) for r in recs if r[0] == "PW"], ora, "PW")
+    pwp = [r[1] for r in recs if r[0] == "PWP"][0]
+    assert np.array_equal(np.array(pwp).view(np.uint64), sp.position(player).view(np.uint64))
+    # 8. whole-Space iterator (Add order), then ByDistance
+    sp.set_position(player, 100, 196)
+    solid = [i for i in range(sp.num_shapes) if i != player and i in (0, 1, 2, 3, 4, 6, block, wall)]
+    _same([(r[2], r[3], r[4]) for r in recs if r[0] == "WS"], _replay(sp, player, solid, move=False), "WS")
+    ring = []
+    for i in range(sp.num_shapes):
+        q = sp.position(i)
+        dd = float(np.sqrt((q[0] - 100.0) ** 2 + (q[1] - 196.0) ** 2))
+        if i != player and 50 < dd < 200:
+            ring.append(i)
+    _same([(r[2], r[3], r[4]) for r in recs if r[0] == "BD"], _replay(sp, player, ring, move=False), "BD")
+    # 9. 24 candidates in two rings of exactly equal distances: callback order == the oracle's (pdqsort beyond 12 elements)
+    hub = sp.add_circle(300, 100, 5.5, PLAYER)
+    off = [(3, 4), (-3, 4), (3, -4), (-3, -4), (4, 3), (-4, 3), (4, -3), (-4, -3), (5, 0), (-5, 0), (0, 5), (0, -5),
+           (5, 5), (-5, 5), (5, -5), (-5, -5), (1, 7), (-1, 7), (1, -7), (-1, -7), (7, 1), (-7, 1), (7, -1), (-7, -1)]
+    for ox, oy in off:
+        sp.add_circle(300 + ox, 100 + oy, 2, PLATFORM)
+    n = sp.num_shapes
+    fc, cands, hits = sp.frame(1, tester=only(hub), use_any=np.ones(n, np.uint8), any_mask=np.full(n, PLATFORM, np.uint64))
+    assert fc.candidates == 24 and fc.hits == 24
+    ora = _sets(hits, hits.a == hub)
+    dev = [(r[2], r[3], r[4]) for r in recs if r[0] == "PQ"]
+    _same(dev, ora, "PQ")
+    assert [d[0] for d in dev] != sorted(d[0] for d in dev[:12]) + sorted(d[0] for d in dev[12:]), "order should not be the stable one"
+    # 10. the Lines quirk: {3} == {0} (only line 0 is looked at), a four-element slice == every line == no Lines
+    lq = lambda v: [(r[1] - v * 10000, r[2], r[3], r[4]) for r in recs if r[0] == "LQ" and r[1] // 10000 == v]
+    assert lq(0) == lq(1) == []          # line 0 is the top edge: it does not face the cast direction, no rays, no sets
+    sp.set_position(player, 416, 190)
+    sh = sp.shape_linetest(player, (0.0, 12.0), margin=4, use_any=True, any_mask=PLATFORM)
+    ora = _sets(sh, sh.a == player)
+    _same([(r[1], r[2], r[3][:2] + [0.0, 0.0] + r[3][4:]) for r in lq(2)], [(o[0], o[1], o[2]) for o in ora], "LQ all lines")
+    lqr = {r[1][0]: r[1][1] for r in recs if r[0] == "LQR"}
+    assert lqr == {0: 0, 1: 0, 2: 1} and len(ora) >= 1
