@@ -151,6 +151,21 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def pcie_fraction(n_gpus, h2d_total, d2h_total, seconds_per_step):
+    """How much of the box's measured host <-> device bandwidth the e2e leg uses: the busier direction's bytes per rank
+    and step over the step time, against what scripts/measure_pcie.py measured on this pool with n_gpus ranks copying
+    both ways at once (profiles/r2_pcie.json). {} when no measurement for this rank count is committed."""
+    try:
+        rows = json.load(open(os.path.join(ROOT, "profiles", "r2_pcie.json")))
+        row = next(r for r in rows if r["n_gpus"] == n_gpus)
+    except Exception:
+        return {}
+    per_rank = max(h2d_total, d2h_total) / max(n_gpus, 1)
+    got = per_rank / seconds_per_step / 1e9
+    return {"pcie_gbs_per_rank": got, "pcie_peak_gbs_per_rank": row["both_gbs_per_rank_per_direction"],
+            "pcie_frac": got / row["both_gbs_per_rank_per_direction"], "pcie_peak_source": "profiles/r2_pcie.json (scripts/measure_pcie.py)"}
+
+
 def kernel_algorithmic_bytes(c, w, n_cells, filters=False):
     """Algorithmic bytes each kernel must move per launch: every datum counted once per kernel
     (caches assumed perfect within a kernel), gathers counted at the size of the datum, atomics as 8 B (RMW)."""
@@ -158,9 +173,9 @@ def kernel_algorithmic_bytes(c, w, n_cells, filters=False):
     vb = 16.0 * float(w.nv.sum()) / max(N, 1)   # average vertex bytes per shape
     C1 = n_cells + 1
     return {
-        "clear": 4 * C1,                                   # zero the per-cell counters
+        "clear": 8 * (C1 // 8192 + 1) + 256,               # scan tile states + frame counters (the per-cell counters are zeroed by the scan)
         "bounds": N * (16 + 32 + 4) + N * (32 + 16 + 4) + 8 * R,   # pos, local AABB, meta -> AABB, cell rect, table reset; one RED per entry
-        "scan": 8 * C1,                                    # counters in, offsets out
+        "scan": 12 * C1,                                   # counters in, zeros back over them, offsets out
         "scatter": N * (16 + 4) + 8 * R + 4 * R,           # cell rect, meta; cursor RMW per entry; entry word out
         "cellsort": 4 * C1 + 8 * R + (4 * R + 32 * N + 16 * R) + (16 * R if filters else 0) + 8 * N,
         # offsets, entries in/out; k_entboxes: entries, each AABB once, float boxes out (+ tags in, per-entry tags out), home records
@@ -394,7 +409,8 @@ def run_b200(args):
         "parity_counts_ok": None if parity is None else parity["ok"],
         "parity": parity,
         "clocks": clocks,
-        "e2e": {"value": N * K / e2e_t, "unit": UNIT, "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K,
+        "e2e": {**pcie_fraction(1, h2d // K, d2h // K, e2e_t / K),
+                "value": N * K / e2e_t, "unit": UNIT, "h2d_bytes_per_step": h2d // K, "d2h_bytes_per_step": d2h // K,
                 "ms_per_step": 1e3 * e2e_t / K, "mode": "pipelined: two frames in flight; H2D of step i (upload stream) and D2H of step i-1 (copy stream) overlap the kernels",
                 "sequential_ms_per_step": 1e3 * e2e_seq / K, "sequential_value": N * K / e2e_seq},
         # kernels of this library launched inside the timed `value` region, per frame: k_clear, k_bounds, k_scan, k_scatter,
@@ -423,20 +439,46 @@ def run_b200(args):
 
 def ray_sweep(args, ds, w, batch=2_000_000):
     """cfg5's LineTest sweep on the grid of the last frame: args.rays segments (start uniform, direction uniform,
-    16-512 px), in batches, DDA iterator; device time of the line kernel (CUDA events on the library's stream)."""
+    16-512 px), in batches; device time of the line kernel (CUDA events on the library's stream). Two iterators:
+    RECT — space.FilterCells(bounds of the cast line).FilterShapes(), the reference-expressible TestAgainst, results
+    equal to the reference's for that iterator bit for bit — is the headline; DDA (cells under the cast line only; a
+    documented non-reference iterator that skips far-away "+1 fudge" phantoms) is reported next to it. A 1 % sample of
+    the rays is also run through the CPU oracle with the RECT iterator: hit and contact counts must be equal."""
     from resolv_b200 import _abi, worlds
-    tot_us, hits, cands, done = 0.0, 0, 0, 0
+    ds.select_pos_page(0)
+    ds.set_positions(w.pos)          # the world's current positions (the ones the CPU sample below sees)
     ds.frame(w.margin, _abi.FRAME_GRID_ONLY)
-    while done < args.rays:
-        n = min(batch, args.rays - done)
-        rays = worlds.make_rays(n, 20265 + done, w.space_w, w.space_h)
-        rc = ds.linetest(rays, flags=_abi.LINE_DDA)
-        tot_us += rc.kernel_us
-        hits += int(rc.n_hits)
-        cands += int(rc.n_candidates)
-        done += n
-    return {"n_rays": done, "iterator": "DDA", "kernel_ms": tot_us / 1e3, "rays_per_sec": done / (tot_us * 1e-6),
-            "n_candidates": cands, "n_hits": hits}
+    out = {}
+    for name, fl in (("rect", 0), ("dda", _abi.LINE_DDA)):
+        tot_us, hits, cands, done = 0.0, 0, 0, 0
+        while done < args.rays:
+            n = min(batch, args.rays - done)
+            rays = worlds.make_rays(n, 20265 + done, w.space_w, w.space_h)
+            rc = ds.linetest(rays, flags=fl)
+            tot_us += rc.kernel_us
+            hits += int(rc.n_hits)
+            cands += int(rc.n_candidates)
+            done += n
+        out[name] = {"kernel_ms": tot_us / 1e3, "rays_per_sec": done / (tot_us * 1e-6), "n_candidates": cands, "n_hits": hits}
+    res = {"n_rays": args.rays, "iterator": "RECT == space.FilterCells(bounds of the cast line).FilterShapes()",
+           "kernel_ms": out["rect"]["kernel_ms"], "rays_per_sec": out["rect"]["rays_per_sec"], "n_candidates": out["rect"]["n_candidates"],
+           "n_hits": out["rect"]["n_hits"], "dda": out["dda"]}
+    if not args.no_cpu_baseline and w.n <= 4_000_000:   # (the oracle would need minutes just to build a 16 M-shape Space)
+        import time as _t
+        from oracle import oracle as orc
+        m = max(args.rays // 100, 1000)
+        rays = worlds.make_rays(m, 20265, w.space_w, w.space_h)          # == the first m rays of the sweep
+        sp = oracle_space(w)
+        th = args.cpu_threads or orc.hardware_threads() or 1
+        t0 = _t.perf_counter()
+        fc, _ = sp.linetest(rays, record=False, threads=th, mode="rect")
+        dt = _t.perf_counter() - t0
+        rc = ds.linetest(rays, flags=0)
+        res["cpu_baseline"] = {"value": m / dt, "unit": "rays/s", "cores": th, "kind": "port",
+                               "sample": f"the first {m} rays of the sweep (1 %), RECT iterator, oracle port on {th} threads",
+                               "parity_counts_ok": bool(int(rc.n_hits) == int(fc.hits) and int(rc.n_contacts) == int(fc.contacts)),
+                               "device": [int(rc.n_hits), int(rc.n_contacts)], "oracle": [int(fc.hits), int(fc.contacts)]}
+    return res
 
 
 def run_cfg4(args, rank, world, local_rank):
@@ -470,12 +512,20 @@ def run_cfg4(args, rank, world, local_rank):
         msk[:, 1] = 0
         msk[:, 2] = (np.asarray(use_any, np.uint64) & np.uint64(1)) | (np.asarray(sidx, np.uint64) << np.uint64(32))
 
+    bd = {}      # host clock around every ABI call of the e2e step
+
+    def timed(name, fn):
+        t0 = time.perf_counter()
+        r = fn()
+        bd[name] = bd.get(name, 0.0) + time.perf_counter() - t0
+        return r
+
     def step(i, download, resident):
-        ds.frame_launch(w.margin, flags | (_abi.FRAME_DOWNLOAD if download else 0))
-        ds._check(L.rsv_linetest_launch(ds.h, n_rays, (_abi.FRAME_DOWNLOAD if download else 0) | (_abi.LINE_RESIDENT if resident else 0)))
-        c = ds.frame_finish()
+        timed("frame_launch", lambda: ds.frame_launch(w.margin, flags | (_abi.FRAME_DOWNLOAD if download else 0)))
+        timed("linetest_launch", lambda: ds._check(L.rsv_linetest_launch(ds.h, n_rays, (_abi.FRAME_DOWNLOAD if download else 0) | (_abi.LINE_RESIDENT if resident else 0))))
+        c = timed("frame_finish", lambda: ds.frame_finish())
         rc = _abi.RayCounts()
-        ds._check(L.rsv_linetest_finish(ds.h, C.byref(rc)))
+        timed("linetest_finish", lambda: ds._check(L.rsv_linetest_finish(ds.h, C.byref(rc))))
         return c, rc
 
     # warm-up: sizes the buffers, builds the static cache, captures the graphs
@@ -484,6 +534,8 @@ def run_cfg4(args, rank, world, local_rank):
     ds.linetest(probes[0][0], use_any=probes[0][1], any_mask=probes[0][2], space_idx=probes[0][3])
     for i in range(max(W, 6)):
         c, rc = step(i, False, True)
+    for i in range(2):      # the e2e call pattern too (its graphs, its pinned mirrors)
+        step(i, True, False)
     sampler = ClockSampler(local_rank)
     sampler.start()
     if world > 1:
@@ -507,11 +559,12 @@ def run_cfg4(args, rank, world, local_rank):
     bodies = np.nonzero(w.tester != 0)[0].astype(np.uint32)        # only the bodies move: only their positions go up
     list_slots, list_xy = ds.pos_list()
     list_slots[:len(bodies)] = bodies
+    bd.clear()
     for i in range(K):
         list_xy[:2 * len(bodies)] = frames[i % len(frames)][bodies].reshape(-1)   # the game moving its bodies and aiming its probes (untimed)
         stage_rays(i)
         t0 = time.perf_counter()
-        ds.commit_pos_list(len(bodies))
+        timed("commit_pos_list", lambda: ds.commit_pos_list(len(bodies)))
         ce, re_ = step(i, True, False)
         e2e_t += time.perf_counter() - t0
         h2d += 20 * len(bodies) + 56 * n_rays
@@ -544,7 +597,8 @@ def run_cfg4(args, rank, world, local_rank):
         "clocks": clocks,
         "e2e": {"value": N * K / float(tot[1].item()), "unit": UNIT, "h2d_bytes_per_step": int(cnt[6].item()), "d2h_bytes_per_step": int(cnt[7].item()),
                 "ms_per_step": 1e3 * float(tot[1].item()) / K,
-                "mode": "sequential: sparse position update of the bodies (rsv_commit_pos_list) -> frame + probes -> download"},
+                "mode": "sequential: sparse position update of the bodies (rsv_commit_pos_list) -> frame + probes -> download",
+                "breakdown_ms_rank0": {k: round(1e3 * v / K, 3) for k, v in bd.items()}},
         # per GPU and step: k_clear, k_bounds, k_scan<true>, k_static_place, k_scatter, k_cellfix, k_pairs, k_bin, k_bin_scatter, k_narrow x2, k_linetest
         "gpu_launches": K * 12 * world,
         "roofline": {"bound": "hbm", "kernel": "frame", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,

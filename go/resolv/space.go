@@ -33,6 +33,8 @@ type Space struct {
 	moveEpoch, frameEpoch uint64 // bumped by every move / edit; value at the last device frame
 	testerFirst           []uint32
 	testerCount           []uint32
+	cellEnds, cellEntries []uint32 // snapshot of the device grid (Space.Cell / FilterCells), valid for cellEpoch
+	cellEpoch             uint64
 
 	// dirty tracking + static / dynamic classification for incremental frames (RSV_META_STATIC, RSV_FRAME_INCREMENTAL)
 	fullCommit, metaDirty bool
@@ -318,32 +320,64 @@ func (s *Space) testPairs(pairs [][2]IShape) []IntersectionSet {
 	return out
 }
 
-// shapesInCells — the shapes registered in the cell rect, row-major, first occurrence only (cell.go:86-121), read back
-// from the device grid of the last frame (rsv_debug_cells). Only explicit Space.FilterCells selections come here.
-func (s *Space) shapesInCells(x0, y0, x1, y1 int) ShapeCollection {
+// Cell — cell.go:4-7, space.go:135-142: a read-only snapshot of cell (cx, cy) of the device grid after the last frame
+// (nil outside the grid). Shapes are in the cell's stored order (ascending Add order: the order of a freshly built
+// reference Space).
+type Cell struct {
+	X, Y   int
+	Shapes []IShape
+}
+
+func (s *Space) Cell(cx, cy int) *Cell {
+	if cx < 0 || cy < 0 || cx >= s.width || cy >= s.height {
+		return nil
+	}
+	s.snapshotCells()
+	c := cy*s.width + cx
+	lo := uint32(0)
+	if c > 0 {
+		lo = s.cellEnds[c-1]
+	}
+	cell := &Cell{X: cx, Y: cy}
+	for _, slot := range s.cellEntries[lo:s.cellEnds[c]] {
+		cell.Shapes = append(cell.Shapes, s.shapes[slot])
+	}
+	return cell
+}
+
+// snapshotCells reads the cell membership of the current positions back from the device (rsv_debug_cells), once per
+// move epoch.
+func (s *Space) snapshotCells() {
+	if !s.stale && s.cellEpoch == s.frameEpoch && s.cellEnds != nil {
+		return
+	}
 	s.ensureFrame(maxInt(s.margin, 1))
 	nCells := s.width * s.height
-	ends := make([]uint32, nCells)
-	C.rsv_debug_cells(s.h, (*C.uint32_t)(unsafe.Pointer(&ends[0])), C.uint64_t(nCells), nil, 0)
-	total := 0
-	if nCells > 0 {
-		total = int(ends[nCells-1])
+	s.cellEnds = make([]uint32, nCells)
+	C.rsv_debug_cells(s.h, (*C.uint32_t)(unsafe.Pointer(&s.cellEnds[0])), C.uint64_t(nCells), nil, 0)
+	total := int(s.cellEnds[nCells-1])
+	s.cellEntries = make([]uint32, total+1)
+	if total > 0 {
+		C.rsv_debug_cells(s.h, nil, 0, (*C.uint32_t)(unsafe.Pointer(&s.cellEntries[0])), C.uint64_t(total))
 	}
+	s.cellEntries = s.cellEntries[:total]
+	s.cellEpoch = s.frameEpoch
+}
+
+// shapesInCells — the shapes registered in the cell rect, row-major, first occurrence only (cell.go:86-121), from the
+// snapshot of the device grid. Only explicit Space.FilterCells selections come here.
+func (s *Space) shapesInCells(x0, y0, x1, y1 int) ShapeCollection {
+	s.snapshotCells()
 	var out ShapeCollection
-	if total == 0 {
-		return out
-	}
-	entries := make([]uint32, total)
-	C.rsv_debug_cells(s.h, nil, 0, (*C.uint32_t)(unsafe.Pointer(&entries[0])), C.uint64_t(total))
 	seen := map[uint32]bool{}
 	for y := maxInt(y0, 0); y <= y1 && y < s.height; y++ {
 		for x := maxInt(x0, 0); x <= x1 && x < s.width; x++ {
 			c := y*s.width + x
 			lo := uint32(0)
 			if c > 0 {
-				lo = ends[c-1]
+				lo = s.cellEnds[c-1]
 			}
-			for _, slot := range entries[lo:ends[c]] {
+			for _, slot := range s.cellEntries[lo:s.cellEnds[c]] {
 				if !seen[slot] {
 					seen[slot] = true
 					out = append(out, s.shapes[slot])

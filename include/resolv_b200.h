@@ -103,6 +103,8 @@ typedef struct rsv_counts {
 #define RSV_OVF_ENTRIES 0x1u
 #define RSV_OVF_PAIRS 0x2u
 #define RSV_OVF_CONTACTS 0x4u
+#define RSV_OVF_PAIR_CONTACTS 0x40u /* ONE pair produced more than 127 contacts (count_rank holds 7 bits): not a buffer size,
+                                        rsv_reserve + retry cannot fix it */
 
 /* One record per AABB-gated ordered pair, grouped by tester (all records of one tester are contiguous and in the
  * reference's candidate generation order: row-major cell walk, in-cell order, first occurrence; cell.go:86-121).

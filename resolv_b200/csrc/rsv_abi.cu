@@ -248,6 +248,11 @@ int32_t rsv_create(const rsv_config* cfg, rsv_space** out) {
             return fail(nullptr, RSV_ERR_BAD_ARG, "rsv_create: strip [%d,%d) not inside [0,%d)", row_lo, row_hi, H);
         }
     }
+    // (home records pack a shape's clamped column / row span into 16 bits each: rsv_grid.cuh k_entboxes)
+    if (W > 65536 || row_hi - row_lo > 65536) {
+        delete s;
+        return fail(nullptr, RSV_ERR_BAD_ARG, "rsv_create: %d x %d cells: at most 65536 columns and 65536 stored rows are supported", W, row_hi - row_lo);
+    }
     uint32_t n_spaces = cfg->n_spaces ? cfg->n_spaces : 1;
     unsigned long long cps = (unsigned long long)W * (unsigned long long)(row_hi - row_lo);
     unsigned long long n_cells = cps * n_spaces;
@@ -299,6 +304,8 @@ int32_t rsv_create(const rsv_config* cfg, rsv_space** out) {
     s->n_tiles = (uint32_t)((n_cells + 1 + kScanTile - 1) / kScanTile);
     CUC(cudaMalloc(&d.cell, ((size_t)s->n_tiles * kScanTile + 16) * 4));   // (+16: 16-byte-aligned row windows of the tile kernel)
     CUC(cudaMemsetAsync(d.cell, 0, ((size_t)s->n_tiles * kScanTile) * 4, s->stream));
+    CUC(cudaMalloc(&d.cnt, ((size_t)s->n_tiles * kScanTile + 16) * 4));
+    CUC(cudaMemsetAsync(d.cnt, 0, ((size_t)s->n_tiles * kScanTile + 16) * 4, s->stream));
     CUC(cudaMalloc(&d.tile_state, (size_t)s->n_tiles * 8));
     CUC(cudaMalloc(&d.tester_start, (size_t)N * 4));
     CUC(cudaMalloc(&d.tester_count, (size_t)N * 4));
@@ -345,7 +352,7 @@ int32_t rsv_destroy(rsv_space* s) {
         if (s->host_buf[b]) cudaFreeHost(s->host_buf[b]);
     }
     DevView& d = s->d;
-    void* dev[] = {d.aabb, d.crect, d.cell, d.entries, d.ent_box, d.ent_home, d.ent_tags, d.multi, d.tile_state, d.tester_start, d.tester_count, d.orphans, d.ghosts, d.n_ghosts, d.ctr};
+    void* dev[] = {d.aabb, d.crect, d.cell, d.cnt, d.entries, d.ent_box, d.ent_home, d.ent_tags, d.multi, d.tile_state, d.tester_start, d.tester_count, d.orphans, d.ghosts, d.n_ghosts, d.ctr};
     for (void* p : dev) if (p) cudaFree(p);
     if (s->h_ctr) cudaFreeHost(s->h_ctr);
     if (s->host_pos_page1) cudaFreeHost(s->host_pos_page1);
@@ -590,13 +597,8 @@ static int32_t enqueue_frame(rsv_space* s, const DevView& d, int32_t margin, uin
     const uint32_t max_items = inc ? d.n_dyn : (d.own_hi - d.own_lo) + ((d.n_ghosts && !halo) ? d.cap_ghosts : 0u);
     if (phases & RSV_HALO_SEND) {
         mark(RSV_K_CLEAR);
-        {
-            // the cell array is allocated in whole scan tiles, so it can be cleared 16 B at a time past n_cells + 1
-            const uint32_t n4 = (uint32_t)(((size_t)d.n_cells + 1 + 3) / 4);
-            k_clear<<<blocks_for(n4, kGridBlock, s->sm_count * 8), kGridBlock, 0, st>>>(
-                reinterpret_cast<uint4*>(d.cell), n4, d.tile_state, s->n_tiles, reinterpret_cast<uint32_t*>(d.ctr),
-                (uint32_t)(offsetof(Counters, ray_hit_cursor) / 4));
-        }
+        k_clear<<<4, kGridBlock, 0, st>>>(d.tile_state, s->n_tiles, reinterpret_cast<uint32_t*>(d.ctr),
+                                         (uint32_t)(offsetof(Counters, ray_hit_cursor) / 4));
         mark(RSV_K_BOUNDS);
         // (an incremental frame launches k_bounds even without dynamic shapes: it carries the static counts over)
         if (halo) {
@@ -614,9 +616,9 @@ static int32_t enqueue_frame(rsv_space* s, const DevView& d, int32_t margin, uin
     if (halo) k_halo_apply_bounds<<<dim3(blocks_for(halo->cap, kGridBlock, s->sm_count), 2), kGridBlock, 0, st>>>(d, margin, *halo);
     mark(RSV_K_SCAN);
     const int scan_blocks = (d.n_cells + 1 + kScanTile - 1) / kScanTile;
-    if (inc) k_scan<true><<<scan_blocks, kScanBlock, 0, st>>>(d.cell, d.n_cells + 1, d.tile_state, &d.ctr->scan_ticket, d.multi,
+    if (inc) k_scan<true><<<scan_blocks, kScanBlock, 0, st>>>(d.cnt, d.cell, d.n_cells + 1, d.tile_state, &d.ctr->scan_ticket, d.multi,
                                                               &d.ctr->n_multi, d.cap_multi, s->sg.count);
-    else k_scan<false><<<scan_blocks, kScanBlock, 0, st>>>(d.cell, d.n_cells + 1, d.tile_state, &d.ctr->scan_ticket, d.multi,
+    else k_scan<false><<<scan_blocks, kScanBlock, 0, st>>>(d.cnt, d.cell, d.n_cells + 1, d.tile_state, &d.ctr->scan_ticket, d.multi,
                                                            &d.ctr->n_multi, d.cap_multi, nullptr);
     mark(RSV_K_SCATTER);
     if (inc && d.static_entries) k_static_place<<<blocks_for(d.static_entries, kGridBlock, gcap), kGridBlock, 0, st>>>(d, s->sg, flags);
@@ -710,10 +712,8 @@ static int32_t build_static(rsv_space* s) {
     v.subset = kSubsetStaticBuild;
     v.cell = sg.cell;
     const int gcap = s->sm_count * 8;
-    const uint32_t n4 = (uint32_t)(((size_t)d.n_cells + 1 + 3) / 4);
-    k_clear<<<blocks_for(n4, kGridBlock, gcap), kGridBlock, 0, st>>>(reinterpret_cast<uint4*>(sg.cell), n4, d.tile_state, s->n_tiles,
-                                                                     reinterpret_cast<uint32_t*>(d.ctr),
-                                                                     (uint32_t)(offsetof(Counters, ray_hit_cursor) / 4));
+    k_clear<<<4, kGridBlock, 0, st>>>(d.tile_state, s->n_tiles, reinterpret_cast<uint32_t*>(d.ctr),
+                                     (uint32_t)(offsetof(Counters, ray_hit_cursor) / 4));
     CU(s, cudaMemsetAsync(d.n_dyn_dev, 0, 4, st));
     const uint32_t items = d.own_hi - d.own_lo;
     if (items) k_bounds<false><<<blocks_for(items, kGridBlock, gcap), kGridBlock, 0, st>>>(v, 0, HaloArgs{});
@@ -738,7 +738,7 @@ static int32_t build_static(rsv_space* s) {
         sg.cap = cap;
     }
     v.entries = sg.entries; v.ent_box = sg.ent_box; v.ent_home = sg.ent_home; v.ent_tags = sg.ent_tags; v.cap_entries = sg.cap;
-    k_scan<false><<<(d.n_cells + 1 + kScanTile - 1) / kScanTile, kScanBlock, 0, st>>>(sg.cell, d.n_cells + 1, d.tile_state, &d.ctr->scan_ticket,
+    k_scan<false><<<(d.n_cells + 1 + kScanTile - 1) / kScanTile, kScanBlock, 0, st>>>(d.cnt, sg.cell, d.n_cells + 1, d.tile_state, &d.ctr->scan_ticket,
                                                                                      d.multi, &d.ctr->n_multi, d.cap_multi, nullptr);
     if (items) k_scatter<<<blocks_for(items, kGridBlock, gcap), kGridBlock, 0, st>>>(v);
     k_cellsort<<<blocks_for(std::min<uint32_t>(d.n_cells, d.cap_multi), kGridBlock, gcap), kGridBlock, 0, st>>>(v);
@@ -857,13 +857,23 @@ int32_t rsv_frame_finish(rsv_space* s, rsv_counts* out) {
         s->timing.frame_us *= 1000.f;
     }
     s->last_records = 0; s->last_contacts = 0;
+    if (rc.overflow & RSV_OVF_PAIR_CONTACTS)
+        return fail(s, RSV_ERR_CAPACITY, "rsv_frame: a pair produced more than 127 contacts (the per-pair count is 7 bits wide); "
+                    "rsv_reserve cannot fix this: split polygons with very many vertices");
+    if (rc.overflow & RSV_OVF_GHOSTS)
+        return fail(s, RSV_ERR_CAPACITY, "rsv_frame: more halo records than the ghost list / mailbox holds (results incomplete): "
+                    "grow max_ghosts (rsv_strip_setup) and the mailbox capacity (rsv_halo_mailbox)");
     if (rc.overflow)
         return fail(s, RSV_ERR_CAPACITY, "rsv_frame: capacity exceeded (need entries=%llu pairs=%llu contacts=%llu; have %u/%u/%u)",
                     (unsigned long long)rc.n_entries, (unsigned long long)rc.n_gated, (unsigned long long)rc.n_contacts,
                     s->d.cap_entries, s->d.cap_pairs, s->d.cap_contacts);
     if (s->launched_flags & RSV_FRAME_DOWNLOAD) {
-        int32_t rcode = ensure_mirrors(s, sl);
-        if (rcode != RSV_OK) return rcode;
+        // (both result slots at once: pinning a few hundred MB takes tens of milliseconds and must not land in the middle
+        // of a host's steady state when the second slot is first used)
+        for (auto& each : s->slot) {
+            int32_t rcode = ensure_mirrors(s, each);
+            if (rcode != RSV_OK) return rcode;
+        }
         // on the copy stream: overlaps the upload and kernels of a newer frame already queued on `stream`
         if (rc.n_gated) CU(s, cudaMemcpyAsync(sl.h_hits, sl.hits, (size_t)rc.n_gated * sizeof(rsv_hit), cudaMemcpyDeviceToHost, s->copy_stream));
         if (rc.n_contacts) CU(s, cudaMemcpyAsync(sl.h_contacts, sl.contacts, (size_t)rc.n_contacts * sizeof(rsv_contact), cudaMemcpyDeviceToHost, s->copy_stream));
@@ -935,8 +945,7 @@ int32_t rsv_test_pairs(rsv_space* s, uint32_t n_pairs, rsv_counts* out) {
     DevView& d = s->d;
     d.hits = sl.hits; d.contacts = sl.contacts; d.kind_queue = sl.kind_queue;
     cudaStream_t st = s->stream;
-    k_clear<<<1, kGridBlock, 0, st>>>(reinterpret_cast<uint4*>(d.cell), 0u, d.tile_state, 0u, reinterpret_cast<uint32_t*>(d.ctr),
-                                     (uint32_t)(offsetof(Counters, ray_hit_cursor) / 4));
+    k_clear<<<1, kGridBlock, 0, st>>>(d.tile_state, 0u, reinterpret_cast<uint32_t*>(d.ctr), (uint32_t)(offsetof(Counters, ray_hit_cursor) / 4));
     if (n_pairs) {
         CU(s, cudaMemcpyAsync(s->d_pair_list, s->h_pair_list, (size_t)n_pairs * 8, cudaMemcpyHostToDevice, st));
         k_pairs_from_list<<<blocks_for(n_pairs, 256, s->sm_count * 4), 256, 0, st>>>(d, s->d_pair_list, n_pairs);

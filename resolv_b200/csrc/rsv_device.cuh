@@ -53,6 +53,7 @@ struct DevView {
     Box* aabb;            // world Bounds() per shape (circle.go:33-39, convexPolygon.go:158-161)
     int4* crect;          // Bounds.toCellSpace() per shape (utils.go:90-98), clamped to +-2^30
     uint32_t* cell;       // [n_cells+1]: after the frame, cell c holds entries[cell[c] .. cell[c+1])
+    uint32_t* cnt;        // [n_cells+1]: per-cell registration counters of the running frame; zero between frames (k_scan)
     uint32_t* entries;    // shape slot << 6 | flag bits (rsv_grid.cuh), ascending per cell
     float4* ent_box;      // per entry: outward-rounded float32 copy of the shape's world AABB (minx,miny,maxx,maxy)
     unsigned long long* ent_tags;  // per entry: the shape's tags (written only in frames that use tag filters)

@@ -73,7 +73,9 @@ __device__ __forceinline__ void warp_big_rects(bool big, int x0, int y0, int x1,
 // the owned shapes that reach a neighbour's stored rows straight into that neighbour's mailbox while it registers
 // them, its last block publishes the counts and raises the neighbours' `ready` flags; k_halo_apply_bounds then waits
 // for this device's own flags, applies the received positions and registers the ghosts. Epochs live on the device, so
-// a strip frame is one fixed launch sequence (one CUDA graph).
+// a strip frame is one fixed launch sequence (one CUDA graph). (Tried: a separate pack + publish pass IN FRONT of
+// k_clear / k_bounds so that the neighbours' batches travel while the owned shapes are registered — the extra pass
+// over the owned shapes cost 28 us and the frame got slower, 0.501 against 0.485 ms at N = 2.)
 struct HaloRec;
 struct HaloMailboxHeader;
 struct HaloArgs {
@@ -140,12 +142,12 @@ __device__ __forceinline__ void bounds_item(const DevView& d, int margin, bool v
             if (!big)
                 for (int y = y0; y <= y1; y++) {
                     uint32_t row = base + (uint32_t)(y - d.row_lo) * (uint32_t)d.W;
-                    for (int x = x0; x <= x1; x++) atomicAdd(d.cell + row + x + 1, 1u);
+                    for (int x = x0; x <= x1; x++) atomicAdd(d.cnt + row + x + 1, 1u);
                 }
         }
     }
     warp_big_rects(big, x0, y0, x1, y1, 0u, base, [&](int x, int y, int, int, int, int, uint32_t, uint32_t bb) {
-        atomicAdd(d.cell + bb + (uint32_t)(y - d.row_lo) * (uint32_t)d.W + x + 1, 1u);
+        atomicAdd(d.cnt + bb + (uint32_t)(y - d.row_lo) * (uint32_t)d.W + x + 1, 1u);
     });
     if (d.subset == kSubsetStaticBuild) {   // warp-aggregated append keeps dyn_list nearly in slot order
         const uint32_t lm = __ballot_sync(0xffffffffu, listed);
@@ -181,18 +183,20 @@ __device__ __forceinline__ void st_vol_u32(uint32_t* p, uint32_t v) { *reinterpr
 template <bool HALO>
 __global__ void __launch_bounds__(kGridBlock) k_bounds(DevView d, int margin, HaloArgs h);
 
-// Zeroes everything a frame accumulates into:// Zeroes everything a frame accumulates into: per-cell counters, scan tile states, frame counters. One launch.
-__global__ void __launch_bounds__(kGridBlock) k_clear(uint4* __restrict__ cell4, uint32_t n4, unsigned long long* __restrict__ state,
-                                                      uint32_t n_tiles, uint32_t* __restrict__ ctr_words, uint32_t n_ctr_words) {
+// Zeroes what a frame accumulates into besides the per-cell counters (those are zeroed by k_scan as it consumes them):
+// scan tile states and frame counters. One small launch.
+__global__ void __launch_bounds__(kGridBlock) k_clear(unsigned long long* __restrict__ state, uint32_t n_tiles,
+                                                      uint32_t* __restrict__ ctr_words, uint32_t n_ctr_words) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-    for (uint32_t i = tid; i < n4; i += stride) cell4[i] = make_uint4(0u, 0u, 0u, 0u);
     for (uint32_t i = tid; i < n_tiles; i += stride) state[i] = 0ull;
     for (uint32_t i = tid; i < n_ctr_words; i += stride) ctr_words[i] = 0u;
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Single-pass chained exclusive scan of uint32, in place: one read and one write of the array. Tiles take their id
-// from an atomic ticket so a tile only ever waits on tiles that already started.
+// Single-pass chained exclusive scan of uint32: one read of the counters, one write of the offsets — and one write of
+// zeros over the counters, so that the next frame finds them cleared (a separate 4 (C + 1)-byte clear kernel cost
+// 10 us per frame; this kernel is one latency-bound wave and the extra stores ride along). Tiles take their id from an
+// atomic ticket so a tile only ever waits on tiles that already started.
 constexpr int kScanBlock = 256;
 constexpr int kScanItems = 32;  // per thread, as 8 lane-striped uint4 (every load instruction reads 512 contiguous bytes); 64 -> 32: 25 -> 20 us (513 tiles, 64 registers)
 constexpr int kScanTile = kScanBlock * kScanItems;
@@ -206,9 +210,9 @@ __device__ __forceinline__ void st_state(unsigned long long* p, unsigned long lo
     *reinterpret_cast<volatile unsigned long long*>(p) = v;
 }
 
-// In-place exclusive scan of the per-cell counters (data[c + 1] = count of cell c on entry, = first entry of cell c on
-// exit; data[0] = 0). Also appends every cell that holds two or more entries to `multi` — the only cells whose
-// entries k_cellsort has to order.
+// Exclusive scan of the per-cell counters (data[c + 1] = count of cell c) into out[c + 1] = first entry of cell c
+// (out[0] = 0); data is left zeroed. Also appends every cell that holds two or more entries to `multi` — the only
+// cells whose entries k_cellsort has to order.
 //
 // MERGE (incremental frames): `data` holds the counts of the DYNAMIC registrations only and `scount` the static
 // ones of the cached static grid, in the same layout. The scan runs over dynamic + static counts, and
@@ -216,7 +220,7 @@ __device__ __forceinline__ void st_state(unsigned long long* p, unsigned long lo
 // the cell by k_static_place and the cursor atomics of k_scatter append the dynamic ones behind them. `multi` then
 // lists the cells that received at least one dynamic registration (k_cellfix).
 template <bool MERGE>
-__global__ void __launch_bounds__(kScanBlock) k_scan(uint32_t* __restrict__ data, uint32_t n,
+__global__ void __launch_bounds__(kScanBlock) k_scan(uint32_t* __restrict__ data, uint32_t* __restrict__ out, uint32_t n,
                                                      unsigned long long* __restrict__ state, unsigned int* ticket,
                                                      uint32_t* __restrict__ multi, unsigned int* n_multi, uint32_t cap_multi,
                                                      const uint32_t* __restrict__ scount) {
@@ -230,11 +234,12 @@ __global__ void __launch_bounds__(kScanBlock) k_scan(uint32_t* __restrict__ data
     const uint32_t wbase = tile * kScanTile + warp * kWarpItems;
     // group g of lane l covers items wbase + (g * 32 + l) * 4 .. + 3 (the array is allocated in whole tiles)
     uint4 q[kGroups];
-    const uint4* src = reinterpret_cast<const uint4*>(data + wbase) + lane;
+    uint4* src = reinterpret_cast<uint4*>(data + wbase) + lane;
 #pragma unroll
     for (int g = 0; g < kGroups; g++) {
         const uint32_t e0 = wbase + (g * 32 + lane) * 4;
         q[g] = e0 < n ? src[g * 32] : make_uint4(0u, 0u, 0u, 0u);
+        if (e0 < n) src[g * 32] = make_uint4(0u, 0u, 0u, 0u);   // consumed: cleared for the next frame
         if (e0 < n && e0 + 4 > n) {  // last, partial group
             if (e0 + 1 >= n) q[g].y = 0u;
             if (e0 + 2 >= n) q[g].z = 0u;
@@ -326,7 +331,7 @@ __global__ void __launch_bounds__(kScanBlock) k_scan(uint32_t* __restrict__ data
     }
     __syncthreads();
     const uint32_t pre = s_prefix + warp_excl;
-    uint4* dst = reinterpret_cast<uint4*>(data + wbase) + lane;
+    uint4* dst = reinterpret_cast<uint4*>(out + wbase) + lane;
 #pragma unroll
     for (int g = 0; g < kGroups; g++) {
         const uint32_t e0 = wbase + (g * 32 + lane) * 4;

@@ -412,7 +412,7 @@ __device__ __forceinline__ void narrow_one(const DevView& d, double2* sva, doubl
         first = __shfl_sync(0xffffffffu, first, 0) + (inc - n);
         if (!live) return;
         V2 mtv{0, 0};
-        if (n > 127) { atomicOr(&d.ctr->overflow, RSV_OVF_CONTACTS); n = 127; }
+        if (n > 127) { atomicOr(&d.ctr->overflow, RSV_OVF_PAIR_CONTACTS); n = 127; }
         if (n && (unsigned long long)first + n <= d.cap_contacts) {
             rsv_contact* out = d.contacts + first;
             uint32_t w = 0;

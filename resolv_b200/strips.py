@@ -318,7 +318,7 @@ def run_bench(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from . import _abi, worlds, space_for_world
-    from bench import ClockSampler, METRIC, UNIT, workload_name, measured_peaks, N_POS_PAGES
+    from bench import ClockSampler, METRIC, UNIT, workload_name, measured_peaks, N_POS_PAGES, pcie_fraction
 
     K, W = args.steps, max(args.warmup, 3)
     kind = args.workload
@@ -442,23 +442,27 @@ def run_bench(args, rank, world, local_rank):
     rays = None
     if n_rays:
         batch = 2_000_000
-        t_us, hits, done = 0.0, 0, 0
         ds.select_pos_page(0)
         sr.step_launch()
         ds.frame_finish()
-        while done < n_rays:
-            m = min(batch, n_rays - done)
-            seg = worlds.make_rays(m, 20265 + done, sr.w.space_w, sr.w.space_h)
-            rc = ds.linetest(seg, flags=_abi.LINE_DDA | _abi.LINE_HOME_ONLY)
-            t_us += rc.kernel_us
-            hits += int(rc.n_hits)
-            done += m
-        rt = torch.tensor([t_us], device=dev, dtype=torch.float64)
-        dist.all_reduce(rt, op=dist.ReduceOp.MAX)
-        rh = torch.tensor([hits], device=dev, dtype=torch.int64)
-        dist.all_reduce(rh, op=dist.ReduceOp.SUM)
-        rays = {"n_rays": n_rays, "iterator": "DDA, every rank tests all rays against the shapes homed on it (union = whole Space)",
-                "kernel_ms": float(rt.item()) / 1e3, "rays_per_sec": n_rays / (float(rt.item()) * 1e-6), "n_hits": int(rh.item())}
+        rays = {"n_rays": n_rays}
+        for name, fl in (("rect", 0), ("dda", _abi.LINE_DDA)):
+            t_us, hits, done = 0.0, 0, 0
+            while done < n_rays:
+                m = min(batch, n_rays - done)
+                seg = worlds.make_rays(m, 20265 + done, sr.w.space_w, sr.w.space_h)
+                rc = ds.linetest(seg, flags=fl | _abi.LINE_HOME_ONLY)
+                t_us += rc.kernel_us
+                hits += int(rc.n_hits)
+                done += m
+            rt = torch.tensor([t_us], device=dev, dtype=torch.float64)
+            dist.all_reduce(rt, op=dist.ReduceOp.MAX)
+            rh = torch.tensor([hits], device=dev, dtype=torch.int64)
+            dist.all_reduce(rh, op=dist.ReduceOp.SUM)
+            rays[name] = {"kernel_ms": float(rt.item()) / 1e3, "rays_per_sec": n_rays / (float(rt.item()) * 1e-6), "n_hits": int(rh.item())}
+        rays["iterator"] = ("RECT == space.FilterCells(bounds of the cast line).FilterShapes(); every rank tests all rays against the shapes "
+                            "homed on it (RSV_LINE_HOME_ONLY): the union over ranks is the sweep on the whole Space")
+        rays["kernel_ms"], rays["rays_per_sec"], rays["n_hits"] = rays["rect"]["kernel_ms"], rays["rect"]["rays_per_sec"], rays["rect"]["n_hits"]
     sr_peer, sr_fused = sr.peer_mode, sr.fused
     dist.barrier()      # (a rank must not unmap a neighbour's mailbox while that neighbour is still running)
     sr.close()
@@ -481,8 +485,9 @@ def run_bench(args, rank, world, local_rank):
         "strip_counts_ok": None if check is None else check["ok"], "strip_check": check,
         "clocks": clocks,
         "kernels_us_rank0": {k: round(v, 2) for k, v in acc.items()},
-        "e2e": {"value": N * K / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int(tot[4].item()),
-                "d2h_bytes_per_step": int(tot[5].item()), "ms_per_step": 1e3 * float(te.item()) / K},
+        "e2e": dict({"value": N * K / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int(tot[4].item()),
+                     "d2h_bytes_per_step": int(tot[5].item()), "ms_per_step": 1e3 * float(te.item()) / K},
+                    **pcie_fraction(world, int(tot[4].item()), int(tot[5].item()), float(te.item()) / K)),
         # per rank and step: 11 frame kernels + the exchange (fused: 1 extra kernel; separate peer chain: 4; NCCL: pack + 2 applies)
         "gpu_launches": K * (11 + (1 if (sr_peer and sr_fused) else (4 if sr_peer else 3))) * world,
         "roofline": {"bound": "hbm", "kernel": "frame", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,

@@ -6,7 +6,7 @@ sys.path.insert(0, ".")
 from resolv_b200 import _abi, space_for_world, worlds  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--workload", default="cfg2")
+ap.add_argument("--workload", default="cfg3")
 ap.add_argument("--shapes", type=int, default=1_000_000)
 ap.add_argument("--frames", type=int, default=3)
 a = ap.parse_args()

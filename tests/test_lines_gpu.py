@@ -83,6 +83,43 @@ def test_rect_iterator_matches_reference_filtercells(filtered):
         ds.close()
 
 
+def test_rect_iterator_is_brute_force_restricted_to_the_shapes_under_the_rect():
+    """Where the RECT iterator stands against TestAgainst = space.FilterShapes() (every shape, the brute force of SURVEY
+    §3.4): every set it reports is the brute-force set of that (ray, shape), bit for bit, and every brute-force set it
+    does not report belongs to a shape that is registered in NO cell under the cast line's bounds — a contact the "+1"
+    fudge of IntersectionPointsLine (convexPolygon.go:721-726) invents for a far-away, nearly parallel edge, which no
+    cell-based TestAgainst of the reference would be handed either. Exact integer check, no tolerance."""
+    w, ds, sp, rays, kw = _setup(n_rays=30000)
+    try:
+        ds.linetest(rays)
+        hits, con, first, count = ds.ray_results()
+        fc, oh = sp.linetest(rays, mode="all")
+        h, n, dc = _canon_dev(hits, con)
+        o, oc = _canon_ora(oh)
+        dev_keys = h["ray"].astype(np.int64) * w.n + h["b"]
+        ora_keys = oh.a[o].astype(np.int64) * w.n + oh.b[o]
+        assert np.isin(dev_keys, ora_keys).all(), "RECT reported a set brute force does not have"
+        sel = np.isin(ora_keys, dev_keys)
+        osel = o[sel]
+        ocs = np.concatenate([oh.contacts[f:f + k] for f, k in zip(oh.first[osel], oh.count[osel])])
+        assert np.array_equal(n, oh.count[osel]) and np.array_equal(bits(dc), bits(ocs))
+        assert np.array_equal(bits(h["mtv"]), bits(oh.mtv[osel])) and np.array_equal(bits(h["key"]), bits(oh.dist[osel]))
+        gw, gh = -(-w.space_w // w.cell_w), -(-w.space_h // w.cell_h)
+        for m in o[~sel]:
+            r, b = int(oh.a[m]), int(oh.b[m])
+            s_, e_ = rays[r, :2], rays[r, 2:]
+            vu = (e_ - s_) / np.hypot(*(e_ - s_))
+            st = s_ - 0.01 * vu
+            # cell rect of the cast line's bounds (utils.go:90-98), clipped to the grid, against the shape's cell rect
+            qx0, qx1 = sorted((int(np.floor(st[0] / w.cell_w)), int(np.floor(e_[0] / w.cell_w))))
+            qy0, qy1 = sorted((int(np.floor(st[1] / w.cell_h)), int(np.floor(e_[1] / w.cell_h))))
+            bx0, by0, bx1, by1 = [int(v) for v in sp.cell_rect(b)]
+            shared = (max(qx0, bx0, 0) <= min(qx1, bx1, gw - 1)) and (max(qy0, by0, 0) <= min(qy1, by1, gh - 1))
+            assert not shared, f"ray {r}: shape {b} shares a cell with the cast line's bounds but RECT did not report its set"
+    finally:
+        ds.close()
+
+
 def _supercover_touches(rays_i, cell_rect, cw, ch):
     """Exact: does the closed segment (pulled-back start -> end) touch any cell of the inclusive rect?"""
     (x0, y0, x1, y1) = [Fraction(float(v)) for v in rays_i]
