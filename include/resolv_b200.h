@@ -140,6 +140,10 @@ typedef struct rsv_results {
 #define RSV_FRAME_NO_TAG_FILTERS 0x8u  /* the host asserts that no tester's TestAgainst chain contains ByTags / NotByTags
                                           this frame: RSV_BUF_QMASK / RSV_BUF_TAGS are not read (META_USE_ANY ignored) */
 #define RSV_FRAME_TESTER_TABLE 0x10u   /* also fill the per-tester (first record, record count) table for random access */
+#define RSV_FRAME_CANDIDATE_WALK 0x80u /* run the reference's literal candidate walk (every tester visits every entry of its
+                                          margin-grown cell rect) so that counts.n_candidates is produced. Without it (and
+                                          without RSV_FRAME_ALL_CANDIDATES) a frame finds the Bounds-gated pairs cell by cell
+                                          and derives their ranks afterwards: same records, n_candidates = 0 */
 #define RSV_HIT_NOT_GATED 0x80u
 
 /* Per-kernel device times of the last RSV_FRAME_TIMING frame, microseconds, CUDA events on the space's stream. */

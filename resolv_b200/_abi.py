@@ -22,6 +22,7 @@ META_POLYGON, META_CLOSED, META_TESTER, META_USE_ANY, META_ABSENT, META_NV_SHIFT
 META_STATIC = 0x20
 FRAME_DOWNLOAD, FRAME_ALL_CANDIDATES, FRAME_TIMING, FRAME_NO_TAG_FILTERS, FRAME_TESTER_TABLE = 1, 2, 4, 8, 16
 FRAME_INCREMENTAL = 0x40
+FRAME_CANDIDATE_WALK = 0x80
 HIT_NOT_GATED = 0x80
 KERNEL_NAMES = ["clear", "bounds", "scan", "scatter", "cellsort", "pairs", "narrow"]
 

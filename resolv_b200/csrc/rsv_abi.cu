@@ -22,6 +22,7 @@
 #include "rsv_lines.cuh"
 #include "rsv_narrow.cuh"
 #include "rsv_pairs.cuh"
+#include "rsv_cellpairs.cuh"
 
 using namespace rsv;
 
@@ -41,7 +42,9 @@ struct rsv_space {
     size_t buf_bytes[RSV_BUF_COUNT] = {};
     size_t elem_bytes[RSV_BUF_COUNT] = {};
     uint32_t n_shapes = 0, n_verts = 0;
-    uint32_t n_tiles = 0;
+    uint32_t n_tiles = 0;          // scan tiles of the cell array
+    uint32_t n_tiles_shapes = 0;   // scan tiles of the per-tester record counts (cell-pair path)
+    bool grid_complete = true;     // false after a cell-pair frame: cells are unordered and carry no per-entry boxes / tags / home records
     // Two frames can be in flight: frame f's results are copied to the host on `copy_stream` while frame f+1's
     // upload and kernels run on `stream`, so each slot has its own result buffers, pinned mirrors and counters.
     struct FrameSlot {
@@ -55,6 +58,7 @@ struct rsv_space {
         cudaEvent_t ev_done = nullptr;
         uint32_t flags = 0;
         bool pending = false;
+        bool cellpairs = false;     // the frame took the cell-pair path (tester table always filled, n_candidates not counted)
     } slot[2];
     int launch_slot = 0, finish_slot = 0, last_slot = 0;
     // captured launch sequence of a frame, one per result slot (frame_via_graph)
@@ -84,6 +88,7 @@ struct rsv_space {
     uint32_t* h_list_slots = nullptr; double* h_list_xy = nullptr;
     uint32_t* d_list_slots = nullptr; double2* d_list_xy = nullptr;
     uint32_t launched_flags = 0;     // flags of the last finished frame
+    bool launched_cellpairs = false; // ... and whether it took the cell-pair path
     rsv_counts last_counts{};
     uint64_t last_records = 0, last_contacts = 0;
     cudaEvent_t ev[RSV_K_COUNT + 1] = {};
@@ -204,6 +209,11 @@ static int32_t alloc_outputs(rsv_space* s, uint32_t cap_entries, uint32_t cap_pa
             CU(s, cudaMalloc(&sl.hits, (size_t)cap_pairs * sizeof(rsv_hit)));
             CU(s, cudaMalloc(&sl.kind_queue, (size_t)cap_pairs * sizeof(uint32_t)));
         }
+        if (d.ptmp) cudaFree(d.ptmp);
+        if (d.pgrp) cudaFree(d.pgrp);
+        d.ptmp = nullptr; d.pgrp = nullptr;
+        CU(s, cudaMalloc(&d.ptmp, (size_t)cap_pairs * sizeof(uint4)));
+        CU(s, cudaMalloc(&d.pgrp, (size_t)cap_pairs * sizeof(uint4)));
         d.cap_pairs = cap_pairs;
     }
     if (cap_contacts > d.cap_contacts) {
@@ -306,9 +316,14 @@ int32_t rsv_create(const rsv_config* cfg, rsv_space** out) {
     CUC(cudaMemsetAsync(d.cell, 0, ((size_t)s->n_tiles * kScanTile) * 4, s->stream));
     CUC(cudaMalloc(&d.cnt, ((size_t)s->n_tiles * kScanTile + 16) * 4));
     CUC(cudaMemsetAsync(d.cnt, 0, ((size_t)s->n_tiles * kScanTile + 16) * 4, s->stream));
-    CUC(cudaMalloc(&d.tile_state, (size_t)s->n_tiles * 8));
-    CUC(cudaMalloc(&d.tester_start, (size_t)N * 4));
-    CUC(cudaMalloc(&d.tester_count, (size_t)N * 4));
+    s->n_tiles_shapes = (uint32_t)(((size_t)N + kScanTile - 1) / kScanTile);
+    CUC(cudaMalloc(&d.tile_state, (size_t)(s->n_tiles + s->n_tiles_shapes) * 8));
+    d.tile_state2 = d.tile_state + s->n_tiles;
+    const size_t shape_tiles_bytes = (size_t)s->n_tiles_shapes * kScanTile * 4;   // (k_scan moves whole 16-byte groups)
+    CUC(cudaMalloc(&d.tester_start, shape_tiles_bytes));
+    CUC(cudaMalloc(&d.tester_count, shape_tiles_bytes));
+    CUC(cudaMalloc(&d.grp_count, shape_tiles_bytes));
+    CUC(cudaMemsetAsync(d.grp_count, 0, shape_tiles_bytes, s->stream));
     CUC(cudaMalloc(&d.orphans, (size_t)N * 4));
     CUC(cudaMalloc(&d.ctr, sizeof(Counters)));
     CUC(cudaHostAlloc(&s->h_ctr, sizeof(Counters), cudaHostAllocDefault));
@@ -352,7 +367,7 @@ int32_t rsv_destroy(rsv_space* s) {
         if (s->host_buf[b]) cudaFreeHost(s->host_buf[b]);
     }
     DevView& d = s->d;
-    void* dev[] = {d.aabb, d.crect, d.cell, d.cnt, d.entries, d.ent_box, d.ent_home, d.ent_tags, d.multi, d.tile_state, d.tester_start, d.tester_count, d.orphans, d.ghosts, d.n_ghosts, d.ctr};
+    void* dev[] = {d.aabb, d.crect, d.cell, d.cnt, d.entries, d.ent_box, d.ent_home, d.ent_tags, d.multi, d.tile_state, d.tester_start, d.tester_count, d.grp_count, d.ptmp, d.pgrp, d.orphans, d.ghosts, d.n_ghosts, d.ctr};
     for (void* p : dev) if (p) cudaFree(p);
     if (s->h_ctr) cudaFreeHost(s->h_ctr);
     if (s->host_pos_page1) cudaFreeHost(s->host_pos_page1);
@@ -586,6 +601,25 @@ int32_t rsv_sync(rsv_space* s) {
 }
 
 
+// Which candidate path a frame takes (see rsv_cellpairs.cuh).
+static inline bool cell_pair_frame(uint32_t flags, bool incremental) {
+    return !incremental && !(flags & (RSV_FRAME_ALL_CANDIDATES | RSV_FRAME_CANDIDATE_WALK | RSV_FRAME_GRID_ONLY));
+}
+
+// After a cell-pair frame the cells are unordered and the per-entry boxes / tags / home records are not filled: the
+// consumers of the full grid (LineTest, the grid read-back) complete it first. The frame's counters (n_multi,
+// n_entries) are still on the device: they are only cleared by the next frame or rsv_test_pairs.
+static int32_t ensure_full_grid(rsv_space* s) {
+    if (s->grid_complete) return RSV_OK;
+    const DevView& d = s->d;
+    const int gcap = s->sm_count * 8;
+    k_cellsort<<<blocks_for(std::min<uint32_t>(d.n_cells, d.cap_multi), kGridBlock, gcap), kGridBlock, 0, s->stream>>>(d);
+    k_entboxes<<<gcap, kGridBlock, 0, s->stream>>>(d, 0u);
+    CU(s, cudaGetLastError());
+    s->grid_complete = true;
+    return RSV_OK;
+}
+
 // The kernels of one frame plus the counter read-back, enqueued on `st` (directly, or into a stream capture).
 // halo != nullptr: the frame of a strip-partitioned space with the halo exchange folded in (rsv_strip_frame_launch);
 // phases selects the part before the wait on the neighbours (RSV_HALO_SEND) and / or the part after it (RSV_HALO_RECV).
@@ -597,7 +631,7 @@ static int32_t enqueue_frame(rsv_space* s, const DevView& d, int32_t margin, uin
     const uint32_t max_items = inc ? d.n_dyn : (d.own_hi - d.own_lo) + ((d.n_ghosts && !halo) ? d.cap_ghosts : 0u);
     if (phases & RSV_HALO_SEND) {
         mark(RSV_K_CLEAR);
-        k_clear<<<4, kGridBlock, 0, st>>>(d.tile_state, s->n_tiles, reinterpret_cast<uint32_t*>(d.ctr),
+        k_clear<<<4, kGridBlock, 0, st>>>(d.tile_state, s->n_tiles + s->n_tiles_shapes, reinterpret_cast<uint32_t*>(d.ctr),
                                          (uint32_t)(offsetof(Counters, ray_hit_cursor) / 4));
         mark(RSV_K_BOUNDS);
         // (an incremental frame launches k_bounds even without dynamic shapes: it carries the static counts over)
@@ -625,21 +659,34 @@ static int32_t enqueue_frame(rsv_space* s, const DevView& d, int32_t margin, uin
     const uint32_t scatter_items = max_items + (halo ? d.cap_ghosts : 0u);   // (k_scatter walks own + ghosts)
     if (d.n_shapes && scatter_items) k_scatter<<<blocks_for(scatter_items, kGridBlock, gcap), kGridBlock, 0, st>>>(d);
     mark(RSV_K_CELLSORT);
+    const bool grid_only = (flags & RSV_FRAME_GRID_ONLY) != 0;
+    // Cell-pair path (rsv_cellpairs.cuh): frames that only need the Bounds-gated pairs. The reference's literal walk
+    // (k_pairs) serves the frames that dump every candidate or count them, incremental frames (their k_scan lists
+    // other cells) and grid-only frames (a LineTest follows: it needs ordered cells and per-entry boxes).
+    const bool cellpairs = cell_pair_frame(flags, inc);
     if (inc) {
         k_cellfix<<<blocks_for(std::min<uint32_t>(d.n_cells, 4u * std::max<uint32_t>(d.n_dyn, 1u)), kGridBlock, gcap), kGridBlock, 0, st>>>(d, flags);
-    } else {
+    } else if (!cellpairs) {
         k_cellsort<<<blocks_for(std::min<uint32_t>(d.n_cells, d.cap_multi), kGridBlock, gcap), kGridBlock, 0, st>>>(d);
         k_entboxes<<<gcap, kGridBlock, 0, st>>>(d, flags);
     }
     mark(RSV_K_PAIRS);
-    const bool grid_only = (flags & RSV_FRAME_GRID_ONLY) != 0;
     if (d.n_shapes && !grid_only) {
-        if (flags & RSV_FRAME_NO_TAG_FILTERS) k_pairs<false><<<s->pairs_blocks[0], kPairsBlock, 0, st>>>(d, margin, flags);
+        if (cellpairs) {
+            const bool nf = (flags & RSV_FRAME_NO_TAG_FILTERS) != 0;
+            if (nf) k_cellpairs<false><<<s->sm_count * 8, kCpBlock, 0, st>>>(d, margin);
+            else k_cellpairs<true><<<s->sm_count * 8, kCpBlock, 0, st>>>(d, margin);
+            k_scan<false, false><<<(d.n_shapes + kScanTile - 1) / kScanTile, kScanBlock, 0, st>>>(
+                d.grp_count, d.tester_start, d.n_shapes, d.tile_state2, &d.ctr->scan_ticket2, d.tester_count, nullptr, 0u, nullptr);
+            if (nf) k_rank<false><<<s->sm_count * 4, 256, 0, st>>>(d, margin);
+            else k_rank<true><<<s->sm_count * 4, 256, 0, st>>>(d, margin);
+            k_place<<<s->sm_count * 4, 256, 0, st>>>(d);
+        } else if (flags & RSV_FRAME_NO_TAG_FILTERS) k_pairs<false><<<s->pairs_blocks[0], kPairsBlock, 0, st>>>(d, margin, flags);
         else k_pairs<true><<<s->pairs_blocks[1], kPairsBlock, 0, st>>>(d, margin, flags);
     }
     mark(RSV_K_NARROW);
     if (!grid_only) {
-        k_bin<<<s->sm_count * 8, 256, 0, st>>>(d);
+        k_bin<<<s->sm_count * 8, 256, 0, st>>>(d, cellpairs);
         k_bin_scatter<<<s->sm_count * 4, 256, 0, st>>>(d);
         // the two narrowphase kernels touch disjoint records: run them side by side (their tails overlap)
         CU(s, cudaEventRecord(s->ev_fork, st));
@@ -712,7 +759,7 @@ static int32_t build_static(rsv_space* s) {
     v.subset = kSubsetStaticBuild;
     v.cell = sg.cell;
     const int gcap = s->sm_count * 8;
-    k_clear<<<4, kGridBlock, 0, st>>>(d.tile_state, s->n_tiles, reinterpret_cast<uint32_t*>(d.ctr),
+    k_clear<<<4, kGridBlock, 0, st>>>(d.tile_state, s->n_tiles + s->n_tiles_shapes, reinterpret_cast<uint32_t*>(d.ctr),
                                      (uint32_t)(offsetof(Counters, ray_hit_cursor) / 4));
     CU(s, cudaMemsetAsync(d.n_dyn_dev, 0, 4, st));
     const uint32_t items = d.own_hi - d.own_lo;
@@ -806,6 +853,8 @@ int32_t rsv_frame_launch(rsv_space* s, int32_t margin, uint32_t flags) {
     sl.flags = flags;
     sl.pending = true;
     s->launch_slot ^= 1;
+    sl.cellpairs = cell_pair_frame(flags, inc);
+    s->grid_complete = !sl.cellpairs;
     return RSV_OK;
 }
 
@@ -835,6 +884,7 @@ int32_t rsv_frame_finish(rsv_space* s, rsv_counts* out) {
     s->last_slot = s->finish_slot;
     s->finish_slot ^= 1;
     s->launched_flags = sl.flags;
+    s->launched_cellpairs = sl.cellpairs;
     const Counters& c = *sl.h_ctr;
     rsv_counts rc{};
     rc.n_shapes = s->d.n_shapes;
@@ -945,11 +995,15 @@ int32_t rsv_test_pairs(rsv_space* s, uint32_t n_pairs, rsv_counts* out) {
     DevView& d = s->d;
     d.hits = sl.hits; d.contacts = sl.contacts; d.kind_queue = sl.kind_queue;
     cudaStream_t st = s->stream;
+    {
+        const int32_t rcg = ensure_full_grid(s);   // (its counters are about to be cleared)
+        if (rcg != RSV_OK) return rcg;
+    }
     k_clear<<<1, kGridBlock, 0, st>>>(d.tile_state, 0u, reinterpret_cast<uint32_t*>(d.ctr), (uint32_t)(offsetof(Counters, ray_hit_cursor) / 4));
     if (n_pairs) {
         CU(s, cudaMemcpyAsync(s->d_pair_list, s->h_pair_list, (size_t)n_pairs * 8, cudaMemcpyHostToDevice, st));
         k_pairs_from_list<<<blocks_for(n_pairs, 256, s->sm_count * 4), 256, 0, st>>>(d, s->d_pair_list, n_pairs);
-        k_bin<<<blocks_for(n_pairs, 256, s->sm_count * 8), 256, 0, st>>>(d);
+        k_bin<<<blocks_for(n_pairs, 256, s->sm_count * 8), 256, 0, st>>>(d, false);
         k_bin_scatter<<<blocks_for(n_pairs, 256, s->sm_count * 4), 256, 0, st>>>(d);
         k_narrow<1><<<s->narrow_blocks1, kNarrowBlock, 0, st>>>(d);
         k_narrow<0><<<s->narrow_blocks, kNarrowBlock, 0, st>>>(d);
@@ -959,6 +1013,7 @@ int32_t rsv_test_pairs(rsv_space* s, uint32_t n_pairs, rsv_counts* out) {
     CU(s, cudaEventRecord(sl.ev_done, st));
     sl.flags = RSV_FRAME_DOWNLOAD;
     sl.pending = true;
+    sl.cellpairs = false;
     s->launch_slot ^= 1;
     const int32_t rc = rsv_frame_finish(s, out);
     if (out) { out->n_testers = 0; out->n_entries = 0; out->n_candidates = n_pairs; }
@@ -999,6 +1054,10 @@ int32_t rsv_timer_stop(rsv_space* s, float* ms) {
 int32_t rsv_debug_cells(rsv_space* s, uint32_t* cell_end, uint64_t n_cells, uint32_t* entries, uint64_t cap_entries) {
     if (!s) return RSV_ERR_BAD_ARG;
     CU(s, cudaSetDevice(s->device));
+    {
+        const int32_t rcg = ensure_full_grid(s);
+        if (rcg != RSV_OK) return rcg;
+    }
     CU(s, cudaStreamSynchronize(s->stream));
     if (cell_end) {
         if (n_cells != s->d.n_cells) return fail(s, RSV_ERR_BAD_ARG, "rsv_debug_cells: expected %u cells", s->d.n_cells);

@@ -1,0 +1,280 @@
+// rsv_cellpairs.cuh — the cell-pair path: Bounds-gated pairs found cell by cell, ranks derived afterwards.
+//
+// What a frame has to deliver for tester A is the reference's
+//   for B in A.SelectTouchingCells(margin).FilterShapes()[.ByTags][.NotByTags]:  A.Intersection(B)      shape.go:220-237,273-316
+// i.e. one IntersectionSet per candidate B that passes Bounds().IsIntersecting (the first statement of every pair
+// test, shape.go:322,360,403,442; utils.go:146-173), plus each such B's position in possibleIntersections (the tie
+// break of the distance sort, shape.go:291-293). The walk kernel (rsv_pairs.cuh) reproduces the reference's loop
+// literally: every tester visits every entry of its margin-grown cell rect (11 per tester in the 1 M-shape configs)
+// although 92 % of the candidates it finds fail the Bounds gate at once. This path turns the loop inside out:
+//
+//  1. k_cellpairs — two shapes whose Bounds intersect share a point, and the cell that holds the point holds both
+//     registrations (both rects are clamped to the same grid; three pairwise-intersecting intervals have a common
+//     point, so clamping cannot separate them). Gated pairs are therefore found among the entries of ONE cell: every
+//     cell with two or more entries (listed by k_scan) is expanded into its unordered entry pairs, a pair is taken at
+//     the first cell the two rects share ((A.firstCol | B.firstCol) & (A.firstRow | B.firstRow), the owner-cell rule
+//     of cell.go:105 restricted to the tester's own rect), the exact float64 gate runs on the two AABBs, the tag
+//     filters (shapefilter.go:44-61, tags.go:29-31) on the survivors, and (A, B) / (B, A) records are appended for
+//     the sides that are testers. 1.5 M unordered pairs instead of 11 M visited entries in config 3. Testers that hold
+//     no cell but whose margin reaches the grid (the orphan list of k_bounds) walk their query rect directly.
+//  2. k_scan<false,false> — per-tester record counts -> first record of every tester (records are grouped by tester,
+//     as the walk kernel's are; the tester table comes for free).
+//  3. k_rank — per record, the candidate's index in possibleIntersections: the number of candidates the reference's
+//     row-major walk over A's margin-grown rect (cell.go:86-121) offers before B — whole cell rows in front of B's
+//     first shared row, whole cells in front of its first shared cell, and the entries of that cell with a smaller
+//     slot (in-cell order of a freshly built Space is ascending slot, cell.go:21). Only the 0.17 records per tester
+//     pay for a walk, and no in-cell ordering of the entry array is needed (k_cellsort / k_entboxes are skipped; they
+//     run lazily if a LineTest or a grid read-back follows).
+//  4. k_place — orders a tester's records by rank (generation order).
+//
+// The frame's outputs (hit records incl. rank, MTV, contacts, tester table) are identical to the walk kernel's;
+// what is not produced is the statistic n_candidates (it needs the full walk: RSV_FRAME_CANDIDATE_WALK) and the
+// RSV_FRAME_ALL_CANDIDATES dump.
+#pragma once
+#include "rsv_device.cuh"
+#include "rsv_grid.cuh"
+
+namespace rsv {
+
+constexpr int kCpBlock = 128;
+constexpr int kCpWarps = kCpBlock / 32;
+constexpr int kCpSmall = 6;                                          // cells up to this size are expanded into pair items
+constexpr int kCpQueue = 32 * (kCpSmall * (kCpSmall - 1) / 2) + 32;  // 32 cells' items + a partial round carried over
+constexpr int kCpStage = 160;                                        // staged records per warp (flushed from 96 on; a round adds <= 64)
+
+struct CpWarpSmem {
+    uint32_t qs[kCpQueue];    // pair item: first entry of its cell
+    uint16_t qij[kCpQueue];   //            i | j << 8 (entry indices within the cell, i < j)
+    uint32_t stA[kCpStage];   // staged records
+    uint32_t stB[kCpStage];
+};
+
+// ByTags / NotByTags of tester A (entry or pseudo entry word eA carries its useAny bit) against shape B.
+template <bool FILTERS>
+__device__ __forceinline__ bool cp_filter(const DevView& d, uint32_t eA, uint32_t A, uint32_t B) {
+    if (!FILTERS) return true;
+    const bool useAny = (eA & kEntUseAny) != 0;
+    const ulonglong2 qm = __ldg(d.qmask + A);
+    if (!useAny && qm.y == 0) return true;
+    const unsigned long long tg = __ldg(d.tags + B);
+    if (useAny && (tg & qm.x) == 0) return false;   // ByTags: Has == any bit (tags.go:29-31)
+    return (tg & qm.y) == 0;                        // NotByTags
+}
+
+__device__ __forceinline__ bool cp_gate(const Box& a, const Box& o) {
+    return bounds_gate(a.minx, a.miny, a.maxx, a.maxy, o.minx, o.miny, o.maxx, o.maxy);
+}
+
+// Appends the staged records of the warp to the unordered record list; each record takes its index within its
+// tester's records from the tester's counter.
+__device__ __forceinline__ void cp_flush(const DevView& d, CpWarpSmem& sm, uint32_t& staged) {
+    const int lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == 0 && staged) {
+        base = atomicAdd(&d.ctr->pair_cursor, staged);
+        if (base + staged > d.cap_pairs || base + staged < base) atomicOr(&d.ctr->overflow, RSV_OVF_PAIRS);
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (uint32_t r = lane; r < staged; r += 32) {
+        const unsigned long long pos = (unsigned long long)base + r;
+        if (pos < d.cap_pairs) {
+            const uint32_t A = sm.stA[r];
+            const uint32_t idx = atomicAdd(d.grp_count + A, 1u);
+            d.ptmp[pos] = make_uint4(A, sm.stB[r], idx, 0u);
+        }
+    }
+    __syncwarp();
+    staged = 0;
+}
+
+// Warp-wide: stages (A0, A1) for lanes with e01 and (A1, A0) for lanes with e10.
+__device__ __forceinline__ void cp_emit(const DevView& d, CpWarpSmem& sm, uint32_t& staged, bool e01, bool e10, uint32_t A0, uint32_t A1) {
+    const uint32_t lt = (1u << (threadIdx.x & 31)) - 1u;
+    const uint32_t m0 = __ballot_sync(0xffffffffu, e01), m1 = __ballot_sync(0xffffffffu, e10);
+    if (!(m0 | m1)) return;
+    if (e01) { const uint32_t p = staged + __popc(m0 & lt); sm.stA[p] = A0; sm.stB[p] = A1; }
+    if (e10) { const uint32_t p = staged + __popc(m0) + __popc(m1 & lt); sm.stA[p] = A1; sm.stB[p] = A0; }
+    staged += __popc(m0) + __popc(m1);
+    __syncwarp();
+    if (staged >= kCpStage - 64) cp_flush(d, sm, staged);
+}
+
+template <bool FILTERS>
+__device__ __forceinline__ void cp_item(const DevView& d, CpWarpSmem& sm, uint32_t& staged, bool valid, uint32_t r) {
+    bool e01 = false, e10 = false;
+    uint32_t A0 = 0, A1 = 0;
+    if (valid) {
+        const uint32_t s = sm.qs[r], ij = sm.qij[r];
+        const uint32_t e0 = d.entries[s + (ij & 0xffu)], e1 = d.entries[s + (ij >> 8)];
+        const uint32_t u = e0 | e1;
+        // some side is a tester, and this is the first cell the two rects share
+        if ((u & kEntTester) && (u & kEntFirstCol) && (u & kEntFirstRow)) {
+            A0 = e0 >> kEntShift; A1 = e1 >> kEntShift;
+            if (cp_gate(load_box_nc(d.aabb + A0), load_box_nc(d.aabb + A1))) {   // (symmetric predicate)
+                e01 = (e0 & kEntTester) && cp_filter<FILTERS>(d, e0, A0, A1);
+                e10 = (e1 & kEntTester) && cp_filter<FILTERS>(d, e1, A1, A0);
+            }
+        }
+    }
+    cp_emit(d, sm, staged, e01, e10, A0, A1);
+}
+
+template <bool FILTERS>
+__global__ void __launch_bounds__(kCpBlock) k_cellpairs(DevView d, int margin) {
+    __shared__ CpWarpSmem s_warp[kCpWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    CpWarpSmem& sm = s_warp[warp];
+    const uint32_t nm = min(d.ctr->n_multi, d.cap_multi);
+    const uint32_t n_warps = gridDim.x * kCpWarps, wid = blockIdx.x * kCpWarps + warp;
+    uint32_t qn = 0, staged = 0;
+    for (uint32_t base = wid * 32u; base < nm; base += n_warps * 32u) {
+        uint32_t s = 0, n = 0;
+        if (base + lane < nm) {
+            const uint32_t c = d.multi[base + lane];
+            s = d.cell[c];
+            const uint32_t e = d.cell[c + 1];
+            if (e <= d.cap_entries && e > s) n = e - s;   // (an overflowed entry array fails the frame anyway)
+        }
+        const bool small = n >= 2 && n <= (uint32_t)kCpSmall;
+        const uint32_t np = small ? n * (n - 1) / 2 : 0u;
+        uint32_t inc = np;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (small) {
+            uint32_t at = qn + inc - np;
+            for (uint32_t i = 0; i + 1 < n; i++)
+                for (uint32_t j = i + 1; j < n; j++) { sm.qs[at] = s; sm.qij[at] = (uint16_t)(i | (j << 8)); at++; }
+        }
+        qn += __shfl_sync(0xffffffffu, inc, 31);
+        __syncwarp();
+        uint32_t r = 0;
+        for (; r + 32 <= qn; r += 32) cp_item<FILTERS>(d, sm, staged, true, r + lane);
+        if (r) {   // carry the partial round to the front
+            const uint32_t rest = qn - r;
+            uint32_t ts = 0; uint16_t tij = 0;
+            if ((uint32_t)lane < rest) { ts = sm.qs[r + lane]; tij = sm.qij[r + lane]; }
+            __syncwarp();
+            if ((uint32_t)lane < rest) { sm.qs[lane] = ts; sm.qij[lane] = tij; }
+            qn = rest;
+            __syncwarp();
+        }
+        // crowded cells: the warp takes them one at a time, lane = tester entry, all lanes stream the cell's entries
+        for (uint32_t m = __ballot_sync(0xffffffffu, n > (uint32_t)kCpSmall); m; m &= m - 1) {
+            const int src = __ffs(m) - 1;
+            const uint32_t bs = __shfl_sync(0xffffffffu, s, src), bn = __shfl_sync(0xffffffffu, n, src);
+            for (uint32_t i0 = 0; i0 < bn; i0 += 32) {
+                const uint32_t ia = i0 + lane;
+                const bool va = ia < bn;
+                const uint32_t eA = va ? d.entries[bs + ia] : 0u;
+                const uint32_t A = eA >> kEntShift;
+                const bool ta = va && (eA & kEntTester);
+                Box ba{0.0, 0.0, 0.0, 0.0};
+                if (ta) ba = load_box_nc(d.aabb + A);
+                if (!__any_sync(0xffffffffu, ta)) continue;
+                for (uint32_t j = 0; j < bn; j++) {
+                    const uint32_t eB = d.entries[bs + j], B = eB >> kEntShift;   // (uniform address: one broadcast load)
+                    const uint32_t u = eA | eB;
+                    bool ok = ta && j != ia && (u & kEntFirstCol) && (u & kEntFirstRow);
+                    if (ok) ok = cp_gate(ba, load_box_nc(d.aabb + B)) && cp_filter<FILTERS>(d, eA, A, B);
+                    cp_emit(d, sm, staged, ok, false, A, B);
+                }
+            }
+        }
+    }
+    if (qn) cp_item<FILTERS>(d, sm, staged, (uint32_t)lane < qn, (uint32_t)lane);
+    cp_flush(d, sm, staged);
+    // testers that hold no stored cell but whose margin reaches the grid: the reference's walk, one thread each
+    const uint32_t n_orph = min(d.ctr->n_orphans, d.n_shapes);
+    for (uint32_t o = blockIdx.x * kCpBlock + threadIdx.x; o < n_orph; o += gridDim.x * kCpBlock) {
+        const uint32_t A = d.orphans[o];
+        const int4 r = d.crect[A];
+        const int qx0 = max(r.x - margin, 0), qx1 = min(r.z + margin, d.W - 1);
+        const int qy0 = max(r.y - margin, d.row_lo), qy1 = min(r.w + margin, d.row_hi - 1);
+        if (qx0 > qx1 || qy0 > qy1) continue;
+        const uint32_t eA = (FILTERS && (__ldg(d.meta + A) & RSV_META_USE_ANY)) ? kEntUseAny : 0u;
+        const Box ba = load_box_nc(d.aabb + A);
+        const uint32_t* cellp = d.cell + cell_base(d, A);
+        for (int y = qy0; y <= qy1; y++) {
+            const uint32_t* row = cellp + (size_t)(y - d.row_lo) * (size_t)d.W;
+            const uint32_t s0 = min(row[qx0], d.cap_entries), s1 = min(row[qx0 + 1], d.cap_entries), e = min(row[qx1 + 1], d.cap_entries);
+            for (uint32_t k = s0; k < e; k++) {
+                const uint32_t eB = d.entries[k], B = eB >> kEntShift;
+                if (B == A || !((eB & kEntFirstCol) || k < s1) || !((eB & kEntFirstRow) || y == qy0)) continue;
+                if (!cp_gate(ba, load_box_nc(d.aabb + B)) || !cp_filter<FILTERS>(d, eA, A, B)) continue;
+                const uint32_t pos = atomicAdd(&d.ctr->pair_cursor, 1u);
+                if (pos < d.cap_pairs) d.ptmp[pos] = make_uint4(A, B, atomicAdd(d.grp_count + A, 1u), 0u);
+                else atomicOr(&d.ctr->overflow, RSV_OVF_PAIRS);
+            }
+        }
+    }
+}
+
+// Rank of every record = number of candidates the reference's walk offers before B (see the header of this file).
+template <bool FILTERS>
+__global__ void __launch_bounds__(256) k_rank(DevView d, int margin) {
+    if (d.ctr->overflow & RSV_OVF_PAIRS) return;
+    const uint32_t n_rec = min(d.ctr->pair_cursor, d.cap_pairs);
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_rec; t += gridDim.x * blockDim.x) {
+        const uint4 rec = d.ptmp[t];
+        const uint32_t A = rec.x, B = rec.y;
+        const int4 ra = d.crect[A], rb = d.crect[B];
+        const int qx0 = max(ra.x - margin, 0), qx1 = min(ra.z + margin, d.W - 1);
+        const int qy0 = max(ra.y - margin, d.row_lo), qy1 = min(ra.w + margin, d.row_hi - 1);
+        // first cell of the walk that holds B: where B's (clamped) rect starts inside the query rect
+        const int fx = min(max(qx0, max(rb.x, 0)), qx1), fy = min(max(qy0, max(rb.y, d.row_lo)), qy1);
+        bool filtered = false, useAny = false;
+        ulonglong2 qm = make_ulonglong2(0ull, 0ull);
+        if (FILTERS) {
+            useAny = (__ldg(d.meta + A) & RSV_META_USE_ANY) != 0;
+            qm = __ldg(d.qmask + A);
+            filtered = useAny || qm.y != 0;
+        }
+        auto cand = [&](uint32_t E, bool first_col_cell, bool first_row) -> uint32_t {
+            const uint32_t S = E >> kEntShift;
+            if (S == A || !((E & kEntFirstCol) || first_col_cell) || !((E & kEntFirstRow) || first_row)) return 0u;   // cell.go:101,105
+            if (FILTERS && filtered) {
+                const unsigned long long tg = __ldg(d.tags + S);
+                if (useAny && (tg & qm.x) == 0) return 0u;
+                if ((tg & qm.y) != 0) return 0u;
+            }
+            return 1u;
+        };
+        const uint32_t* cellp = d.cell + cell_base(d, A);
+        uint32_t rank = 0;
+        for (int y = qy0; y <= fy; y++) {
+            const uint32_t* row = cellp + (size_t)(y - d.row_lo) * (size_t)d.W;
+            const uint32_t s0 = min(row[qx0], d.cap_entries), s1 = min(row[qx0 + 1], d.cap_entries);
+            const int xe = y < fy ? qx1 + 1 : fx;                // whole cells [qx0, xe)
+            const uint32_t e = xe > qx0 ? min(row[xe], d.cap_entries) : s0;
+            for (uint32_t k = s0; k < e; k++) rank += cand(d.entries[k], k < s1, y == qy0);
+            if (y == fy) {                                       // B's cell: the entries in front of it
+                const uint32_t ps = min(row[fx], d.cap_entries), pe = min(row[fx + 1], d.cap_entries);
+                for (uint32_t k = ps; k < pe; k++) {
+                    const uint32_t E = d.entries[k];
+                    if ((E >> kEntShift) < B) rank += cand(E, fx == qx0, y == qy0);
+                }
+            }
+        }
+        const unsigned long long g = (unsigned long long)d.tester_start[A] + rec.z;
+        if (g < d.cap_pairs) d.pgrp[g] = make_uint4(A, B, rank, 0u);
+    }
+}
+
+// Generation order within a tester: a record's place is the number of its tester's records with a smaller rank.
+__global__ void __launch_bounds__(256) k_place(DevView d) {
+    if (d.ctr->overflow & RSV_OVF_PAIRS) return;
+    const uint32_t n_rec = min(d.ctr->pair_cursor, d.cap_pairs);
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n_rec; g += gridDim.x * blockDim.x) {
+        const uint4 rec = d.pgrp[g];
+        const uint32_t s = d.tester_start[rec.x], n = d.tester_count[rec.x];
+        uint32_t pos = 0;
+        if (n > 1)
+            for (uint32_t q = s; q < s + n; q++) pos += d.pgrp[q].z < rec.z;
+        *reinterpret_cast<uint4*>(d.hits + s + pos) = make_uint4(rec.x, rec.y, 0u, rec.z << 8);
+    }
+}
+
+}  // namespace rsv

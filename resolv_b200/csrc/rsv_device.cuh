@@ -26,7 +26,9 @@ struct Counters {
     unsigned int contact_cursor;           // allocation cursor of the contact buffer
     unsigned int overflow;                 // RSV_OVF_*
     unsigned int scan_ticket;              // dynamic tile ids of the chained scan
-    unsigned int n_multi;                  // cells holding two or more entries (k_scan -> k_cellsort)
+    unsigned int n_multi;                  // cells holding two or more entries (k_scan -> k_cellsort / k_cellpairs)
+    unsigned int scan_ticket2;             // tile ids of the per-tester record scan (cell-pair path)
+    unsigned int pad_;
     unsigned int kind_count[20];           // gated records per narrowphase bin (k_bin)
     unsigned int kind_cursor[20];          // fill cursors of the bins (k_bin_scatter)
     // line tests
@@ -64,6 +66,11 @@ struct DevView {
     uint32_t* tester_start;          // first pair record of tester i
     uint32_t* tester_count;          // number of pair records of tester i
     uint32_t* orphans;               // see Counters::n_orphans
+    // ---- cell-pair path (rsv_cellpairs.cuh)
+    uint32_t* grp_count;             // [n_shapes, whole scan tiles]: records per tester of the running frame; zero between frames
+    uint4* ptmp;                     // [cap_pairs]: (A, B, index within A's records) in arrival order
+    uint4* pgrp;                     // [cap_pairs]: (A, B, rank) grouped by tester
+    unsigned long long* tile_state2; // scan tile descriptors of the per-tester scan
     // ---- strip partitioning (multi-GPU): which slots this device processes and which rows it tests
     uint32_t own_lo, own_hi;         // owned slot range (default [0, n_shapes))
     uint32_t* ghosts;                // halo slots received this frame

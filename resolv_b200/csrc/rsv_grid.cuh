@@ -219,7 +219,11 @@ __device__ __forceinline__ void st_state(unsigned long long* p, unsigned long lo
 // data[c + 1] is left at "first entry of cell c + its static count": the static entries are copied to the front of
 // the cell by k_static_place and the cursor atomics of k_scatter append the dynamic ones behind them. `multi` then
 // lists the cells that received at least one dynamic registration (k_cellfix).
-template <bool MERGE>
+//
+// CELLS = false: a plain exclusive scan of any counter array with the same machinery (the per-tester record counts of
+// the cell-pair path, rsv_cellpairs.cuh): no list is emitted, the consumed counts are copied to `multi` instead (so
+// the caller keeps them although `data` is left zeroed), n_multi / cap_multi are unused.
+template <bool MERGE, bool CELLS = true>
 __global__ void __launch_bounds__(kScanBlock) k_scan(uint32_t* __restrict__ data, uint32_t* __restrict__ out, uint32_t n,
                                                      unsigned long long* __restrict__ state, unsigned int* ticket,
                                                      uint32_t* __restrict__ multi, unsigned int* n_multi, uint32_t cap_multi,
@@ -246,6 +250,13 @@ __global__ void __launch_bounds__(kScanBlock) k_scan(uint32_t* __restrict__ data
             q[g].w = 0u;
         }
     }
+    if (!CELLS) {
+        uint4* cpy = reinterpret_cast<uint4*>(multi + wbase) + lane;
+#pragma unroll
+        for (int g = 0; g < kGroups; g++)
+            if (wbase + (g * 32 + lane) * 4 < n) cpy[g * 32] = q[g];
+    }
+    if (CELLS) {
     // cells with >= 2 entries (array index e holds the count of cell e - 1); MERGE: cells with a dynamic entry
     constexpr uint32_t kListed = MERGE ? 1u : 2u;
     uint32_t m = 0;
@@ -270,6 +281,7 @@ __global__ void __launch_bounds__(kScanBlock) k_scan(uint32_t* __restrict__ data
             if (q[g].z >= kListed) { if (mbase < cap_multi) multi[mbase] = e0 + 1; mbase++; }
             if (q[g].w >= kListed) { if (mbase < cap_multi) multi[mbase] = e0 + 2; mbase++; }
         }
+    }
     }
     // MERGE: static counts of the same cells, in the same layout (index e: static entries of cell e - 1)
     // (they are read again for the output instead of being kept: 32 registers less, and the second read hits L1/L2)

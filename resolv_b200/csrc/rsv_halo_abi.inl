@@ -263,6 +263,8 @@ int32_t rsv_strip_frame_launch(rsv_space* s, int32_t margin, uint32_t flags, int
     }
     sl.flags = flags;
     sl.pending = true;
+    sl.cellpairs = cell_pair_frame(flags, false);
+    s->grid_complete = !sl.cellpairs;
     s->launch_slot ^= 1;
     return RSV_OK;
 }
@@ -271,7 +273,7 @@ int32_t rsv_strip_frame_launch(rsv_space* s, int32_t margin, uint32_t flags, int
 int32_t rsv_tester_table(rsv_space* s, uint32_t* first, uint32_t* count, uint64_t n_shapes) {
     if (!s || !first || !count) return RSV_ERR_BAD_ARG;
     if (n_shapes != s->d.n_shapes) return fail(s, RSV_ERR_BAD_ARG, "rsv_tester_table: expected %u shapes", s->d.n_shapes);
-    if (!(s->launched_flags & RSV_FRAME_TESTER_TABLE)) return fail(s, RSV_ERR_BAD_ARG, "rsv_tester_table: last frame ran without RSV_FRAME_TESTER_TABLE");
+    if (!(s->launched_flags & RSV_FRAME_TESTER_TABLE) && !s->launched_cellpairs) return fail(s, RSV_ERR_BAD_ARG, "rsv_tester_table: last frame ran without RSV_FRAME_TESTER_TABLE");
     CU(s, cudaSetDevice(s->device));
     CU(s, cudaStreamSynchronize(s->stream));
     if (n_shapes) {

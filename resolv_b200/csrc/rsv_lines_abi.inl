@@ -55,6 +55,8 @@ int32_t rsv_linetest_launch(rsv_space* s, uint32_t n_rays, uint32_t flags) {
     CU(s, cudaSetDevice(s->device));
     int32_t rc = lines_ensure(s);
     if (rc != RSV_OK) return rc;
+    rc = ensure_full_grid(s);   // (the last frame may have taken the cell-pair path: unordered cells, no per-entry boxes)
+    if (rc != RSV_OK) return rc;
     LineState& L = s->lines;
     if (n_rays > L.max_rays) return fail(s, RSV_ERR_BAD_ARG, "rsv_linetest: %u rays > max_rays %u", n_rays, L.max_rays);
     cudaStream_t st = s->stream;

@@ -265,7 +265,8 @@ __device__ __forceinline__ int size_class(uint32_t nv) { return nv <= 4 ? 0 : (n
 //  * computes the record's narrowphase bin (parked in the still unused first_contact field) and counts the bins.
 // A mixed world otherwise diverges four ways per warp, times the spread of polygon sizes: 3 active lanes per warp
 // were measured before binning.
-__global__ void __launch_bounds__(256) k_bin(DevView d) {
+// pregated: the records come from the cell-pair path, which already applied the exact gate.
+__global__ void __launch_bounds__(256) k_bin(DevView d, bool pregated) {
     if (d.ctr->overflow & RSV_OVF_PAIRS) return;  // records past the capacity were never written: frame is retried
     const uint32_t n_rec = min(d.ctr->pair_cursor, d.cap_pairs);
     const int lane = threadIdx.x & 31;
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(256) k_bin(DevView d) {
         if (p < n_rec) {
             const uint4 rec = *reinterpret_cast<const uint4*>(d.hits + p);
             bool gated = !(rec.w & RSV_HIT_NOT_GATED);
-            if (gated) {
+            if (gated && !pregated) {
                 const Box a = load_box_nc(d.aabb + rec.x), o = load_box_nc(d.aabb + rec.y);
                 gated = bounds_gate(a.minx, a.miny, a.maxx, a.maxy, o.minx, o.miny, o.maxx, o.maxy);
                 if (!gated) d.hits[p].count_rank = rec.w | RSV_HIT_NOT_GATED;

@@ -62,6 +62,7 @@ def test_flag_constants_match_the_header():
     for name, val in (("RSV_META_STATIC", _abi.META_STATIC), ("RSV_META_ABSENT", _abi.META_ABSENT), ("RSV_META_TESTER", _abi.META_TESTER),
                       ("RSV_FRAME_INCREMENTAL", _abi.FRAME_INCREMENTAL), ("RSV_FRAME_GRID_ONLY", _abi.FRAME_GRID_ONLY),
                       ("RSV_FRAME_NO_TAG_FILTERS", _abi.FRAME_NO_TAG_FILTERS), ("RSV_FRAME_TESTER_TABLE", _abi.FRAME_TESTER_TABLE),
+                      ("RSV_FRAME_CANDIDATE_WALK", _abi.FRAME_CANDIDATE_WALK),
                       ("RSV_LINE_DDA", _abi.LINE_DDA), ("RSV_LINE_HOME_ONLY", _abi.LINE_HOME_ONLY)):
         assert defs[name] == val, name
     frame_bits = [v for k, v in defs.items() if k.startswith(("RSV_FRAME_", "RSV_LINE_"))]

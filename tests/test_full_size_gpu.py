@@ -1,6 +1,6 @@
 """Parity at BASELINE size: the 1 M-shape frames the bench times, against the oracle on the SAME world.
 
-The regular frame (what bench.py launches: records for float-gated pairs only) is compared — hit set, contact
+The regular frame (what bench.py launches: the cell-pair path, records for the Bounds-gated pairs only) is compared — hit set, contact
 counts, MTV and contacts, generation ranks of the hits, all counters — and, for config 3, the frame after one step of
 motion as well (sets only: the oracle's in-cell order is history-dependent after moves).
 The oracle frame runs single-threaded with record=1 (a few seconds per frame at 1 M shapes).
@@ -25,7 +25,7 @@ def _full(w, frames):
                 ob.set_positions(w.pos)
                 ds.set_positions(w.pos)
             # check_candidates=False: the regular frame (gated records only), exactly what the bench times
-            c, exact = compare_frame(ds, ob, w.margin, check_candidates=False, extra_flags=flags)
+            c, exact = compare_frame(ds, ob, w.margin, check_candidates=False, check_rank=(f == 0), extra_flags=flags)
             assert exact, "MTV/contacts within 1e-9 but not bit-identical"
             if f == 0:
                 # generation ranks of the gated records against the oracle's candidate list

@@ -142,8 +142,10 @@ def test_incremental_frames_replay_as_a_graph_and_feed_linetest():
                 d.frame_launch(w.margin, fl | _abi.FRAME_DOWNLOAD)
                 c = d.frame_finish()
                 h, k = d.results()
-                o = np.lexsort((h["b"], h["a"]))
-                out.append((c.as_dict(), h["a"][o].copy(), h["b"][o].copy(), h["count_rank"][o].copy(),
+                h = h[(h["count_rank"] & 0x80) == 0]      # (the incremental frame walks: float-gated records, exact gate per record;
+                o = np.lexsort((h["b"], h["a"]))          #  the full one takes the cell-pair path: exactly the gated pairs, no candidate count)
+                cd = {k_: v for k_, v in c.as_dict().items() if k_ not in ("n_candidates", "n_gated")}
+                out.append((cd, h["a"][o].copy(), h["b"][o].copy(), h["count_rank"][o].copy(),
                             h["mtv"][o].view(np.uint64).copy()))
             assert out[0][0] == out[1][0]
             for x, y in zip(out[0][1:], out[1][1:]):

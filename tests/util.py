@@ -68,28 +68,11 @@ def bits(a):
     return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
 
 
-def compare_frame(ds, ob, margin, check_candidates=True, check_rank=True, extra_flags=0):
-    """Runs one frame on both sides and asserts: candidate set (with generation rank) bit-exact, hit set bit-exact,
-    contacts/MTV within 1e-9 absolute (the north-star tolerance) — and reports whether they are bit-identical."""
-    from resolv_b200 import _abi
-    flags = _abi.FRAME_DOWNLOAD | (_abi.FRAME_ALL_CANDIDATES if check_candidates else 0) | extra_flags
-    c = ds.frame(margin, flags, grow=True)
-    tot, cands, oh = ob.frame(margin)
-    hits, con = ds.results()
-    assert c.n_testers == tot["testers"]
-    assert c.n_candidates == tot["candidates"], (c.n_candidates, tot["candidates"])
-    if check_candidates:
-        # The generation rank is defined for a Space whose cells are in append order (freshly built). After moves
-        # the reference's in-cell order depends on its swap-remove history (cell.go:26-38), so against a moved
-        # oracle only the candidate SET is compared (check_rank=False).
-        rank = hits["count_rank"] >> 8
-        dev = np.stack([hits["a"], hits["b"], rank if check_rank else 0 * rank], -1).astype(np.int64)
-        ora = np.stack([cands["a"], cands["b"], cands["rank"] if check_rank else 0 * cands["rank"]], -1).astype(np.int64)
-        dev = dev[np.lexsort((dev[:, 1], dev[:, 0]))]
-        ora = ora[np.lexsort((ora[:, 1], ora[:, 0]))]
-        assert dev.shape == ora.shape and np.array_equal(dev, ora), "candidate set / generation rank mismatch"
+def _check_results(c, hits, con, tot, oh):
+    """Hit set bit-exact, contact counts equal, MTV / contacts within 1e-9; returns whether they are bit-identical."""
     n = hits["count_rank"] & 0x7f
     live = n > 0
+    assert c.n_testers == tot["testers"]
     assert c.n_hits == tot["hits"] == int(live.sum()), (c.n_hits, tot["hits"], int(live.sum()))
     assert c.n_contacts == tot["contacts"]
     dh = hits[live]
@@ -114,5 +97,80 @@ def compare_frame(ds, ob, margin, check_candidates=True, check_rank=True, extra_
     same_nan = np.isnan(dcon) == np.isnan(ocon)
     assert same_nan.all()
     assert np.all((np.abs(dcon - ocon) <= 1e-9) | np.isnan(ocon)), "contacts beyond 1e-9"
-    exact = bool(np.array_equal(bits(dm), bits(om)) and np.array_equal(bits(dcon), bits(ocon)))
-    return c, exact
+    return bool(np.array_equal(bits(dm), bits(om)) and np.array_equal(bits(dcon), bits(ocon)))
+
+
+def _records(hits, gated_only=True):
+    """(a, b, rank) rows of a frame's records, in buffer order."""
+    h = hits[(hits["count_rank"] & 0x80) == 0] if gated_only else hits
+    return np.stack([h["a"], h["b"], h["count_rank"] >> 8], -1).astype(np.int64)
+
+
+def _check_grouping(rec):
+    """Records are grouped by tester, a tester's records in generation order (ascending rank)."""
+    if not len(rec):
+        return
+    a = rec[:, 0]
+    starts = np.concatenate([[True], a[1:] != a[:-1]])
+    assert len(np.unique(a[starts])) == int(starts.sum()), "a tester's records are not contiguous"
+    same = ~starts[1:]
+    assert np.all(rec[1:, 2][same] > rec[:-1, 2][same]), "a tester's records are not in generation order"
+
+
+def compare_frame(ds, ob, margin, check_candidates=True, check_rank=True, extra_flags=0):
+    """Runs one frame on both sides and asserts: candidate set (with generation rank) bit-exact, hit set bit-exact,
+    contacts/MTV within 1e-9 absolute (the north-star tolerance) — and reports whether they are bit-identical.
+
+    The device side runs the frame three ways: the literal walk dumping every candidate (RSV_FRAME_ALL_CANDIDATES),
+    the literal walk recording only gated pairs (RSV_FRAME_CANDIDATE_WALK), and the default cell-pair path
+    (rsv_cellpairs.cuh), whose records must be the gated records of the dump — same pairs, same ranks."""
+    from resolv_b200 import _abi
+    tot, cands, oh = ob.frame(margin)
+    exact = True
+    gated_ref = None
+    c_all = None
+    if check_candidates:
+        c = ds.frame(margin, _abi.FRAME_DOWNLOAD | _abi.FRAME_ALL_CANDIDATES | extra_flags, grow=True)
+        hits, con = ds.results()
+        assert c.n_candidates == tot["candidates"], (c.n_candidates, tot["candidates"])
+        # The generation rank is defined for a Space whose cells are in append order (freshly built). After moves
+        # the reference's in-cell order depends on its swap-remove history (cell.go:26-38), so against a moved
+        # oracle only the candidate SET is compared (check_rank=False).
+        rank = hits["count_rank"] >> 8
+        dev = np.stack([hits["a"], hits["b"], rank if check_rank else 0 * rank], -1).astype(np.int64)
+        ora = np.stack([cands["a"], cands["b"], cands["rank"] if check_rank else 0 * cands["rank"]], -1).astype(np.int64)
+        dev = dev[np.lexsort((dev[:, 1], dev[:, 0]))]
+        ora = ora[np.lexsort((ora[:, 1], ora[:, 0]))]
+        assert dev.shape == ora.shape and np.array_equal(dev, ora), "candidate set / generation rank mismatch"
+        exact &= _check_results(c, hits, con, tot, oh)
+        gated_ref = _records(hits)
+        gated_ref = gated_ref[np.lexsort((gated_ref[:, 1], gated_ref[:, 0]))]
+        c_all = c
+        # the literal walk without the dump: float-gated records, the exact gate applied per record afterwards
+        c = ds.frame(margin, _abi.FRAME_DOWNLOAD | _abi.FRAME_CANDIDATE_WALK | extra_flags, grow=True)
+        hits, con = ds.results()
+        assert c.n_candidates == tot["candidates"], (c.n_candidates, tot["candidates"])
+        exact &= _check_results(c, hits, con, tot, oh)
+        rec = _records(hits)
+        _check_grouping(rec)
+        assert np.array_equal(rec[np.lexsort((rec[:, 1], rec[:, 0]))], gated_ref), "walk records != gated candidates of the dump"
+    # the default frame
+    c = ds.frame(margin, _abi.FRAME_DOWNLOAD | extra_flags, grow=True)
+    hits, con = ds.results()
+    exact &= _check_results(c, hits, con, tot, oh)
+    rec = _records(hits, gated_only=False)
+    _check_grouping(rec)
+    srt = rec[np.lexsort((rec[:, 1], rec[:, 0]))]
+    if gated_ref is not None:
+        if not (extra_flags & _abi.FRAME_INCREMENTAL):
+            assert c.n_gated == len(gated_ref) and not np.any(hits["count_rank"] & 0x80), "cell-pair records are exactly the gated pairs"
+        srt = srt[(hits["count_rank"][np.lexsort((rec[:, 1], rec[:, 0]))] & 0x80) == 0]
+        assert np.array_equal(srt, gated_ref), "default-frame records != gated candidates of the dump (pairs / ranks)"
+    elif check_rank:
+        # every record is one of the oracle's candidates, with the oracle's generation rank
+        key = lambda a, b: a.astype(np.int64) * (1 << 32) + b.astype(np.int64)
+        ok = np.argsort(key(cands["a"], cands["b"]))
+        pos = np.searchsorted(key(cands["a"], cands["b"])[ok], key(srt[:, 0], srt[:, 1]))
+        assert np.all(pos < len(ok))
+        assert np.array_equal(cands["rank"][ok][pos], srt[:, 2]) and np.array_equal(cands["b"][ok][pos], srt[:, 1])
+    return (c_all if c_all is not None else c), exact
