@@ -43,7 +43,6 @@ struct rsv_space {
     size_t elem_bytes[RSV_BUF_COUNT] = {};
     uint32_t n_shapes = 0, n_verts = 0;
     uint32_t n_tiles = 0;          // scan tiles of the cell array
-    uint32_t n_tiles_shapes = 0;   // scan tiles of the per-tester record counts (cell-pair path)
     bool grid_complete = true;     // false after a cell-pair frame: cells are unordered and carry no per-entry boxes / tags / home records
     // Two frames can be in flight: frame f's results are copied to the host on `copy_stream` while frame f+1's
     // upload and kernels run on `stream`, so each slot has its own result buffers, pinned mirrors and counters.
@@ -194,7 +193,7 @@ static int32_t alloc_outputs(rsv_space* s, uint32_t cap_entries, uint32_t cap_pa
         if (d.multi) cudaFree(d.multi);
         d.multi = nullptr;
         d.cap_multi = cap_entries + 1;  // (incremental frames list every cell that received a dynamic registration)
-        CU(s, cudaMalloc(&d.multi, (size_t)d.cap_multi * 4));
+        CU(s, cudaMalloc(&d.multi, (size_t)d.cap_multi * sizeof(uint2)));
         CU(s, cudaMalloc(&d.entries, ((size_t)cap_entries + 8) * 4));
         CU(s, cudaMalloc(&d.ent_box, ((size_t)cap_entries + 8) * sizeof(float4)));
         CU(s, cudaMalloc(&d.ent_home, ((size_t)cap_entries + 8) * sizeof(uint2)));
@@ -316,14 +315,11 @@ int32_t rsv_create(const rsv_config* cfg, rsv_space** out) {
     CUC(cudaMemsetAsync(d.cell, 0, ((size_t)s->n_tiles * kScanTile) * 4, s->stream));
     CUC(cudaMalloc(&d.cnt, ((size_t)s->n_tiles * kScanTile + 16) * 4));
     CUC(cudaMemsetAsync(d.cnt, 0, ((size_t)s->n_tiles * kScanTile + 16) * 4, s->stream));
-    s->n_tiles_shapes = (uint32_t)(((size_t)N + kScanTile - 1) / kScanTile);
-    CUC(cudaMalloc(&d.tile_state, (size_t)(s->n_tiles + s->n_tiles_shapes) * 8));
-    d.tile_state2 = d.tile_state + s->n_tiles;
-    const size_t shape_tiles_bytes = (size_t)s->n_tiles_shapes * kScanTile * 4;   // (k_scan moves whole 16-byte groups)
-    CUC(cudaMalloc(&d.tester_start, shape_tiles_bytes));
-    CUC(cudaMalloc(&d.tester_count, shape_tiles_bytes));
-    CUC(cudaMalloc(&d.grp_count, shape_tiles_bytes));
-    CUC(cudaMemsetAsync(d.grp_count, 0, shape_tiles_bytes, s->stream));
+    CUC(cudaMalloc(&d.tile_state, (size_t)s->n_tiles * 8));
+    CUC(cudaMalloc(&d.tester_start, (size_t)N * 4));
+    CUC(cudaMalloc(&d.tester_count, (size_t)N * 4));
+    CUC(cudaMalloc(&d.grp_count, (size_t)N * 4));
+    CUC(cudaMemsetAsync(d.grp_count, 0, (size_t)N * 4, s->stream));
     CUC(cudaMalloc(&d.orphans, (size_t)N * 4));
     CUC(cudaMalloc(&d.ctr, sizeof(Counters)));
     CUC(cudaHostAlloc(&s->h_ctr, sizeof(Counters), cudaHostAllocDefault));
@@ -631,7 +627,7 @@ static int32_t enqueue_frame(rsv_space* s, const DevView& d, int32_t margin, uin
     const uint32_t max_items = inc ? d.n_dyn : (d.own_hi - d.own_lo) + ((d.n_ghosts && !halo) ? d.cap_ghosts : 0u);
     if (phases & RSV_HALO_SEND) {
         mark(RSV_K_CLEAR);
-        k_clear<<<4, kGridBlock, 0, st>>>(d.tile_state, s->n_tiles + s->n_tiles_shapes, reinterpret_cast<uint32_t*>(d.ctr),
+        k_clear<<<4, kGridBlock, 0, st>>>(d.tile_state, s->n_tiles, reinterpret_cast<uint32_t*>(d.ctr),
                                          (uint32_t)(offsetof(Counters, ray_hit_cursor) / 4));
         mark(RSV_K_BOUNDS);
         // (an incremental frame launches k_bounds even without dynamic shapes: it carries the static counts over)
@@ -657,9 +653,9 @@ static int32_t enqueue_frame(rsv_space* s, const DevView& d, int32_t margin, uin
     mark(RSV_K_SCATTER);
     if (inc && d.static_entries) k_static_place<<<blocks_for(d.static_entries, kGridBlock, gcap), kGridBlock, 0, st>>>(d, s->sg, flags);
     const uint32_t scatter_items = max_items + (halo ? d.cap_ghosts : 0u);   // (k_scatter walks own + ghosts)
+    const bool grid_only = (flags & RSV_FRAME_GRID_ONLY) != 0;
     if (d.n_shapes && scatter_items) k_scatter<<<blocks_for(scatter_items, kGridBlock, gcap), kGridBlock, 0, st>>>(d);
     mark(RSV_K_CELLSORT);
-    const bool grid_only = (flags & RSV_FRAME_GRID_ONLY) != 0;
     // Cell-pair path (rsv_cellpairs.cuh): frames that only need the Bounds-gated pairs. The reference's literal walk
     // (k_pairs) serves the frames that dump every candidate or count them, incremental frames (their k_scan lists
     // other cells) and grid-only frames (a LineTest follows: it needs ordered cells and per-entry boxes).
@@ -674,13 +670,12 @@ static int32_t enqueue_frame(rsv_space* s, const DevView& d, int32_t margin, uin
     if (d.n_shapes && !grid_only) {
         if (cellpairs) {
             const bool nf = (flags & RSV_FRAME_NO_TAG_FILTERS) != 0;
-            if (nf) k_cellpairs<false><<<s->sm_count * 8, kCpBlock, 0, st>>>(d, margin);
-            else k_cellpairs<true><<<s->sm_count * 8, kCpBlock, 0, st>>>(d, margin);
-            k_scan<false, false><<<(d.n_shapes + kScanTile - 1) / kScanTile, kScanBlock, 0, st>>>(
-                d.grp_count, d.tester_start, d.n_shapes, d.tile_state2, &d.ctr->scan_ticket2, d.tester_count, nullptr, 0u, nullptr);
-            if (nf) k_rank<false><<<s->sm_count * 4, 256, 0, st>>>(d, margin);
-            else k_rank<true><<<s->sm_count * 4, 256, 0, st>>>(d, margin);
-            k_place<<<s->sm_count * 4, 256, 0, st>>>(d);
+            if (nf) k_cellpairs<false><<<s->sm_count * 6, kCpBlock, 0, st>>>(d, margin);
+            else k_cellpairs<true><<<s->sm_count * 6, kCpBlock, 0, st>>>(d, margin);
+            k_alloc<<<s->sm_count * 8, 256, 0, st>>>(d);
+            if (nf) k_rank<false><<<s->sm_count * 8, 256, 0, st>>>(d, margin);
+            else k_rank<true><<<s->sm_count * 8, 256, 0, st>>>(d, margin);
+            k_place<<<s->sm_count * 8, 256, 0, st>>>(d);
         } else if (flags & RSV_FRAME_NO_TAG_FILTERS) k_pairs<false><<<s->pairs_blocks[0], kPairsBlock, 0, st>>>(d, margin, flags);
         else k_pairs<true><<<s->pairs_blocks[1], kPairsBlock, 0, st>>>(d, margin, flags);
     }
@@ -759,7 +754,7 @@ static int32_t build_static(rsv_space* s) {
     v.subset = kSubsetStaticBuild;
     v.cell = sg.cell;
     const int gcap = s->sm_count * 8;
-    k_clear<<<4, kGridBlock, 0, st>>>(d.tile_state, s->n_tiles + s->n_tiles_shapes, reinterpret_cast<uint32_t*>(d.ctr),
+    k_clear<<<4, kGridBlock, 0, st>>>(d.tile_state, s->n_tiles, reinterpret_cast<uint32_t*>(d.ctr),
                                      (uint32_t)(offsetof(Counters, ray_hit_cursor) / 4));
     CU(s, cudaMemsetAsync(d.n_dyn_dev, 0, 4, st));
     const uint32_t items = d.own_hi - d.own_lo;

@@ -8,7 +8,7 @@
 
 namespace rsv {
 
-struct alignas(16) Box {  // (minx, miny, maxx, maxy); loaded as two 128-bit halves
+struct alignas(32) Box {  // (minx, miny, maxx, maxy); moved with ONE 256-bit load / store (LDG.E.256 / STG.E.256, sm_100)
     double minx, miny, maxx, maxy;
 };
 
@@ -27,7 +27,7 @@ struct Counters {
     unsigned int overflow;                 // RSV_OVF_*
     unsigned int scan_ticket;              // dynamic tile ids of the chained scan
     unsigned int n_multi;                  // cells holding two or more entries (k_scan -> k_cellsort / k_cellpairs)
-    unsigned int scan_ticket2;             // tile ids of the per-tester record scan (cell-pair path)
+    unsigned int grp_cursor;               // allocation cursor of the per-tester record groups (cell-pair path, k_alloc)
     unsigned int pad_;
     unsigned int kind_count[20];           // gated records per narrowphase bin (k_bin)
     unsigned int kind_cursor[20];          // fill cursors of the bins (k_bin_scatter)
@@ -61,16 +61,15 @@ struct DevView {
     unsigned long long* ent_tags;  // per entry: the shape's tags (written only in frames that use tag filters)
     uint2* ent_home;      // per HOME entry: (global index of the home cell, columns-1 | rows-1 << 16 of the clamped rect)
     unsigned long long* tile_state;  // chained-scan tile descriptors
-    uint32_t* multi;                 // cells with >= 2 entries
+    uint2* multi;                    // (first entry, entry count) of the cells with >= 2 entries
     uint32_t cap_multi;
     uint32_t* tester_start;          // first pair record of tester i
     uint32_t* tester_count;          // number of pair records of tester i
     uint32_t* orphans;               // see Counters::n_orphans
     // ---- cell-pair path (rsv_cellpairs.cuh)
-    uint32_t* grp_count;             // [n_shapes, whole scan tiles]: records per tester of the running frame; zero between frames
+    uint32_t* grp_count;             // [n_shapes]: records per tester of the running frame; zero between frames (k_alloc)
     uint4* ptmp;                     // [cap_pairs]: (A, B, index within A's records) in arrival order
     uint4* pgrp;                     // [cap_pairs]: (A, B, rank) grouped by tester
-    unsigned long long* tile_state2; // scan tile descriptors of the per-tester scan
     // ---- strip partitioning (multi-GPU): which slots this device processes and which rows it tests
     uint32_t own_lo, own_hi;         // owned slot range (default [0, n_shapes))
     uint32_t* ghosts;                // halo slots received this frame
@@ -101,20 +100,20 @@ struct DevView {
     uint32_t cap_entries, cap_pairs, cap_contacts;
 };
 
-__device__ __forceinline__ Box load_box(const Box* p) {
-    const double2* q = reinterpret_cast<const double2*>(p);
-    double2 lo = __ldg(q), hi = __ldg(q + 1);
-    return Box{lo.x, lo.y, hi.x, hi.y};
+// A gather of a Box by shape slot is one L1 wavefront per lane with a 256-bit access instead of two with 128-bit halves
+// (every lane hits a different line), and these gathers are what the candidate and narrowphase kernels wait on.
+__device__ __forceinline__ Box load_box(const Box* p) {      // host-committed data: read-only path
+    Box b;
+    asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(b.minx), "=d"(b.miny), "=d"(b.maxx), "=d"(b.maxy) : "l"(p));
+    return b;
 }
-__device__ __forceinline__ Box load_box_nc(const Box* p) {  // written earlier in the same frame: plain loads
-    const double2* q = reinterpret_cast<const double2*>(p);
-    double2 lo = q[0], hi = q[1];
-    return Box{lo.x, lo.y, hi.x, hi.y};
+__device__ __forceinline__ Box load_box_nc(const Box* p) {   // written by an EARLIER kernel of the same frame: plain load
+    Box b;                                                   // (no kernel reads a Box it wrote itself, so the asm needs no memory clobber)
+    asm("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(b.minx), "=d"(b.miny), "=d"(b.maxx), "=d"(b.maxy) : "l"(p));
+    return b;
 }
 __device__ __forceinline__ void store_box(Box* p, Box b) {
-    double2* q = reinterpret_cast<double2*>(p);
-    q[0] = make_double2(b.minx, b.miny);
-    q[1] = make_double2(b.maxx, b.maxy);
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(b.minx), "d"(b.miny), "d"(b.maxx), "d"(b.maxy) : "memory");
 }
 
 // Outward-rounded float32 copy of a float64 box: contains the exact box, so "disjoint in float" implies

@@ -211,22 +211,19 @@ __device__ __forceinline__ void st_state(unsigned long long* p, unsigned long lo
 }
 
 // Exclusive scan of the per-cell counters (data[c + 1] = count of cell c) into out[c + 1] = first entry of cell c
-// (out[0] = 0); data is left zeroed. Also appends every cell that holds two or more entries to `multi` — the only
-// cells whose entries k_cellsort has to order.
+// (out[0] = 0); data is left zeroed. Also appends (first entry, entry count) of every cell that holds two or more
+// entries to `multi` — the cells whose entries k_cellsort has to order and k_cellpairs has to pair up; they get the
+// cell's run of the entry array from one coalesced load and never touch the offset array.
 //
 // MERGE (incremental frames): `data` holds the counts of the DYNAMIC registrations only and `scount` the static
 // ones of the cached static grid, in the same layout. The scan runs over dynamic + static counts, and
 // data[c + 1] is left at "first entry of cell c + its static count": the static entries are copied to the front of
 // the cell by k_static_place and the cursor atomics of k_scatter append the dynamic ones behind them. `multi` then
 // lists the cells that received at least one dynamic registration (k_cellfix).
-//
-// CELLS = false: a plain exclusive scan of any counter array with the same machinery (the per-tester record counts of
-// the cell-pair path, rsv_cellpairs.cuh): no list is emitted, the consumed counts are copied to `multi` instead (so
-// the caller keeps them although `data` is left zeroed), n_multi / cap_multi are unused.
-template <bool MERGE, bool CELLS = true>
+template <bool MERGE>
 __global__ void __launch_bounds__(kScanBlock) k_scan(uint32_t* __restrict__ data, uint32_t* __restrict__ out, uint32_t n,
                                                      unsigned long long* __restrict__ state, unsigned int* ticket,
-                                                     uint32_t* __restrict__ multi, unsigned int* n_multi, uint32_t cap_multi,
+                                                     uint2* __restrict__ multi, unsigned int* n_multi, uint32_t cap_multi,
                                                      const uint32_t* __restrict__ scount) {
     __shared__ uint32_t s_tile, s_prefix, s_warp[kScanBlock / 32];
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
@@ -250,14 +247,8 @@ __global__ void __launch_bounds__(kScanBlock) k_scan(uint32_t* __restrict__ data
             q[g].w = 0u;
         }
     }
-    if (!CELLS) {
-        uint4* cpy = reinterpret_cast<uint4*>(multi + wbase) + lane;
-#pragma unroll
-        for (int g = 0; g < kGroups; g++)
-            if (wbase + (g * 32 + lane) * 4 < n) cpy[g * 32] = q[g];
-    }
-    if (CELLS) {
-    // cells with >= 2 entries (array index e holds the count of cell e - 1); MERGE: cells with a dynamic entry
+    // cells with >= 2 entries (array index e holds the count of cell e - 1); MERGE: cells with a dynamic entry.
+    // Their places in the list are reserved now; the records are written at the end, when the offsets are known.
     constexpr uint32_t kListed = MERGE ? 1u : 2u;
     uint32_t m = 0;
 #pragma unroll
@@ -272,17 +263,6 @@ __global__ void __launch_bounds__(kScanBlock) k_scan(uint32_t* __restrict__ data
     const uint32_t mtotal = __shfl_sync(0xffffffffu, minc, 31);
     if (lane == 31 && mtotal) mbase = atomicAdd(n_multi, mtotal);
     mbase = __shfl_sync(0xffffffffu, mbase, 31) + (minc - m);
-    if (m) {
-#pragma unroll
-        for (int g = 0; g < kGroups; g++) {
-            const uint32_t e0 = wbase + (g * 32 + lane) * 4;
-            if (q[g].x >= kListed) { if (mbase < cap_multi) multi[mbase] = e0 - 1; mbase++; }
-            if (q[g].y >= kListed) { if (mbase < cap_multi) multi[mbase] = e0; mbase++; }
-            if (q[g].z >= kListed) { if (mbase < cap_multi) multi[mbase] = e0 + 1; mbase++; }
-            if (q[g].w >= kListed) { if (mbase < cap_multi) multi[mbase] = e0 + 2; mbase++; }
-        }
-    }
-    }
     // MERGE: static counts of the same cells, in the same layout (index e: static entries of cell e - 1)
     // (they are read again for the output instead of being kept: 32 registers less, and the second read hits L1/L2)
     const uint4* ssrc = reinterpret_cast<const uint4*>(scount + wbase) + lane;
@@ -354,7 +334,15 @@ __global__ void __launch_bounds__(kScanBlock) k_scan(uint32_t* __restrict__ data
             o.y = run; run += q[g].y;
             o.z = run; run += q[g].z;
             o.w = run;
-            if (MERGE) { const uint4 c4 = __ldg(ssrc + g * 32); o.x += c4.x; o.y += c4.y; o.z += c4.z; o.w += c4.w; }
+            uint4 c4 = make_uint4(0u, 0u, 0u, 0u);
+            if (MERGE) c4 = __ldg(ssrc + g * 32);
+            if (m) {   // (first entry, entries) of the listed cells; listed by their DYNAMIC count in merged frames
+                if (q[g].x - c4.x >= kListed) { if (mbase < cap_multi) multi[mbase] = make_uint2(o.x, q[g].x); mbase++; }
+                if (q[g].y - c4.y >= kListed) { if (mbase < cap_multi) multi[mbase] = make_uint2(o.y, q[g].y); mbase++; }
+                if (q[g].z - c4.z >= kListed) { if (mbase < cap_multi) multi[mbase] = make_uint2(o.z, q[g].z); mbase++; }
+                if (q[g].w - c4.w >= kListed) { if (mbase < cap_multi) multi[mbase] = make_uint2(o.w, q[g].w); mbase++; }
+            }
+            if (MERGE) { o.x += c4.x; o.y += c4.y; o.z += c4.z; o.w += c4.w; }
             dst[g * 32] = o;
         }
     }
@@ -407,11 +395,10 @@ __global__ void __launch_bounds__(kGridBlock) k_scatter(DevView d) {
 __global__ void __launch_bounds__(kGridBlock) k_cellsort(DevView d) {
     const uint32_t nm = min(d.ctr->n_multi, d.cap_multi);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nm; i += gridDim.x * blockDim.x) {
-        const uint32_t c = d.multi[i];
-        uint32_t s = d.cell[c], e = d.cell[c + 1];
-        if (e - s < 2 || e > d.cap_entries) continue;
+        const uint2 sn = d.multi[i];
+        const uint32_t s = sn.x, n = sn.y;
+        if (n < 2 || (unsigned long long)s + n > d.cap_entries) continue;
         uint32_t* a = d.entries + s;
-        uint32_t n = e - s;
         for (uint32_t i = 1; i < n; i++) {
             uint32_t key = a[i];
             uint32_t j = i;
@@ -495,11 +482,10 @@ __global__ void __launch_bounds__(kGridBlock) k_cellfix(DevView d, uint32_t flag
     const bool filters = !(flags & RSV_FRAME_NO_TAG_FILTERS);
     const uint32_t nm = min(d.ctr->n_multi, d.cap_multi);
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nm; t += gridDim.x * blockDim.x) {
-        const uint32_t c = d.multi[t];
-        const uint32_t s = d.cell[c], e = d.cell[c + 1];
-        if (e <= s || e > d.cap_entries) continue;
+        const uint2 sn = d.multi[t];
+        const uint32_t s = sn.x, n = sn.y, e = s + n;
+        if (n == 0 || (unsigned long long)s + n > d.cap_entries) continue;
         uint32_t* a = d.entries + s;
-        const uint32_t n = e - s;
         for (uint32_t i = 1; i < n; i++) {
             const uint32_t key = a[i];
             uint32_t j = i;
