@@ -166,12 +166,55 @@ def pcie_fraction(n_gpus, h2d_total, d2h_total, seconds_per_step):
             "pcie_frac": got / row["both_gbs_per_rank_per_direction"], "pcie_peak_source": "profiles/r2_pcie.json (scripts/measure_pcie.py)"}
 
 
-def kernel_algorithmic_bytes(c, w, n_cells, filters=False):
+def grid_stats(w, pos):
+    """Cell occupancy of one frame, computed on the host from the world (for the byte accounting of the cell-pair
+    kernels only): cells holding >= 2 entries, the entries in them, and the mean number of entries in a tester's
+    margin-grown query rect."""
+    la = np.asarray(w.local_aabb, dtype=np.float64).reshape(-1, 4)
+    Wc, Hc = int(np.ceil(w.space_w / w.cell_w)), int(np.ceil(w.space_h / w.cell_h))
+    x0 = np.floor((la[:, 0] + pos[:, 0]) / w.cell_w).astype(np.int64); x1 = np.floor((la[:, 2] + pos[:, 0]) / w.cell_w).astype(np.int64)
+    y0 = np.floor((la[:, 1] + pos[:, 1]) / w.cell_h).astype(np.int64); y1 = np.floor((la[:, 3] + pos[:, 1]) / w.cell_h).astype(np.int64)
+    cx0, cx1, cy0, cy1 = np.clip(x0, 0, Wc - 1), np.clip(x1, 0, Wc - 1), np.clip(y0, 0, Hc - 1), np.clip(y1, 0, Hc - 1)
+    ok = (x1 >= 0) & (x0 < Wc) & (y1 >= 0) & (y0 < Hc)
+    cnt = np.zeros(Wc * Hc, dtype=np.int64)
+    span = int(min(max((cx1 - cx0).max(), (cy1 - cy0).max()) + 1, 64))
+    for dy in range(span):
+        for dx in range(span):
+            m = ok & (cx0 + dx <= cx1) & (cy0 + dy <= cy1)
+            if m.any():
+                np.add.at(cnt, (cy0[m] + dy) * Wc + cx0[m] + dx, 1)
+    multi = cnt >= 2
+    m_ = w.margin
+    qcells = (np.minimum(cx1 + m_, Wc - 1) - np.maximum(cx0 - m_, 0) + 1) * (np.minimum(cy1 + m_, Hc - 1) - np.maximum(cy0 - m_, 0) + 1)
+    return {"multi_cells": int(multi.sum()), "multi_entries": int(cnt[multi].sum()),
+            "query_entries": float(qcells[ok].mean() * cnt.sum() / max(Wc * Hc, 1)) if ok.any() else 0.0}
+
+
+def kernel_algorithmic_bytes(c, w, n_cells, filters=False, gs=None):
     """Algorithmic bytes each kernel must move per launch: every datum counted once per kernel
-    (caches assumed perfect within a kernel), gathers counted at the size of the datum, atomics as 8 B (RMW)."""
+    (caches assumed perfect within a kernel), gathers counted at the size of the datum, atomics as 8 B (RMW).
+    gs = grid_stats(...) selects the accounting of the cell-pair path (the default frame); None = the literal walk."""
     N, R, G, K = c.n_shapes, c.n_entries, c.n_gated, c.n_contacts
     vb = 16.0 * float(w.nv.sum()) / max(N, 1)   # average vertex bytes per shape
     C1 = n_cells + 1
+    if gs is not None:
+        M, E2, v = gs["multi_cells"], gs["multi_entries"], 0.5 * gs["query_entries"]
+        return {
+            "clear": 8 * (C1 // 8192 + 1) + 256,
+            "bounds": N * (16 + 32 + 4) + N * (32 + 16 + 4) + 8 * R,
+            "scan": 12 * C1 + 8 * M,                           # + (first entry, count) of the cells holding >= 2 entries
+            "scatter": N * (16 + 4) + 8 * R + 4 * R,
+            "cellsort": 0,                                     # (cells stay unordered; no per-entry boxes / tags / home records)
+            # k_cellpairs: cell list, entry words of the listed cells, one AABB per shape in a listed cell, filter masks and
+            # tags of the gated pairs, arrival records out; k_alloc: records in, tester table out; k_rank: record, two cell
+            # rects, ~3 rows of offsets and the entries (+ tags) of half a query rect per record, grouped record out;
+            # k_place: grouped record in, hit record out
+            "pairs": 8 * M + 4 * E2 + 32 * min(E2, N) + ((16 + 8) * 2 * G if filters else 0) + 16 * G
+                     + 16 * G + 12 * G
+                     + G * (16 + 32 + 36 + 4 * v + (8 * v + 20 if filters else 0)) + 16 * G
+                     + 16 * G + 16 * G,
+            "narrow": G * (16 + 2 * (16 + 4 + 4 + 32)) + G * 2 * vb + 32 * G + 32 * K,
+        }
     return {
         "clear": 8 * (C1 // 8192 + 1) + 256,               # scan tile states + frame counters (the per-cell counters are zeroed by the scan)
         "bounds": N * (16 + 32 + 4) + N * (32 + 16 + 4) + 8 * R,   # pos, local AABB, meta -> AABB, cell rect, table reset; one RED per entry
@@ -238,21 +281,35 @@ def parity_counts(sp, w, pos, dev):
     import ctypes as C
     cnt = np.zeros(n_cells, dtype=np.uint32)
     R = int(sp.L.orc_cells_dump(sp.h, cnt.ctypes.data_as(C.POINTER(C.c_uint32)), None, 0))
-    c, msum = dev
+    c, msum, same = dev
     want = {"n_testers": int(fc.testers), "n_entries": R, "n_candidates": int(fc.candidates), "n_hits": int(fc.hits), "n_contacts": int(fc.contacts)}
     got = {k: int(getattr(c, k)) for k in want}
     tol = 1e-9 * max(int(fc.hits), 1)
-    ok = got == want and abs(msum[0] - fc.mtv_sum_x) <= tol and abs(msum[1] - fc.mtv_sum_y) <= tol
+    ok = same and got == want and abs(msum[0] - fc.mtv_sum_x) <= tol and abs(msum[1] - fc.mtv_sum_y) <= tol
     return ok, {"device": got, "oracle": want, "mtv_sum_device": [float(msum[0]), float(msum[1])],
-                "mtv_sum_oracle": [float(fc.mtv_sum_x), float(fc.mtv_sum_y)]}
+                "mtv_sum_oracle": [float(fc.mtv_sum_x), float(fc.mtv_sum_y)], "walk_and_cell_pair_paths_agree": same,
+                "note": "n_candidates from the literal-walk frame (RSV_FRAME_CANDIDATE_WALK); every other counter and the MTV checksum from the default (cell-pair) frame"}
 
 
 def device_frame_with_checksum(ds, margin, flags):
+    """One frame through both candidate paths. The default frame (cell-pair path: what the bench times) delivers the
+    counters and the MTV checksum that are compared with the oracle; the literal walk (RSV_FRAME_CANDIDATE_WALK) delivers
+    the candidate count P — the default frame does not count candidates — and must agree with the default frame on
+    every other counter and on the checksum."""
     from resolv_b200 import _abi
-    c = ds.frame(margin, flags | _abi.FRAME_DOWNLOAD, grow=True)
-    hits, _ = ds.results()
-    live = (hits["count_rank"] & 0x7f) > 0
-    return c, hits["mtv"][live].sum(axis=0) if live.any() else np.zeros(2)
+
+    def one(fl):
+        c = ds.frame(margin, flags | fl | _abi.FRAME_DOWNLOAD, grow=True)
+        hits, _ = ds.results()
+        live = (hits["count_rank"] & 0x7f) > 0
+        return c, hits["mtv"][live].sum(axis=0) if live.any() else np.zeros(2)
+
+    cw, mw = one(_abi.FRAME_CANDIDATE_WALK)
+    c, m = one(0)
+    same = all(int(getattr(c, k)) == int(getattr(cw, k)) for k in ("n_testers", "n_entries", "n_hits", "n_contacts")) and \
+        bool(np.all(np.abs(np.asarray(m) - np.asarray(mw)) <= 1e-9 * max(int(c.n_hits), 1)))   # (summed in different record orders)
+    c.n_candidates = cw.n_candidates
+    return c, m, bool(same)
 
 
 def run_b200(args):
@@ -339,6 +396,22 @@ def run_b200(args):
             acc[k] += t[k] / K
         for k in cs:
             cs[k] += int(getattr(ck, k)) / K
+    # ---- the literal candidate walk (RSV_FRAME_CANDIDATE_WALK: the reference's loop as written; it is what counts the
+    # candidates P) over the same position cycle: P for pair-tests/s, and its frame time next to the default path's
+    walk_flags = base_flags | _abi.FRAME_CANDIDATE_WALK
+    for i in range(2 * N_POS_PAGES):
+        ds.select_pos_page(i % N_POS_PAGES)
+        cwk = ds.frame(margin, walk_flags, grow=True)
+    ds.sync()
+    ds.timer_start()
+    for i in range(K):
+        ds.select_pos_page(i % N_POS_PAGES)
+        ds.frame_launch(margin, walk_flags)
+    walk_ms = ds.timer_stop() / K
+    ds.drain()
+    for i in range(N_POS_PAGES):
+        ds.select_pos_page(i)
+        cs["n_candidates"] += int(ds.frame(margin, walk_flags).n_candidates) / N_POS_PAGES
     ds.select_pos_page(0)
     # ---- e2e: host buffers, H2D of the step's positions + frame + D2H of hits/contacts, every step.
     # (a) sequential: commit -> frame -> download, one step at a time (latency of a frame through the API)
@@ -385,11 +458,12 @@ def run_b200(args):
     class Avg:   # mean counters of the timed frames (the position cycle changes them slightly from frame to frame)
         n_shapes = N
         n_entries, n_candidates, n_gated, n_hits, n_contacts = (cs[k] for k in ("n_entries", "n_candidates", "n_gated", "n_hits", "n_contacts"))
-    algo = kernel_algorithmic_bytes(Avg, w, n_cells, filters=not (base_flags & _abi.FRAME_NO_TAG_FILTERS))
+    gs = grid_stats(w, frames[0])
+    algo = kernel_algorithmic_bytes(Avg, w, n_cells, filters=not (base_flags & _abi.FRAME_NO_TAG_FILTERS), gs=gs)
     dom = max(acc, key=lambda k: acc[k])
     traffic, traffic_src = None, None   # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_kernel_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r3_kernel_traffic.json")))
         if args.workload in tj and args.shapes == 1_000_000:
             traffic = tj[args.workload]["dram_bytes_per_launch"].get(dom)
             traffic_src = tj[args.workload].get("source")
@@ -404,8 +478,14 @@ def run_b200(args):
         "data": "synthetic",
         "config": {"workload": workload_name(args, 1), "l2": "inputs + per-frame intermediates (~0.3 GB) exceed the 126 MB L2",
                    "margin": margin, "motion": f"timed frames cycle through {N_POS_PAGES} position sets resident in HBM"},
+        # candidates whose Intersection() a frame answers (P, counted by the literal walk over the same positions) per second
+        # of the default frame
         "pair_tests_per_sec": cs["n_candidates"] / (ms_per_step * 1e-3),
-        "counts": c.as_dict(),
+        "counts": {**c.as_dict(), "n_candidates": int(cs["n_candidates"])},
+        "candidate_path": {"default": "cell-pair path (rsv_cellpairs.cuh): Bounds-gated pairs found per cell, ranks derived per record; "
+                                      "same records as the walk, n_candidates not counted",
+                           "literal_walk_ms_per_step": walk_ms, "literal_walk_value": N / (walk_ms * 1e-3),
+                           "grid_stats_page0": gs},
         "parity_counts_ok": None if parity is None else parity["ok"],
         "parity": parity,
         "clocks": clocks,
@@ -414,11 +494,13 @@ def run_b200(args):
                 "ms_per_step": 1e3 * e2e_t / K, "mode": "pipelined: two frames in flight; H2D of step i (upload stream) and D2H of step i-1 (copy stream) overlap the kernels",
                 "sequential_ms_per_step": 1e3 * e2e_seq / K, "sequential_value": N * K / e2e_seq},
         # kernels of this library launched inside the timed `value` region, per frame: k_clear, k_bounds, k_scan, k_scatter,
-        # k_cellsort, k_entboxes, k_pairs_tile, k_pairs (leftover list), k_bin, k_bin_scatter, k_narrow<0>, k_narrow<1>;
+        # k_cellpairs, k_alloc, k_rank, k_place, k_bin, k_bin_scatter, k_narrow<0>, k_narrow<1>;
         # replayed as one CUDA graph per frame once the launch parameters repeat
         "gpu_launches": K * 12,
         "kernels_us": {k: round(v, 2) for k, v in acc.items()},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "note": "kernels_us keys are event segments: pairs = k_cellpairs + k_alloc + k_rank + k_place, narrow = k_bin + k_bin_scatter + k_narrow<0> || k_narrow<1>; "
+                             "ncu: every kernel of the frame is latency-bound (dependent gathers / dependent fp64), none is DRAM-bound (profiles/README.md)",
                      "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_bytes": int(algo[dom]), "peak_source": peak_src,
                      "kernel_fracs": {k: round(algo[k] / (acc[k] * 1e-6) / 1e9 / peak, 4) for k in acc if acc[k] > 0},

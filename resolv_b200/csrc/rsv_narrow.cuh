@@ -484,11 +484,15 @@ __device__ __forceinline__ void narrow_one(const DevView& d, double2* sva, doubl
 
 // One thread per pair. GROUP 0: the convex-convex bins with staged vertices (compiled on their own so that the other
 // pair tests do not inflate this kernel's registers and code). GROUP 1: every other bin.
-// (Tried in round 2 and removed: eight lanes per pair — vertices, edge normals, edge pairs and SAT axes dealt over the
+// (Tried twice in round 2 and removed. Eight lanes per pair — vertices, edge normals, edge pairs and SAT axes dealt over the
 // lanes, `smallest` folded in axis order. Bit-identical, but the sequential tail of a pair (contact sort, fold, sign
 // flips) runs on one lane of eight: 380 warp instructions per pair against 144, and slower on every config —
 // 385 / 158 / 41 us against 125 / 110 / 34 us on configs 2 / 3 / 4; profiles/r2_narrow_coop_unroll_variants.log.
-// Partial unrolling of the vertex / edge loops for more independent fp64 chains: 127 / 114 us at x2, worse at x4.)
+// Partial unrolling of the vertex / edge loops for more independent fp64 chains: 127 / 114 us at x2, worse at x4.
+// Four lanes per pair for the polygon bins above 4 x 4 vertices only, per-axis results in the idle columns of the
+// vertex stage, loops rolled, fold and sort on the first lane (profiles/r3a_narrow_groups.patch): bit-identical
+// again, k_narrow<0> 80 -> 76 us, k_narrow<1> 68 -> 115 us (launch lists profiles/r2z_*, r3a_*); with the per-lane
+// slots in registers the code tripled to 170 KB of SASS and both kernels got slower.)
 template <int GROUP>
 // (the convex-convex instantiation fits 96 registers without spilling: five blocks per SM; the mixed one does not)
 __global__ void __launch_bounds__(kNarrowBlock, GROUP == 0 ? RSV_NARROW_MIN_BLOCKS + 1 : RSV_NARROW_MIN_BLOCKS) k_narrow(DevView d) {

@@ -367,7 +367,9 @@ def run_bench(args, rank, world, local_rank):
             one = space_for_world(whole, device=local_rank)
             cw = one.frame(1, sr.flags, grow=True)
             one.close()
-            want = {k: int(getattr(cw, k)) for k in ("n_testers", "n_candidates", "n_hits", "n_contacts")}
+            # (default frames take the cell-pair path on both sides: n_candidates is not counted there, n_gated — the
+            # Bounds-gated ordered pairs, found exactly once across the strips — is)
+            want = {k: int(getattr(cw, k)) for k in ("n_testers", "n_candidates", "n_gated", "n_hits", "n_contacts")}
             check = {"ok": all(got[k] == want[k] for k in want), "ranks_summed": got, "single_space": want}
             ok[0] = int(check["ok"])
             del whole
