@@ -344,6 +344,9 @@ int32_t rsv_create(const rsv_config* cfg, rsv_space** out) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_narrow<1>, kNarrowBlock, 0) == cudaSuccess && occ > 0)
         s->narrow_blocks1 = s->sm_count * occ;
 
+    // (tuning: blocks per SM of the two narrowphase kernels, which run side by side)
+    if (const char* e = getenv("RSV_NARROW_BLOCKS0")) { const int v = atoi(e); if (v >= 1 && v <= 16) s->narrow_blocks = s->sm_count * v; }
+    if (const char* e = getenv("RSV_NARROW_BLOCKS1")) { const int v = atoi(e); if (v >= 1 && v <= 16) s->narrow_blocks1 = s->sm_count * v; }
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pairs<false>, kPairsBlock, 0) == cudaSuccess && occ > 0)
         s->pairs_blocks[0] = s->sm_count * occ;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pairs<true>, kPairsBlock, 0) == cudaSuccess && occ > 0)
@@ -675,13 +678,13 @@ static int32_t enqueue_frame(rsv_space* s, const DevView& d, int32_t margin, uin
             k_alloc<<<s->sm_count * 8, 256, 0, st>>>(d);
             if (nf) k_rank<false><<<s->sm_count * 8, 256, 0, st>>>(d, margin);
             else k_rank<true><<<s->sm_count * 8, 256, 0, st>>>(d, margin);
-            k_place<<<s->sm_count * 8, 256, 0, st>>>(d);
+            k_place_bin<<<s->sm_count * 8, 256, 0, st>>>(d);   // (place + bin in one pass over the grouped records)
         } else if (flags & RSV_FRAME_NO_TAG_FILTERS) k_pairs<false><<<s->pairs_blocks[0], kPairsBlock, 0, st>>>(d, margin, flags);
         else k_pairs<true><<<s->pairs_blocks[1], kPairsBlock, 0, st>>>(d, margin, flags);
     }
     mark(RSV_K_NARROW);
     if (!grid_only) {
-        k_bin<<<s->sm_count * 8, 256, 0, st>>>(d, cellpairs);
+        if (!cellpairs) k_bin<<<s->sm_count * 8, 256, 0, st>>>(d, false);
         k_bin_scatter<<<s->sm_count * 4, 256, 0, st>>>(d);
         // the two narrowphase kernels touch disjoint records: run them side by side (their tails overlap)
         CU(s, cudaEventRecord(s->ev_fork, st));

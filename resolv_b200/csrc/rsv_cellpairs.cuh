@@ -25,7 +25,8 @@
 //     slot (in-cell order of a freshly built Space is ascending slot, cell.go:21). Only the 0.17 records per tester
 //     pay for a walk, and no in-cell ordering of the entry array is needed (k_cellsort / k_entboxes are skipped; they
 //     run lazily if a LineTest or a grid read-back follows).
-//  4. k_place — orders a tester's records by rank (generation order).
+//  4. k_place_bin (rsv_narrow.cuh) — orders a tester's records by rank (generation order) and bins them for the
+//     narrowphase in the same pass.
 //
 // The frame's outputs (hit records incl. rank, MTV, contacts, tester table) are identical to the walk kernel's;
 // what is not produced is the statistic n_candidates (it needs the full walk: RSV_FRAME_CANDIDATE_WALK) and the
@@ -344,18 +345,7 @@ __global__ void __launch_bounds__(256) k_rank(DevView d, int margin) {
     }
 }
 
-// Generation order within a tester: a record's place is the number of its tester's records with a smaller rank.
-__global__ void __launch_bounds__(256) k_place(DevView d) {
-    if (d.ctr->overflow & RSV_OVF_PAIRS) return;
-    const uint32_t n_rec = min(d.ctr->pair_cursor, d.cap_pairs);
-    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n_rec; g += gridDim.x * blockDim.x) {
-        const uint4 rec = d.pgrp[g];
-        const uint32_t s = d.tester_start[rec.x], n = d.tester_count[rec.x];
-        uint32_t pos = 0;
-        if (n > 1)
-            for (uint32_t q = s; q < s + n; q++) pos += d.pgrp[q].z < rec.z;
-        *reinterpret_cast<uint4*>(d.hits + s + pos) = make_uint4(rec.x, rec.y, 0u, rec.z << 8);
-    }
-}
+// (Generation order within a tester — a record's place is the number of its tester's records with a smaller rank — is
+// established by k_place_bin, rsv_narrow.cuh, together with the narrowphase binning.)
 
 }  // namespace rsv

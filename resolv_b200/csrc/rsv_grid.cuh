@@ -198,7 +198,10 @@ __global__ void __launch_bounds__(kGridBlock) k_clear(unsigned long long* __rest
 // 10 us per frame; this kernel is one latency-bound wave and the extra stores ride along). Tiles take their id from an
 // atomic ticket so a tile only ever waits on tiles that already started.
 constexpr int kScanBlock = 256;
-constexpr int kScanItems = 32;  // per thread, as 8 lane-striped uint4 (every load instruction reads 512 contiguous bytes); 64 -> 32: 25 -> 20 us (513 tiles, 64 registers)
+#ifndef RSV_SCAN_ITEMS
+#define RSV_SCAN_ITEMS 32
+#endif
+constexpr int kScanItems = RSV_SCAN_ITEMS;  // per thread, as 8 lane-striped uint4 (every load instruction reads 512 contiguous bytes); 64 -> 32: 25 -> 20 us (513 tiles, 64 registers)
 constexpr int kScanTile = kScanBlock * kScanItems;
 // Tiles are large on purpose: all tiles of a frame are resident at once, so a tile's look-back finds only
 // aggregates (no finished prefixes) behind it and needs ~tile_index/32 serial rounds; 16 K-item tiles keep that short.

@@ -265,7 +265,49 @@ __device__ __forceinline__ int size_class(uint32_t nv) { return nv <= 4 ? 0 : (n
 //  * computes the record's narrowphase bin (parked in the still unused first_contact field) and counts the bins.
 // A mixed world otherwise diverges four ways per warp, times the spread of polygon sizes: 3 active lanes per warp
 // were measured before binning.
-// pregated: the records come from the cell-pair path, which already applied the exact gate.
+// Narrowphase bin of an ordered pair (see kNarrowBins).
+__device__ __forceinline__ uint32_t narrow_bin_of(const DevView& d, uint32_t A, uint32_t B) {
+    const uint32_t ma = __ldg(d.meta + A), mb = __ldg(d.meta + B);
+    const bool polyA = ma & RSV_META_POLYGON, polyB = mb & RSV_META_POLYGON;
+    const uint32_t na = ma >> RSV_META_NV_SHIFT, nb = mb >> RSV_META_NV_SHIFT;
+    const int kind = (polyA ? 2 : 0) | (polyB ? 1 : 0);
+    if ((polyA && na > kStageVerts) || (polyB && nb > kStageVerts)) return 16 + kind;
+    if (kind == kConvexConvex) return 7 + 3 * size_class(na) + size_class(nb);
+    if (kind == kConvexCircle) return 4 + size_class(na);
+    if (kind == kCircleConvex) return 1 + size_class(nb);
+    return 0;
+}
+
+// Cell-pair frames (rsv_cellpairs.cuh): k_place and k_bin in one pass over the grouped records. A record's place within
+// its tester's group is the number of the group's records with a smaller rank (generation order); the record is
+// written there with its narrowphase bin, and the bins are counted. (The exact Bounds gate was applied by k_cellpairs.)
+__global__ void __launch_bounds__(256) k_place_bin(DevView d) {
+    if (d.ctr->overflow & RSV_OVF_PAIRS) return;
+    const uint32_t n_rec = min(d.ctr->pair_cursor, d.cap_pairs);
+    const int lane = threadIdx.x & 31;
+    __shared__ uint32_t s_cnt[kNarrowBins];
+    if (threadIdx.x < kNarrowBins) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n_rec; base += gridDim.x * blockDim.x) {
+        const uint32_t g = base + threadIdx.x;
+        uint32_t bin = kNoBin;
+        if (g < n_rec) {
+            const uint4 rec = d.pgrp[g];
+            const uint32_t s = d.tester_start[rec.x], n = d.tester_count[rec.x];
+            bin = narrow_bin_of(d, rec.x, rec.y);
+            uint32_t pos = 0;
+            if (n > 1)
+                for (uint32_t q = s; q < s + n; q++) pos += d.pgrp[q].z < rec.z;
+            *reinterpret_cast<uint4*>(d.hits + s + pos) = make_uint4(rec.x, rec.y, bin, rec.z << 8);
+        }
+        const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+        if (bin != kNoBin && lane == __ffs(peers) - 1) atomicAdd(&s_cnt[bin], __popc(peers));
+    }
+    __syncthreads();
+    if (threadIdx.x < kNarrowBins && s_cnt[threadIdx.x]) atomicAdd(&d.ctr->kind_count[threadIdx.x], s_cnt[threadIdx.x]);
+}
+
+// pregated: the records come from a path that already applied the exact gate.
 __global__ void __launch_bounds__(256) k_bin(DevView d, bool pregated) {
     if (d.ctr->overflow & RSV_OVF_PAIRS) return;  // records past the capacity were never written: frame is retried
     const uint32_t n_rec = min(d.ctr->pair_cursor, d.cap_pairs);
@@ -290,15 +332,7 @@ __global__ void __launch_bounds__(256) k_bin(DevView d, bool pregated) {
             if (!gated) {
                 reinterpret_cast<double2*>(d.hits + p)[1] = make_double2(0.0, 0.0);
             } else {
-                const uint32_t ma = __ldg(d.meta + rec.x), mb = __ldg(d.meta + rec.y);
-                const bool polyA = ma & RSV_META_POLYGON, polyB = mb & RSV_META_POLYGON;
-                const uint32_t na = ma >> RSV_META_NV_SHIFT, nb = mb >> RSV_META_NV_SHIFT;
-                const int kind = (polyA ? 2 : 0) | (polyB ? 1 : 0);
-                if ((polyA && na > kStageVerts) || (polyB && nb > kStageVerts)) bin = 16 + kind;
-                else if (kind == kConvexConvex) bin = 7 + 3 * size_class(na) + size_class(nb);
-                else if (kind == kConvexCircle) bin = 4 + size_class(na);
-                else if (kind == kCircleConvex) bin = 1 + size_class(nb);
-                else bin = 0;
+                bin = narrow_bin_of(d, rec.x, rec.y);
             }
             d.hits[p].first_contact = bin;
         }

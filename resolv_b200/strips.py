@@ -406,27 +406,35 @@ def run_bench(args, rank, world, local_rank):
             acc[k] += t[k] / K
     ds.select_pos_page(0)
     # e2e, pipelined like the N = 1 leg: every step each rank uploads the positions of its owned range from a pinned
-    # page, exchanges halos, runs the frame and downloads its results; the download of step i-1 (copy stream)
-    # overlaps the upload + exchange + kernels of step i. Two position sets alternate (pages 0 / 1).
+    # page, exchanges halos, runs the frame and downloads its results; the upload of step i+1 (upload stream) and the
+    # download of step i-1 (copy stream) overlap the exchange + kernels of step i. Two position sets alternate.
     pages = [ds.pos_page(0), ds.pos_page(1)]
     pages[0][2 * n:4 * n] = own0.reshape(-1)
     pages[1][2 * n:4 * n] = (own0 + vel).reshape(-1)
     h2d = d2h = 0
 
+    def upload(i):
+        ds.pos_page_upload(i % 3, i % 2, n, 2 * n)      # (upload stream: overlaps the kernels of the frame in flight)
+
     def launch(i):
-        ds.pos_page_upload(i % 2, i % 2, n, 2 * n)      # (upload stream: overlaps the kernels of the frame in flight)
-        ds.select_pos_page(i % 2)
+        ds.select_pos_page(i % 3)
         sr.step_launch(_abi.FRAME_DOWNLOAD)
 
-    for i in range(4):    # warm this call pattern (graphs of the DOWNLOAD flag set)
+    for i in range(6):    # warm this call pattern (graphs of the DOWNLOAD flag set)
+        upload(i)
         launch(i)
         ds.frame_finish()
     torch.cuda.synchronize()
     dist.barrier()
     t0 = time.perf_counter()
+    upload(0)
     launch(0)
+    if K > 1:
+        upload(1)
     for i in range(1, K):
         launch(i)
+        if i + 1 < K:
+            upload(i + 1)      # three stages at once: upload of step i+1, kernels of step i, download of step i-1
         ce = ds.frame_finish()
         d2h += 32 * int(ce.n_gated) + 32 * int(ce.n_contacts) + 128
     ce = ds.frame_finish()
