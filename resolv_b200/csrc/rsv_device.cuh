@@ -12,6 +12,14 @@ struct alignas(32) Box {  // (minx, miny, maxx, maxy); moved with ONE 256-bit lo
     double minx, miny, maxx, maxy;
 };
 
+// Narrowphase bins (rsv_narrow.cuh): pair kind x EXACT vertex counts of the staged polygons, so that the lanes of a warp
+// run the same pair test with the same loop trip counts.
+//   0        circle-circle
+//   1..8     circle-convex, vertices of the polygon              9..16   convex-circle, vertices of the polygon
+//   17..80   convex-convex, 17 + 8 (nA - 1) + (nB - 1)
+//   80+kind  some polygon has more than kStageVerts (8) vertices (read through L1 instead of the shared-memory stage)
+constexpr int kNarrowBins = 84;
+
 // Device counters of one frame. Cursors are 32-bit (capacities are < 2^32); statistics are 64-bit.
 struct Counters {
     unsigned long long n_testers;
@@ -29,8 +37,8 @@ struct Counters {
     unsigned int n_multi;                  // cells holding two or more entries (k_scan -> k_cellsort / k_cellpairs)
     unsigned int grp_cursor;               // allocation cursor of the per-tester record groups (cell-pair path, k_alloc)
     unsigned int pad_;
-    unsigned int kind_count[20];           // gated records per narrowphase bin (k_bin)
-    unsigned int kind_cursor[20];          // fill cursors of the bins (k_bin_scatter)
+    unsigned int kind_count[kNarrowBins];  // gated records per narrowphase bin (k_bin / k_place_bin)
+    unsigned int kind_cursor[kNarrowBins]; // fill cursors of the bins (k_bin_scatter)
     // line tests
     unsigned int ray_hit_cursor;
     unsigned int ray_contact_cursor;

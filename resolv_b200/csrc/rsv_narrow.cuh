@@ -248,15 +248,14 @@ __device__ __forceinline__ PolyT<STAGED> make_poly(const DevView& d, uint32_t sl
 
 // Pair kinds: bit 1 = tester is a ConvexPolygon, bit 0 = other is a ConvexPolygon (circle.go:69-82, convexPolygon.go:288-300).
 enum { kCircleCircle = 0, kCircleConvex = 1, kConvexCircle = 2, kConvexConvex = 3 };
-// Narrowphase bins: pair kind x vertex-count class of the polygon(s). Within a bin all lanes of a warp run the same
-// pair test with (nearly) the same loop trip counts.
-//   0            circle-circle
-//   1..3         circle-convex, class of the polygon            4..6   convex-circle, class of the polygon
-//   7..15        convex-convex, 7 + 3 * class(A) + class(B)
-//   16 + kind    some polygon has more than kStageVerts vertices (read through L1 instead of the shared-memory stage)
-constexpr int kNarrowBins = 20;
+// Narrowphase bins: kNarrowBins, rsv_device.cuh. (Round 1 binned by vertex-count CLASS, <= 4 / <= 6 / <= 8: a warp of
+// 5-gon and 6-gon pairs ran every lane for 36 edge pairs and 12 axes, 12 of 32 threads active per instruction on the
+// mixed world.)
 constexpr uint32_t kNoBin = 0xffffffffu;
-__device__ __forceinline__ int size_class(uint32_t nv) { return nv <= 4 ? 0 : (nv <= 6 ? 1 : 2); }
+constexpr int kBinUnstaged = 80;   // + kind
+// the staged convex-convex bins by falling nA * nB (processing order of k_narrow<0>: heaviest first)
+__constant__ uint8_t kOrderCC[64] = {80, 79, 72, 71, 78, 64, 70, 63, 77, 56, 62, 69, 55, 76, 48, 61, 54, 68, 47, 53, 75, 60, 46, 40, 67, 39, 52, 45, 59, 38, 74, 44, 32, 51, 37, 66, 31, 58, 43, 36, 30, 50, 29, 35, 73, 42, 28, 24, 65, 23, 57, 34, 27, 22, 49, 21, 41, 26, 20, 33, 19, 25, 18, 17};
+static_assert(kStageVerts == 8 && kNarrowBins == kBinUnstaged + 4, "bin layout");
 
 // Per-record pass in front of the narrowphase, one thread per record:
 //  * the exact float64 Bounds gate (utils.go:146-173) — k_pairs only applied the conservative float32 one; records
@@ -271,10 +270,11 @@ __device__ __forceinline__ uint32_t narrow_bin_of(const DevView& d, uint32_t A, 
     const bool polyA = ma & RSV_META_POLYGON, polyB = mb & RSV_META_POLYGON;
     const uint32_t na = ma >> RSV_META_NV_SHIFT, nb = mb >> RSV_META_NV_SHIFT;
     const int kind = (polyA ? 2 : 0) | (polyB ? 1 : 0);
-    if ((polyA && na > kStageVerts) || (polyB && nb > kStageVerts)) return 16 + kind;
-    if (kind == kConvexConvex) return 7 + 3 * size_class(na) + size_class(nb);
-    if (kind == kConvexCircle) return 4 + size_class(na);
-    if (kind == kCircleConvex) return 1 + size_class(nb);
+    if ((polyA && na > kStageVerts) || (polyB && nb > kStageVerts)) return kBinUnstaged + kind;
+    const uint32_t ca = max(na, 1u) - 1u, cb = max(nb, 1u) - 1u;   // (a polygon without vertices shares the 1-vertex bins)
+    if (kind == kConvexConvex) return 17 + 8 * ca + cb;
+    if (kind == kConvexCircle) return 9 + ca;
+    if (kind == kCircleConvex) return 1 + cb;
     return 0;
 }
 
@@ -348,10 +348,12 @@ __global__ void __launch_bounds__(256) k_bin_scatter(DevView d) {
     if (d.ctr->overflow & RSV_OVF_PAIRS) return;
     __shared__ uint32_t s_off[kNarrowBins];
     __shared__ int s_nonempty;
+    if (threadIdx.x < kNarrowBins) s_off[threadIdx.x] = d.ctr->kind_count[threadIdx.x];
+    __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t run = 0;
         int ne = 0;
-        for (int k = 0; k < kNarrowBins; k++) { s_off[k] = run; run += d.ctr->kind_count[k]; ne += d.ctr->kind_count[k] != 0; }
+        for (int k = 0; k < kNarrowBins; k++) { const uint32_t c = s_off[k]; s_off[k] = run; run += c; ne += c != 0; }
         s_nonempty = ne;
     }
     __syncthreads();
@@ -526,7 +528,9 @@ __device__ __forceinline__ void narrow_one(const DevView& d, double2* sva, doubl
 // Four lanes per pair for the polygon bins above 4 x 4 vertices only, per-axis results in the idle columns of the
 // vertex stage, loops rolled, fold and sort on the first lane (profiles/r3a_narrow_groups.patch): bit-identical
 // again, k_narrow<0> 80 -> 76 us, k_narrow<1> 68 -> 115 us (launch lists profiles/r2z_*, r3a_*); with the per-lane
-// slots in registers the code tripled to 170 KB of SASS and both kernels got slower.)
+// slots in registers the code tripled to 170 KB of SASS and both kernels got slower.
+// A division-free pre-test of every edge pair / polygon line followed by a dense loop over the survivors (so that the
+// IEEE divisions do not diverge inside the full loop): 0.3210 -> 0.3195 ms on config 3, nothing on config 2; not kept.)
 template <int GROUP>
 // (the convex-convex instantiation fits 96 registers without spilling: five blocks per SM; the mixed one does not)
 __global__ void __launch_bounds__(kNarrowBlock, GROUP == 0 ? RSV_NARROW_MIN_BLOCKS + 1 : RSV_NARROW_MIN_BLOCKS) k_narrow(DevView d) {
@@ -537,30 +541,41 @@ __global__ void __launch_bounds__(kNarrowBlock, GROUP == 0 ? RSV_NARROW_MIN_BLOC
     double2* svb = &s_vb[0][threadIdx.x];
     // The bins of this group form one chunk space of 32 records per chunk (a chunk never straddles two bins); warps
     // take chunks round-robin, so every warp runs one pair test with similar trip counts and the load is spread.
-    constexpr int kMaxOrder = 11;
-    __shared__ uint32_t s_off[kMaxOrder], s_cnt[kMaxOrder], s_chunk0[kMaxOrder + 1];
+    constexpr int kMaxOrder = 64;
+    __shared__ uint32_t s_off[kMaxOrder], s_cnt[kMaxOrder], s_chunk0[kMaxOrder + 1], s_kc[kNarrowBins], s_boff[kNarrowBins];
+    __shared__ uint8_t s_bin[kMaxOrder];
     __shared__ int s_n, s_single;
+    if (threadIdx.x < kNarrowBins) s_kc[threadIdx.x] = d.ctr->kind_count[threadIdx.x];
+    __syncthreads();
     if (threadIdx.x == 0) {
-        uint32_t boff[kNarrowBins], off = 0;
+        uint32_t off = 0;
         int ne = 0, only = 0;
         for (int k = 0; k < kNarrowBins; k++) {
-            boff[k] = off; off += d.ctr->kind_count[k];
-            if (d.ctr->kind_count[k]) { ne++; only = k; }
+            s_boff[k] = off; off += s_kc[k];
+            if (s_kc[k]) { ne++; only = k; }
         }
         // a single non-empty bin was not scattered: its "queue" is the record buffer itself (other records: kNoBin)
         s_single = ne == 1 ? only : -1;
-        // processing order: heaviest bins first
-        const int order0[9] = {15, 14, 13, 12, 11, 10, 9, 8, 7};
-        const int order1[11] = {6, 5, 4, 3, 2, 1, 0, 19, 18, 17, 16};
-        const int n = GROUP == 0 ? 9 : 11;
+        // processing order: heaviest bins first. GROUP 0: the staged convex-convex bins by falling nA * nB;
+        // GROUP 1: convex-circle and circle-convex by falling vertex count, circle-circle, the unstaged kinds.
+        const uint32_t pair_cursor = min(d.ctr->pair_cursor, d.cap_pairs);
         uint32_t run = 0;
-        for (int i = 0; i < n; i++) {
-            const int b = GROUP == 0 ? order0[i] : order1[i];
-            s_off[i] = boff[b] | ((uint32_t)b << 27);   // bin id rides in the top bits (queues are < 2^27 records)
-            s_cnt[i] = d.ctr->kind_count[b];
-            if (s_single == b) s_cnt[i] = min(d.ctr->pair_cursor, d.cap_pairs);  // walk every record, skip the others
-            s_chunk0[i] = run;
-            run += (s_cnt[i] + 31) / 32;
+        int n = 0;
+        auto add = [&](int b) {
+            s_off[n] = s_boff[b];
+            s_bin[n] = (uint8_t)b;
+            s_cnt[n] = s_single == b ? pair_cursor : s_kc[b];   // (single bin: walk every record, skip the others)
+            s_chunk0[n] = run;
+            run += (s_cnt[n] + 31) / 32;
+            n++;
+        };
+        if (GROUP == 0) {
+            for (int i = 0; i < 64; i++)
+                if (s_kc[kOrderCC[i]] || s_single == kOrderCC[i]) add(kOrderCC[i]);
+        } else {
+            for (int v = 8; v >= 1; v--) { add(9 + v - 1); add(1 + v - 1); }
+            add(0);
+            add(kBinUnstaged + kConvexConvex); add(kBinUnstaged + kConvexCircle); add(kBinUnstaged + kCircleConvex);
         }
         s_chunk0[n] = run;
         s_n = n;
@@ -574,7 +589,7 @@ __global__ void __launch_bounds__(kNarrowBlock, GROUP == 0 ? RSV_NARROW_MIN_BLOC
         while (c >= s_chunk0[i + 1]) i++;
         const uint32_t idx = (c - s_chunk0[i]) * 32 + lane;
         bool live = idx < s_cnt[i];
-        const uint32_t boff = s_off[i] & 0x7ffffffu;
+        const uint32_t boff = s_off[i];
         uint32_t p = 0;
         if (s_single >= 0) {
             p = idx;
@@ -585,12 +600,12 @@ __global__ void __launch_bounds__(kNarrowBlock, GROUP == 0 ? RSV_NARROW_MIN_BLOC
         if (GROUP == 0) {
             narrow_one<kConvexConvex, true>(d, sva, svb, live, p);
         } else {
-            const int bin = (int)(s_off[i] >> 27);
-            if (bin >= 16) {
-                if (bin == 19) narrow_one<kConvexConvex, false>(d, sva, svb, live, p);
-                else if (bin == 18) narrow_one<kConvexCircle, false>(d, sva, svb, live, p);
-                else if (bin == 17) narrow_one<kCircleConvex, false>(d, sva, svb, live, p);
-            } else if (bin >= 4) narrow_one<kConvexCircle, true>(d, sva, svb, live, p);
+            const int bin = (int)s_bin[i];
+            if (bin >= kBinUnstaged) {
+                if (bin == kBinUnstaged + kConvexConvex) narrow_one<kConvexConvex, false>(d, sva, svb, live, p);
+                else if (bin == kBinUnstaged + kConvexCircle) narrow_one<kConvexCircle, false>(d, sva, svb, live, p);
+                else if (bin == kBinUnstaged + kCircleConvex) narrow_one<kCircleConvex, false>(d, sva, svb, live, p);
+            } else if (bin >= 9) narrow_one<kConvexCircle, true>(d, sva, svb, live, p);
             else if (bin >= 1) narrow_one<kCircleConvex, true>(d, sva, svb, live, p);
             else narrow_one<kCircleCircle, true>(d, sva, svb, live, p);
         }
