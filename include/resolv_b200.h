@@ -92,7 +92,9 @@ typedef struct rsv_counts {
     uint64_t n_shapes;      /* N */
     uint64_t n_testers;
     uint64_t n_entries;     /* R: (cell, shape) registrations == sum of len(cell.Shapes) */
-    uint64_t n_candidates;  /* P: ordered (tester, other) pairs after dedupe + tag filters == pair tests */
+    uint64_t n_candidates;  /* P: ordered (tester, other) pairs after dedupe + tag filters == pair tests. Counted by frames
+                               that run the literal candidate walk (RSV_FRAME_CANDIDATE_WALK, RSV_FRAME_ALL_CANDIDATES,
+                               RSV_FRAME_INCREMENTAL); 0 for the default frame, which never enumerates them */
     uint64_t n_gated;       /* ordered pairs that pass the Bounds gate (utils.go:146-173) */
     uint64_t n_hits;        /* H: ordered pairs with a non-empty IntersectionSet */
     uint64_t n_contacts;    /* K */
@@ -139,7 +141,8 @@ typedef struct rsv_results {
 #define RSV_FRAME_TIMING 0x4u          /* record per-kernel CUDA events; read with rsv_timing */
 #define RSV_FRAME_NO_TAG_FILTERS 0x8u  /* the host asserts that no tester's TestAgainst chain contains ByTags / NotByTags
                                           this frame: RSV_BUF_QMASK / RSV_BUF_TAGS are not read (META_USE_ANY ignored) */
-#define RSV_FRAME_TESTER_TABLE 0x10u   /* also fill the per-tester (first record, record count) table for random access */
+#define RSV_FRAME_TESTER_TABLE 0x10u   /* also fill the per-tester (first record, record count) table for random access
+                                          (default frames always fill it: their records are grouped through it) */
 #define RSV_FRAME_CANDIDATE_WALK 0x80u /* run the reference's literal candidate walk (every tester visits every entry of its
                                           margin-grown cell rect) so that counts.n_candidates is produced. Without it (and
                                           without RSV_FRAME_ALL_CANDIDATES) a frame finds the Bounds-gated pairs cell by cell
