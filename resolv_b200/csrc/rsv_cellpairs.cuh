@@ -41,7 +41,7 @@ constexpr int kCpBlock = 128;
 constexpr int kCpWarps = kCpBlock / 32;
 constexpr int kCpSmall = 6;                                          // cells up to this size are expanded into pair items
 constexpr int kCpQueue = 32 * (kCpSmall * (kCpSmall - 1) / 2) + 64;  // 32 cells' items + a partial double round carried over
-constexpr int kCpStage = 160;                                        // staged records per warp (flushed from 96 on; an emit adds <= 64)
+constexpr int kCpStage = 288;                                        // staged records per warp (flushed from 224 on; an emit adds <= 64)
 
 struct CpWarpSmem {
     uint32_t qs[kCpQueue];    // pair item: first entry of its cell
@@ -291,7 +291,8 @@ __global__ void __launch_bounds__(256) k_rank(DevView d, int margin) {
         uint32_t rank = 0, A = 0, B = 0, idx = 0;
         if (t < n_rec) {
             const uint4 rec = d.ptmp[t];
-            A = rec.x; B = rec.y; idx = rec.z;
+            A = rec.x; B = rec.y;
+            idx = rec.z + d.tester_start[A];   // (requested now, needed at the very end: was 9 % of this kernel's stall samples there)
             const int4 ra = d.crect[A], rb = d.crect[B];
             bool filtered = false, useAny = false;
             ulonglong2 qm = make_ulonglong2(0ull, 0ull);
@@ -339,8 +340,7 @@ __global__ void __launch_bounds__(256) k_rank(DevView d, int margin) {
         rank += __shfl_xor_sync(0xffffffffu, rank, 1);
         rank += __shfl_xor_sync(0xffffffffu, rank, 2);
         if (t < n_rec && sub == 0) {
-            const unsigned long long g = (unsigned long long)d.tester_start[A] + idx;
-            if (g < d.cap_pairs) d.pgrp[g] = make_uint4(A, B, rank, 0u);
+            if (idx < d.cap_pairs) d.pgrp[idx] = make_uint4(A, B, rank, 0u);
         }
     }
 }

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(kScanBlock) k_scan(uint32_t* __restrict__ data
                                                      unsigned long long* __restrict__ state, unsigned int* ticket,
                                                      uint2* __restrict__ multi, unsigned int* n_multi, uint32_t cap_multi,
                                                      const uint32_t* __restrict__ scount) {
-    __shared__ uint32_t s_tile, s_prefix, s_warp[kScanBlock / 32];
+    __shared__ uint32_t s_tile, s_prefix, s_warp[kScanBlock / 32], s_mw[kScanBlock / 32], s_mbase;
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
     const uint32_t tile = s_tile;
@@ -262,10 +262,9 @@ __global__ void __launch_bounds__(kScanBlock) k_scan(uint32_t* __restrict__ data
         uint32_t t = __shfl_up_sync(0xffffffffu, minc, o);
         if (lane >= o) minc += t;
     }
-    uint32_t mbase = 0;
-    const uint32_t mtotal = __shfl_sync(0xffffffffu, minc, 31);
-    if (lane == 31 && mtotal) mbase = atomicAdd(n_multi, mtotal);
-    mbase = __shfl_sync(0xffffffffu, mbase, 31) + (minc - m);
+    // (one allocation per BLOCK, issued by thread 0 behind the first barrier and picked up at the output: a returning
+    // atomic per warp on the one list counter — 4 k of them, each waited for on the spot — was 12 % of this kernel's stalls)
+    if (lane == 31) s_mw[warp] = minc;
     // MERGE: static counts of the same cells, in the same layout (index e: static entries of cell e - 1)
     // (they are read again for the output instead of being kept: 32 registers less, and the second read hits L1/L2)
     const uint4* ssrc = reinterpret_cast<const uint4*>(scount + wbase) + lane;
@@ -294,6 +293,12 @@ __global__ void __launch_bounds__(kScanBlock) k_scan(uint32_t* __restrict__ data
     }
     if (lane == 0) s_warp[warp] = carry;  // warp total
     __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t mt = 0;
+#pragma unroll
+        for (int w = 0; w < kScanBlock / 32; w++) mt += s_mw[w];
+        s_mbase = mt ? atomicAdd(n_multi, mt) : 0u;
+    }
     uint32_t warp_excl = 0, block_sum = 0;
 #pragma unroll
     for (int w = 0; w < kScanBlock / 32; w++) {
@@ -326,6 +331,10 @@ __global__ void __launch_bounds__(kScanBlock) k_scan(uint32_t* __restrict__ data
     }
     __syncthreads();
     const uint32_t pre = s_prefix + warp_excl;
+    uint32_t mbase = s_mbase + (minc - m);
+#pragma unroll
+    for (int w = 0; w < kScanBlock / 32; w++)
+        if (w < warp) mbase += s_mw[w];
     uint4* dst = reinterpret_cast<uint4*>(out + wbase) + lane;
 #pragma unroll
     for (int g = 0; g < kGroups; g++) {
