@@ -9,6 +9,7 @@ import "C"
 
 import (
 	"errors"
+	"sort"
 	"unsafe"
 )
 
@@ -44,7 +45,11 @@ func resultsView(h *C.rsv_space) ([]C.rsv_hit, []C.rsv_contact) {
 	return hits, con
 }
 
-func setFromHit(h *C.rsv_hit, contacts []C.rsv_contact, other IShape) IntersectionSet {
+// setFromHit builds one IntersectionSet from a device record. The device delivers the contacts in the reference's
+// order, except sets of more than 12 contacts of the two kinds the reference sorts (convexConvexTest, shape.go:467-469;
+// convexCircleTest, shape.go:385-387): sort.Slice is pdqsort there, whose result depends on its input order, so those
+// arrive in generation order and are sorted here, by the very call the reference makes.
+func setFromHit(h *C.rsv_hit, contacts []C.rsv_contact, tester, other IShape) IntersectionSet {
 	set := IntersectionSet{}
 	n := int(h.count_rank & 0x7f)
 	if n == 0 {
@@ -56,6 +61,15 @@ func setFromHit(h *C.rsv_hit, contacts []C.rsv_contact, other IShape) Intersecti
 		set.Intersections = append(set.Intersections, Intersection{
 			Point:  Vector{float64(c.px), float64(c.py)},
 			Normal: Vector{float64(c.nx), float64(c.ny)},
+		})
+	}
+	if cp, ok := tester.(*ConvexPolygon); ok && n > 12 {
+		center := cp.Center()
+		if c, isCircle := other.(*Circle); isCircle {
+			center = c.Position()
+		}
+		sort.Slice(set.Intersections, func(i, j int) bool {
+			return set.Intersections[i].Point.DistanceSquared(center) < set.Intersections[j].Point.DistanceSquared(center)
 		})
 	}
 	return set

@@ -127,7 +127,7 @@ func (s *ShapeBase) IntersectionTest(settings IntersectionTestSettings) bool {
 			}
 			p := possibleIntersection{Shape: other, Distance: other.DistanceSquaredTo(s.owner), known: own}
 			if own {
-				p.set = setFromHit(h, contacts, other)
+				p.set = setFromHit(h, contacts, s.owner, other)
 			}
 			list = append(list, p)
 		}

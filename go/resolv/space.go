@@ -314,7 +314,7 @@ func (s *Space) testPairs(pairs [][2]IShape) []IntersectionSet {
 	hits, contacts := resultsView(s.h)
 	for k := range pairs {
 		if k < len(hits) {
-			out[k] = setFromHit(&hits[k], contacts, pairs[k][1])
+			out[k] = setFromHit(&hits[k], contacts, pairs[k][0], pairs[k][1])
 		}
 	}
 	return out

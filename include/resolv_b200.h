@@ -121,7 +121,11 @@ typedef struct rsv_hit {
     double mtv_x, mtv_y;    /* IntersectionSet.MTV */
 } rsv_hit;
 
-/* Replaces Intersection (contactSet.go:8-11). */
+/* Replaces Intersection (contactSet.go:8-11). A set's contacts are in the reference's order: sorted by squared distance
+ * to the tester's Center (convex-convex, shape.go:467-469) / to the circle's position (convex-circle, shape.go:385-387),
+ * unsorted for circle-convex and circle-circle. EXCEPT sets of MORE THAN 12 contacts of the two sorted kinds: for those
+ * sort.Slice is Go's pdqsort_func, whose result depends on its input order, and the device delivers that input — the
+ * generation order — for the host to sort (go/resolv: sort.Slice itself; csrc/host/resolv.hpp: its port GoSortSlice). */
 typedef struct rsv_contact {
     double px, py; /* Point */
     double nx, ny; /* Normal */

@@ -510,19 +510,10 @@ private:
         stale_ = true;
         rsv_results r{};
         rsv_results_view(h_, &r);
-        for (size_t k = 0; k < pairs.size() && k < r.n_hit_records; k++) fillSet(out[k], r.hits[k], r.contacts, pairs[k].second);
+        for (size_t k = 0; k < pairs.size() && k < r.n_hit_records; k++) fillSet(out[k], r.hits[k], r.contacts, pairs[k].first, pairs[k].second);
         return out;
     }
-    static void fillSet(IntersectionSet& set, const rsv_hit& h, const rsv_contact* contacts, Shape* other) {
-        const uint32_t n = h.count_rank & 0x7f;
-        if (n == 0) return;
-        set.OtherShape = other;
-        set.MTV = {h.mtv_x, h.mtv_y};
-        for (uint32_t i = 0; i < n; i++) {
-            const rsv_contact& q = contacts[h.first_contact + i];
-            set.Intersections.push_back({{q.px, q.py}, {q.nx, q.ny}});
-        }
-    }
+    static void fillSet(IntersectionSet& set, const rsv_hit& h, const rsv_contact* contacts, Shape* tester, Shape* other);
     void writeRow(Shape* s, bool isNew) {
         uint32_t i = s->slot_;
         pos_[2 * i] = s->pos_.X; pos_[2 * i + 1] = s->pos_.Y;
@@ -564,6 +555,29 @@ private:
     rsv_counts counts_{};
 };
 
+// One IntersectionSet from a device record. The device sorts the contacts of a set as the reference does — except sets
+// of more than 12 contacts of the two kinds the reference sorts (convexConvexTest by distance to the tester's Center,
+// shape.go:467-469; convexCircleTest by distance to the circle, shape.go:385-387): sort.Slice is pdqsort_func there, so
+// they arrive in generation order and are sorted here with the port of Go's sort.
+inline void Space::fillSet(IntersectionSet& set, const rsv_hit& h, const rsv_contact* contacts, Shape* tester, Shape* other) {
+    const uint32_t n = h.count_rank & 0x7f;
+    if (n == 0) return;
+    set.OtherShape = other;
+    set.MTV = {h.mtv_x, h.mtv_y};
+    for (uint32_t i = 0; i < n; i++) {
+        const rsv_contact& q = contacts[h.first_contact + i];
+        set.Intersections.push_back({{q.px, q.py}, {q.nx, q.ny}});
+    }
+    if (n > 12 && tester && !tester->IsCircle()) {
+        Vector c = other->pos_;                                   // convexCircleTest: circle.position
+        if (!other->IsCircle()) {                                 // convexConvexTest: convexA.Center() == Bounds().Center()
+            const Bounds b = tester->GetBounds();
+            c = {b.Min.X + (b.Max.X - b.Min.X) * 0.5, b.Min.Y + (b.Max.Y - b.Min.Y) * 0.5};
+        }
+        detail::GoSortSlice(set.Intersections, [&](const Intersection& k) { return k.Point.DistanceSquared(c); });
+    }
+}
+
 inline void Shape::update() { if (space_) space_->markDirty(this); }
 inline void Shape::updatePosition() { if (space_) space_->markMoved(this); }
 
@@ -592,7 +606,7 @@ inline bool Shape::IntersectionTest(const IntersectionTestSettings& st) {
             Shape* other = sp.shapes_[h.b];
             if (other == this || !ta.Accepts(*other)) continue;
             Cand c{other->pos_.DistanceSquared(pos_), other, own, {}};   // shape.go:179-181
-            if (own) Space::fillSet(c.set, h, sp.res_.contacts, other);   // copied out: callbacks may invalidate the views
+            if (own) Space::fillSet(c.set, h, sp.res_.contacts, this, other);   // copied out: callbacks may invalidate the views
             list.push_back(std::move(c));
         }
         if (own) validEpoch = sp.frameEpoch_;

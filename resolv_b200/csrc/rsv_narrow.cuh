@@ -188,8 +188,12 @@ __device__ __forceinline__ bool mtv_poly_circle(const Poly& cp, V2 centerCp, V2 
 }
 
 // Stable insertion sort of contacts by squared distance to `c` (sort.Slice with n <= 12 is an insertion sort;
-// shape.go:385-387, 467-469).
+// shape.go:385-387, 467-469). Beyond 12 items sort.Slice is Go's pdqsort_func — unstable, its result depends on the
+// input order — which the host layers run (csrc/host/resolv.hpp: GoSortSlice; the Go package calls sort.Slice itself):
+// such sets are delivered in GENERATION order, the input the reference's sort sees (include/resolv_b200.h: rsv_contact).
+constexpr int kInsertionSortMax = 12;
 __device__ __forceinline__ void sort_contacts(rsv_contact* a, int n, V2 c) {
+    if (n > kInsertionSortMax) return;
     for (int i = 1; i < n; i++) {
         rsv_contact key = a[i];
         double kd = vdist2(V2{key.px, key.py}, c);

@@ -125,3 +125,30 @@ def test_linetest_and_cell_readback_after_a_default_frame_see_the_full_grid():
         assert device_cells(ds, c.n_entries) == ob.cells()
     finally:
         ds.close()
+
+
+def test_sets_of_more_than_twelve_contacts_are_sorted_by_the_host_with_gos_sort():
+    """sort.Slice on more than 12 items is Go's pdqsort_func: unstable, its result depends on the input order. The device
+    delivers such sets in generation order (the input the reference's sort sees) and the host layer sorts them with its
+    port of Go's sort; compare_frame plays the host with the oracle's restatement of that sort — so the contact ORDER is
+    compared exactly, not as a multiset. Octagons cut by a circle (16 points, all at distance r from the circle: every
+    key ties) and by a rotated octagon (16 points at the same distance from the centre)."""
+    def ngon(n, r, phase):
+        t = phase + 2 * np.pi * np.arange(n) / n
+        return np.stack([r * np.cos(t), r * np.sin(t)], -1)
+
+    rows = [dict(kind=1, pos=(100.0, 100.0), radius=0.0, verts=ngon(8, 20.0, 0.0), tags=1),
+            dict(kind=0, pos=(100.0, 100.0), radius=19.2, tags=1),
+            dict(kind=1, pos=(300.0, 200.0), radius=0.0, verts=ngon(8, 30.0, 0.0), tags=1),
+            dict(kind=1, pos=(300.0, 200.0), radius=0.0, verts=ngon(8, 30.0, np.pi / 8), tags=1),
+            dict(kind=1, pos=(500.5, 300.25), radius=0.0, verts=ngon(7, 25.0, 0.3), tags=1),
+            dict(kind=0, pos=(501.0, 300.0), radius=23.5, tags=1)]
+    w = worlds._from_rows(rows, (640, 480), (32, 32), "many_contacts").finalize()
+    ob = OracleBatch(w)
+    ds = space_for_world(w)
+    try:
+        c, exact = compare_frame(ds, ob, 1)
+        hits, _ = ds.results()
+        assert exact and int((hits["count_rank"] & 0x7f).max()) > 12
+    finally:
+        ds.close()

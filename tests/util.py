@@ -68,8 +68,13 @@ def bits(a):
     return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
 
 
-def _check_results(c, hits, con, tot, oh):
-    """Hit set bit-exact, contact counts equal, MTV / contacts within 1e-9; returns whether they are bit-identical."""
+def _check_results(c, hits, con, tot, oh, w=None):
+    """Hit set bit-exact, contact counts equal, MTV / contacts within 1e-9; returns whether they are bit-identical.
+
+    Contacts: sets of at most 12 points arrive sorted as the reference sorts them. Beyond 12, sort.Slice is Go's
+    pdqsort_func, which the HOST layers run on the device's generation-order output (include/resolv_b200.h: rsv_contact);
+    here the oracle's restatement of that sort (oracle.go_sort) plays the host, so the comparison is exact for those too."""
+    from oracle.oracle import go_sort
     n = hits["count_rank"] & 0x7f
     live = n > 0
     assert c.n_testers == tot["testers"]
@@ -85,15 +90,34 @@ def _check_results(c, hits, con, tot, oh):
     dm = dh["mtv"][do]
     om = oh["mtv"][oo]
     assert np.all(np.abs(dm - om) <= 1e-9), "MTV beyond 1e-9"
-    def canon(rows):
-        # DESIGN.md §5 deviation 2: beyond 12 items sort.Slice is an unstable pdqsort, so the order of contacts with
-        # EXACTLY equal sort keys (e.g. 14 points on one circle, all at distance r from its centre) is not defined by
-        # the reference's source; such sets are compared as multisets.
-        return rows[np.lexsort(rows.T[::-1])] if len(rows) > 12 else rows
+    la = None if w is None else np.asarray(w.local_aabb, dtype=np.float64).reshape(-1, 4)
 
-    dcon = np.concatenate([canon(np.concatenate([con["p"][f:f + k], con["n"][f:f + k]], -1))
-                           for f, k in zip(dh["first_contact"][do], dn[do])]) if len(do) else np.zeros((0, 4))
-    ocon = np.concatenate([canon(oh["contacts"][f:f + k]) for f, k in zip(oh["first"][oo], oh["count"][oo])]) if len(oo) else np.zeros((0, 4))
+    def host_sort(rows, a, b):
+        """What the host layer does with a device set of more than 12 contacts (csrc/host/resolv.hpp: Space::fillSet)."""
+        if len(rows) <= 12 or w is None:
+            return rows
+        if w.kind[a] == 0:
+            return rows                                  # circleConvexTest / circleCircleTest do not sort
+        if w.kind[b] == 0:
+            cx, cy = w.pos[b]                            # convexCircleTest: by distance to circle.position
+        else:                                            # convexConvexTest: by distance to convexA.Center()
+            mnx, mny, mxx, mxy = la[a, 0] + w.pos[a, 0], la[a, 1] + w.pos[a, 1], la[a, 2] + w.pos[a, 0], la[a, 3] + w.pos[a, 1]
+            cx, cy = mnx + (mxx - mnx) * 0.5, mny + (mxy - mny) * 0.5
+        dx, dy = rows[:, 0] - cx, rows[:, 1] - cy
+        return rows[go_sort(dx * dx + dy * dy)]
+
+    dcon = np.concatenate([host_sort(np.concatenate([con["p"][f:f + k], con["n"][f:f + k]], -1), a, b)
+                           for f, k, a, b in zip(dh["first_contact"][do], dn[do], dh["a"][do], dh["b"][do])]) if len(do) else np.zeros((0, 4))
+    ocon = np.concatenate([oh["contacts"][f:f + k] for f, k in zip(oh["first"][oo], oh["count"][oo])]) if len(oo) else np.zeros((0, 4))
+    if w is None:   # no world at hand: sets beyond 12 points can only be compared as multisets
+        def canon(rows, counts):
+            out, at = [], 0
+            for k in counts:
+                r = rows[at:at + k]
+                out.append(r[np.lexsort(r.T[::-1])] if k > 12 else r)
+                at += k
+            return np.concatenate(out) if out else rows
+        dcon, ocon = canon(dcon, dn[do]), canon(ocon, oh["count"][oo])
     same_nan = np.isnan(dcon) == np.isnan(ocon)
     assert same_nan.all()
     assert np.all((np.abs(dcon - ocon) <= 1e-9) | np.isnan(ocon)), "contacts beyond 1e-9"
@@ -142,7 +166,7 @@ def compare_frame(ds, ob, margin, check_candidates=True, check_rank=True, extra_
         dev = dev[np.lexsort((dev[:, 1], dev[:, 0]))]
         ora = ora[np.lexsort((ora[:, 1], ora[:, 0]))]
         assert dev.shape == ora.shape and np.array_equal(dev, ora), "candidate set / generation rank mismatch"
-        exact &= _check_results(c, hits, con, tot, oh)
+        exact &= _check_results(c, hits, con, tot, oh, ob.w)
         gated_ref = _records(hits)
         gated_ref = gated_ref[np.lexsort((gated_ref[:, 1], gated_ref[:, 0]))]
         c_all = c
@@ -150,14 +174,14 @@ def compare_frame(ds, ob, margin, check_candidates=True, check_rank=True, extra_
         c = ds.frame(margin, _abi.FRAME_DOWNLOAD | _abi.FRAME_CANDIDATE_WALK | extra_flags, grow=True)
         hits, con = ds.results()
         assert c.n_candidates == tot["candidates"], (c.n_candidates, tot["candidates"])
-        exact &= _check_results(c, hits, con, tot, oh)
+        exact &= _check_results(c, hits, con, tot, oh, ob.w)
         rec = _records(hits)
         _check_grouping(rec)
         assert np.array_equal(rec[np.lexsort((rec[:, 1], rec[:, 0]))], gated_ref), "walk records != gated candidates of the dump"
     # the default frame
     c = ds.frame(margin, _abi.FRAME_DOWNLOAD | extra_flags, grow=True)
     hits, con = ds.results()
-    exact &= _check_results(c, hits, con, tot, oh)
+    exact &= _check_results(c, hits, con, tot, oh, ob.w)
     rec = _records(hits, gated_only=False)
     _check_grouping(rec)
     srt = rec[np.lexsort((rec[:, 1], rec[:, 0]))]
