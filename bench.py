@@ -502,9 +502,9 @@ def run_b200(args):
                 "ms_per_step": 1e3 * e2e_t / K, "mode": "pipelined: H2D of step i+1 (upload stream), kernels of step i and D2H of step i-1 (copy stream) run concurrently",
                 "sequential_ms_per_step": 1e3 * e2e_seq / K, "sequential_value": N * K / e2e_seq},
         # kernels of this library launched inside the timed `value` region, per frame: k_clear, k_bounds, k_scan, k_scatter,
-        # k_cellpairs, k_alloc, k_rank, k_place, k_bin, k_bin_scatter, k_narrow<0>, k_narrow<1>;
+        # k_cellpairs, k_alloc, k_rank, k_place_bin, k_bin_scatter, k_narrow<0>, k_narrow<1> (11);
         # replayed as one CUDA graph per frame once the launch parameters repeat
-        "gpu_launches": K * 12,
+        "gpu_launches": K * 11,
         "kernels_us": {k: round(v, 2) for k, v in acc.items()},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "note": "kernels_us keys are event segments: pairs = k_cellpairs + k_alloc + k_rank + k_place, narrow = k_bin + k_bin_scatter + k_narrow<0> || k_narrow<1>; "
