@@ -58,6 +58,7 @@ struct rsv_space {
         uint32_t flags = 0;
         bool pending = false;
         bool cellpairs = false;     // the frame took the cell-pair path (tester table always filled, n_candidates not counted)
+        bool pair_list = false;     // rsv_test_pairs, not a frame
     } slot[2];
     int launch_slot = 0, finish_slot = 0, last_slot = 0;
     // captured launch sequence of a frame, one per result slot (frame_via_graph)
@@ -97,7 +98,7 @@ struct rsv_space {
     int narrow_blocks1 = 148 * 4;
     int narrow_order = 1;           // 1: submit k_narrow<0> before k_narrow<1> (RSV_NARROW_ORDER=0: the other way round)
     int narrow_blocks0_fixed = 0;   // RSV_NARROW_BLOCKS0 given: no adaptive grid for k_narrow<0>
-    uint32_t last_cc_chunks = 0xffffffffu;   // 32-record chunks of the staged convex-convex bins in the last finished frame
+    int narrow_per_sm = 0;          // blocks per SM of k_narrow<0> chosen from the last finished frames (0: not known yet)
     int pairs_blocks[2] = {148 * 8, 148 * 8};  // k_pairs<false> (no tag filters), k_pairs<true>
     // peer-memory halo transport (rsv_halo_abi.inl)
     void* mailbox = nullptr;            // this device's mailbox
@@ -609,12 +610,18 @@ int32_t rsv_sync(rsv_space* s) {
 // k_narrow<1> finds free registers next to it (measured on one box, blocks per SM of k_narrow<0> = 2 / 3 / 4 / 5:
 // config 3 0.288 / 0.286 / 0.287 / 0.296 ms, config 2 0.384 / 0.335 / 0.308 / 0.298 ms).
 static inline int narrow_grid0(const rsv_space* s) {
-    if (s->narrow_blocks0_fixed || s->last_cc_chunks == 0xffffffffu) return s->narrow_blocks;
-    const uint32_t warps_per_block = kNarrowBlock / 32;
-    // (up to two chunks per resident warp still count as "one wave of long chains": config 3 has 2.4 k chunks)
-    const int per_sm = s->last_cc_chunks > 2u * (uint32_t)s->sm_count * 4u * warps_per_block ? s->narrow_blocks / s->sm_count
-                       : (s->last_cc_chunks > 2u * (uint32_t)s->sm_count * 3u * warps_per_block ? 4 : 3);
-    return s->sm_count * std::min(per_sm, s->narrow_blocks / s->sm_count);
+    if (s->narrow_blocks0_fixed || s->narrow_per_sm == 0) return s->narrow_blocks;
+    return s->sm_count * std::min(s->narrow_per_sm, s->narrow_blocks / s->sm_count);
+}
+// Called with the bin counts of a finished frame. Up to two chunks per resident warp still count as "one wave of long
+// chains" (config 3 has ~4 k chunks of convex-convex pairs). A count within 12 % of a threshold keeps the current choice:
+// the grid is part of the frame graph's key, and a world sitting on a threshold must not re-capture it every frame.
+static inline void narrow_grid0_update(rsv_space* s, uint32_t cc_chunks) {
+    const double w4 = 2.0 * s->sm_count * 4 * (kNarrowBlock / 32), w3 = 2.0 * s->sm_count * 3 * (kNarrowBlock / 32);
+    const int occ = std::max(s->narrow_blocks / s->sm_count, 1);
+    auto cls = [&](double f) { return cc_chunks > f * w4 ? occ : (cc_chunks > f * w3 ? 4 : 3); };
+    const int lo = cls(1.12), hi = cls(0.88);   // the class with the thresholds moved up / down
+    if (lo == hi || s->narrow_per_sm == 0 || (s->narrow_per_sm != lo && s->narrow_per_sm != hi)) s->narrow_per_sm = lo == hi ? lo : cls(1.0);
 }
 
 // Which candidate path a frame takes (see rsv_cellpairs.cuh).
@@ -880,6 +887,7 @@ int32_t rsv_frame_launch(rsv_space* s, int32_t margin, uint32_t flags) {
     sl.pending = true;
     s->launch_slot ^= 1;
     sl.cellpairs = cell_pair_frame(flags, inc);
+    sl.pair_list = false;
     s->grid_complete = !sl.cellpairs;
     return RSV_OK;
 }
@@ -915,7 +923,7 @@ int32_t rsv_frame_finish(rsv_space* s, rsv_counts* out) {
     {
         uint32_t chunks = 0;
         for (int b = 17; b < 81; b++) chunks += (c.kind_count[b] + 31u) / 32u;
-        s->last_cc_chunks = chunks;
+        if (!sl.pair_list) narrow_grid0_update(s, chunks);   // (a pair list says nothing about the next frame's narrowphase)
     }
     rsv_counts rc{};
     rc.n_shapes = s->d.n_shapes;
@@ -1045,10 +1053,9 @@ int32_t rsv_test_pairs(rsv_space* s, uint32_t n_pairs, rsv_counts* out) {
     sl.flags = RSV_FRAME_DOWNLOAD;
     sl.pending = true;
     sl.cellpairs = false;
+    sl.pair_list = true;
     s->launch_slot ^= 1;
-    const uint32_t keep_chunks = s->last_cc_chunks;   // (a pair list says nothing about the next frame's narrowphase grid)
     const int32_t rc = rsv_frame_finish(s, out);
-    s->last_cc_chunks = keep_chunks;
     if (out) { out->n_testers = 0; out->n_entries = 0; out->n_candidates = n_pairs; }
     return rc;
 }

@@ -264,6 +264,7 @@ int32_t rsv_strip_frame_launch(rsv_space* s, int32_t margin, uint32_t flags, int
     sl.flags = flags;
     sl.pending = true;
     sl.cellpairs = cell_pair_frame(flags, false);
+    sl.pair_list = false;
     s->grid_complete = !sl.cellpairs;
     s->launch_slot ^= 1;
     return RSV_OK;
