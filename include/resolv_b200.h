@@ -215,7 +215,12 @@ void* rsv_device_buffer(rsv_space* s, int32_t which);
  *       [.ByTags(any)][.NotByTags(none)], OnIntersect: <record>})                  (shape.go:220-237, 273-316)
  * against the frozen world: grid rebuild (shape.go:183-214, cell.go:19-38) -> candidate pairs (cell.go:86-121,
  * shapefilter.go:26-61) -> Bounds gate + SAT narrowphase (shape.go:318-479, convexPolygon.go:418-514,715-789).
- * OnIntersect is replayed by the host from rsv_results. */
+ * OnIntersect is replayed by the host from rsv_results.
+ * The records — one per ordered pair that passes the Bounds gate, with its index in possibleIntersections, contacts and
+ * MTV, grouped by tester in generation order — do not depend on HOW the candidates are found: frames with
+ * RSV_FRAME_ALL_CANDIDATES / RSV_FRAME_CANDIDATE_WALK (and incremental frames) run the reference's walk over every
+ * tester's margin-grown cell rect; every other frame finds the gated pairs among the entries of one cell and derives
+ * their indices afterwards (csrc/rsv_cellpairs.cuh): identical records, no candidate count, about 30 % less time. */
 int32_t rsv_frame(rsv_space* s, int32_t margin, uint32_t flags, rsv_counts* out);
 /* The same frame split in two so that a host can queue work without blocking: rsv_frame_launch enqueues every
  * kernel on the space's stream and returns; rsv_frame_finish waits for the OLDEST launched frame, fills the counters
