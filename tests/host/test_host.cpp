@@ -149,5 +149,17 @@ int main() {
             printf("LQR %d %d\n", variant, (int)static_cast<ConvexPolygon*>(player)->ShapeLineTest(sl));
         }
     }
+    // 11. one IntersectionSet of more than 12 contacts: a circle cuts every edge of an octagon twice (16 points, all at
+    // distance r from the circle: every sort key ties). sort.Slice is pdqsort beyond 12 items, so the device delivers the
+    // set in generation order and Space::fillSet sorts it with the port of Go's sort.
+    {
+        Shape* oct = add(NewConvexPolygon(500, 40, {20, 0, 14, 14, 0, 20, -14, 14, -20, 0, -14, -14, 0, -20, 14, -14}), Player);
+        add(NewCircle(500, 40, 19), Platform);
+        auto near = oct->SelectTouchingCells(1).ByTags(Platform);
+        IntersectionTestSettings st;
+        st.TestAgainst = &near;
+        st.OnIntersect = [&](const IntersectionSet& set) { print_set("MC", 0, set); return true; };
+        oct->IntersectionTest(st);
+    }
     return 0;
 }

@@ -190,3 +190,12 @@ def test_host_layer_moves_whole_space_filters_and_go_sort(tmp_path):
     _same([(r[1], r[2], r[3][:2] + [0.0, 0.0] + r[3][4:]) for r in lq(2)], [(o[0], o[1], o[2]) for o in ora], "LQ all lines")
     lqr = {r[1][0]: r[1][1] for r in recs if r[0] == "LQR"}
     assert lqr == {0: 0, 1: 0, 2: 1} and len(ora) >= 1
+    # 11. a set of 16 contacts with sixteen equal sort keys: the host layer's port of Go's sort must leave them in the
+    # oracle's order (the device delivers sets of more than 12 contacts in generation order)
+    octagon = sp.add_polygon(500, 40, [20, 0, 14, 14, 0, 20, -14, 14, -20, 0, -14, -14, 0, -20, 14, -14], True, PLAYER)
+    sp.add_circle(500, 40, 19, PLATFORM)
+    n = sp.num_shapes
+    fc, cands, hits = sp.frame(1, tester=only(octagon), use_any=np.ones(n, np.uint8), any_mask=np.full(n, PLATFORM, np.uint64))
+    ora = _sets(hits, hits.a == octagon)
+    assert len(ora) == 1 and ora[0][1] == 16
+    _same([(r[2], r[3], r[4]) for r in recs if r[0] == "MC"], ora, "MC")
